@@ -1,0 +1,219 @@
+/*
+ * ukf_batch.h -- C ABI of the B200-native batched unscented Kalman filter engine.
+ *
+ * Drop-in boundary for the predict/update hot path of rock-slam/slam-pose_estimation.
+ * One handle owns B independent filters of one kind (PoseUKF or OrientationUKF) on
+ * ONE CUDA device; filter b of the batch behaves exactly like one instance of the
+ * reference class.  Every entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The reference is a C++
+ * class API with no FFI of its own; `include/pose_estimation_b200/*.hpp` re-creates
+ * those classes (same names, arguments and exceptions) on top of this ABI, and
+ * INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are caller-owned, dense, row-major,
+ *     IEEE double unless stated; nothing is retained after a call returns.
+ *   - functions without a suffix take HOST pointers and copy inside the call;
+ *     the `_dev` variants take DEVICE pointers (same layout) and only enqueue work
+ *     on the handle's stream.
+ *   - mu layout (quaternion stored x,y,z,w as Eigen does):
+ *       POSE        13: p[0:3] q[3:7] v[7:10] w[10:13]   (PoseWithVelocity.hpp:18-23)
+ *       ORIENTATION 14: q[0:4] v[4:7] bg[7:10] ba[10:13] g[13]  (OrientationState.hpp:20-26)
+ *     covariance: n x n with n = 12 / 13, tangent order as in ukfb_constants.h.
+ *     The engine stores the lower triangle (the covariance is symmetric up to
+ *     rounding in the reference; Cholesky 'L' reads only that triangle anyway).
+ *   - return value: 0 = ok, < 0 = UKFB_ERR_*; ukfb_last_error() gives text.
+ *   - the reference throws std::runtime_error for a negative / too large time
+ *     delta (UnscentedKalmanFilter.hpp:110-122) and for a non-finite measurement
+ *     (:142-147).  A batch cannot throw per filter: the operation is skipped for
+ *     that filter exactly as the throw would have skipped it, and a sticky
+ *     per-filter status bit UKFB_STATUS_* is set.  The C++ shim re-throws.
+ *   - a handle is single-caller (the reference is not thread-safe either,
+ *     UnscentedKalmanFilter.hpp:16); different handles are independent.
+ *   - there is no CPU fallback: every entry point fails with UKFB_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef UKF_BATCH_H
+#define UKF_BATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ukfb_handle ukfb_handle;
+
+/* filter kinds */
+#define UKFB_POSE 0        /* pose_estimation::PoseUKF         (PoseUKF.hpp:17-93)        */
+#define UKFB_ORIENTATION 1 /* pose_estimation::OrientationUKF  (OrientationUKF.hpp:20-59) */
+
+/* measurement kinds: one per integrateMeasurement overload that calls ukf->update */
+#define UKFB_MEAS_NONE (-1)
+#define UKFB_MEAS_POSE_POSITION 0         /* PositionMeasurement        m=3  PoseUKF.cpp:112-117 */
+#define UKFB_MEAS_POSE_XY 1               /* XYMeasurement              m=2  PoseUKF.cpp:119-124 */
+#define UKFB_MEAS_POSE_Z 2                /* ZMeasurement               m=1  PoseUKF.cpp:126-131 */
+#define UKFB_MEAS_POSE_ORIENTATION 3      /* OrientationMeasurement     SO3  PoseUKF.cpp:133-138 */
+#define UKFB_MEAS_POSE_VELOCITY 4         /* VelocityMeasurement        m=3  PoseUKF.cpp:140-145 */
+#define UKFB_MEAS_POSE_XY_VELOCITY 5      /* XYVelocityMeasurement      m=2  PoseUKF.cpp:147-152 */
+#define UKFB_MEAS_POSE_Z_VELOCITY 6       /* ZVelocityMeasurement       m=1  PoseUKF.cpp:154-159 */
+#define UKFB_MEAS_POSE_XVEL_YAWVEL 7      /* XVelYawVelMeasurement      m=2  PoseUKF.cpp:161-166 */
+#define UKFB_MEAS_POSE_ANGULAR_VELOCITY 8 /* AngularVelocityMeasurement m=3  PoseUKF.cpp:168-173 */
+#define UKFB_MEAS_ORI_VELOCITY 9          /* OrientationUKF::VelocityMeasurement m=3  OrientationUKF.cpp:65-72 */
+#define UKFB_MEAS_KIND_COUNT 10
+
+/* sticky per-filter status bits */
+#define UKFB_STATUS_NEG_DT 1u            /* "Delta time is negative!"                          :110-113 */
+#define UKFB_STATUS_DT_TOO_LARGE 2u      /* "Delta time is greater then the allowed maximum!"  :119-122 */
+#define UKFB_STATUS_NONFINITE_MEAS 4u    /* "Measurement or covariance contains non-finite values!" :142-147 */
+#define UKFB_STATUS_NOT_SPD 8u           /* ukfom: Cholesky of sigma failed (MTK asserts)               */
+#define UKFB_STATUS_MEAN_NO_CONVERGE 16u /* ukfom: sigma_points_mean hit max_it (MTK asserts)           */
+
+/* error codes */
+#define UKFB_OK 0
+#define UKFB_ERR_INVALID (-1)         /* bad argument / wrong filter kind for this call */
+#define UKFB_ERR_NOT_INITIALIZED (-2) /* getCurrentState() == false, UnscentedKalmanFilter.hpp:51-60 */
+#define UKFB_ERR_CUDA (-3)            /* CUDA runtime error or no usable device */
+#define UKFB_ERR_NOMEM (-4)
+
+/* Text of the last error on the calling thread. */
+const char* ukfb_last_error(void);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Constructors PoseUKF::PoseUKF (PoseUKF.cpp:99-110) / OrientationUKF::OrientationUKF
+ * (OrientationUKF.cpp:41-51) minus their initializeFilter call (see ukfb_initialize):
+ * base defaults Q = 0, t_last = 0, min_dt = 1e-9, max_dt = DBL_MAX
+ * (UnscentedKalmanFilter.hpp:27-33); POSE: default diagonal Q and acceleration = NaN;
+ * ORIENTATION: tau = +inf, latitude = 0 until ukfb_set_orientation_params. */
+int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_handle** out);
+int ukfb_destroy(ukfb_handle* h);
+
+int64_t ukfb_batch(const ukfb_handle* h);
+int ukfb_dof(const ukfb_handle* h);     /* getStateSize(), UnscentedKalmanFilter.hpp:127 */
+int ukfb_mu_size(const ukfb_handle* h); /* 13 / 14 */
+int ukfb_device(const ukfb_handle* h);
+
+/* initializeFilter(initial_state, state_cov) for every filter
+ * (UnscentedKalmanFilter.hpp:40-44): state replaced, t_last reset to 0.
+ * mu: B x MU, sigma: B x n x n.  The first call on an ORIENTATION handle also does
+ * what the constructor does after it: rotation_rate = 0, acceleration = (0,0,g0)
+ * (OrientationUKF.cpp:49-50). */
+int ukfb_initialize(ukfb_handle* h, const double* mu, const double* sigma);
+/* isInitialized(), :128 */
+int ukfb_is_initialized(const ukfb_handle* h);
+
+/* getCurrentState(state, cov) / getCurrentState(state) (:51-75).  sigma may be NULL.
+ * Returns UKFB_ERR_NOT_INITIALIZED where the reference returns false. */
+int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma);
+int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma);
+
+/* set/getProcessNoiseCovariance (:129-130).  per_filter = 0: Q is n x n and is
+ * broadcast; 1: B x n x n.  The lower triangle is used. */
+int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_filter);
+int ukfb_get_process_noise(ukfb_handle* h, double* Q, int per_filter);
+
+/* set/getMin/MaxTimeDelta (:134-137) */
+int ukfb_set_time_bounds(ukfb_handle* h, double min_dt, double max_dt);
+int ukfb_get_time_bounds(const ukfb_handle* h, double* min_dt, double* max_dt);
+
+/* set/getLastMeasurementTime (:131-133), int64 microseconds like base::Time. */
+int ukfb_set_last_time(ukfb_handle* h, const int64_t* ts_us, int per_filter);
+int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us);
+
+/* OrientationUKF constructor arguments gyro_bias_tau, acc_bias_tau, location.latitude
+ * (OrientationUKF.cpp:41-47): earth_rotation = (EARTHW cos lat, 0, EARTHW sin lat). */
+int ukfb_set_orientation_params(ukfb_handle* h, double gyro_bias_tau, double acc_bias_tau, double latitude);
+
+/* ---- predict -------------------------------------------------------------- */
+
+/* predictionStep(delta_t) (:107-125) -> predictionStepImpl (PoseUKF.cpp:180-196 /
+ * OrientationUKF.cpp:79-89) -> ukfom::ukf::predict.  dt: B values, or 1 when per_filter = 0. */
+int ukfb_predict_dt(ukfb_handle* h, const double* dt, int per_filter);
+int ukfb_predict_dt_dev(ukfb_handle* h, const double* d_dt, int per_filter);
+
+/* predictionStepFromSampleTime(sample_time) (:83-100). */
+int ukfb_predict_time(ukfb_handle* h, const int64_t* ts_us, int per_filter);
+int ukfb_predict_time_dev(ukfb_handle* h, const int64_t* d_ts_us, int per_filter);
+
+/* ---- measurements ----------------------------------------------------------- */
+
+/* integrateMeasurement(<kind>) -> ukfom::ukf::update (PoseUKF.cpp:112-173,
+ * OrientationUKF.cpp:65-72).  mu: B x m; cov: B x m x m, or m x m when
+ * cov_per_filter = 0; mask: B bytes (0 = this filter has no such measurement now)
+ * or NULL for all.  m = ukfb_meas_dim(kind). */
+int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, const double* cov, int cov_per_filter,
+                const uint8_t* mask);
+int ukfb_update_dev(ukfb_handle* h, int meas_kind, const double* d_mu, const double* d_cov, int cov_per_filter,
+                    const uint8_t* d_mask);
+int ukfb_meas_dim(int meas_kind);
+
+/* Asynchronous mixed measurements (BASELINE.json config 5): kinds[b] is the kind
+ * filter b integrates now (UKFB_MEAS_NONE = none).  mu: B x 3 and cov: B x 3 x 3,
+ * the leading m / m x m block of each slot is used. */
+int ukfb_update_mixed(ukfb_handle* h, const int8_t* kinds, const double* mu3, const double* cov33);
+int ukfb_update_mixed_dev(ukfb_handle* h, const int8_t* d_kinds, const double* d_mu3, const double* d_cov33);
+
+/* PoseUKF::integrateMeasurement(AccelerationMeasurement) (PoseUKF.cpp:175-178): stored
+ * unchecked for the next predict; OrientationUKF::integrateMeasurement(Acceleration)
+ * (OrientationUKF.cpp:59-63): finite-checked, then stored.  mu: B x 3, cov: B x 3 x 3
+ * (or 3 x 3).  cov may be NULL = identity (Measurement.hpp:11). */
+int ukfb_set_acceleration(ukfb_handle* h, const double* mu, const double* cov, int cov_per_filter,
+                          const uint8_t* mask);
+int ukfb_set_acceleration_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter,
+                              const uint8_t* d_mask);
+/* OrientationUKF::integrateMeasurement(RotationRate) (OrientationUKF.cpp:53-57). */
+int ukfb_set_rotation_rate(ukfb_handle* h, const double* mu, const double* cov, int cov_per_filter,
+                           const uint8_t* mask);
+int ukfb_set_rotation_rate_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter,
+                               const uint8_t* d_mask);
+/* OrientationUKF::getRotationRate() (OrientationUKF.cpp:74-77): out B x 3. */
+int ukfb_get_rotation_rate(ukfb_handle* h, double* out);
+
+/* ---- fused step ------------------------------------------------------------- */
+
+/* predictionStep(dt) followed by integrateMeasurement(kind) in ONE kernel launch; the
+ * state makes one HBM round trip.  Same results as ukfb_predict_dt + ukfb_update. */
+int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, int meas_kind, const double* mu,
+              const double* cov, int cov_per_filter, const uint8_t* mask);
+int ukfb_step_dev(ukfb_handle* h, const double* d_dt, int dt_per_filter, int meas_kind, const double* d_mu,
+                  const double* d_cov, int cov_per_filter, const uint8_t* d_mask);
+
+/* K consecutive fused steps with the state resident on chip between them.
+ * dt: K x B (or K when dt_per_filter = 0); kinds: K measurement kinds (one per tick,
+ * UKFB_MEAS_NONE = predict only); mu3: K x B x 3; cov33: K x B x 3 x 3, or K x 3 x 3
+ * when cov_per_filter = 0.  For ORIENTATION handles imu: K x B x 6 (gyro xyz, acc xyz)
+ * is stored before each predict (may be NULL). */
+int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, const int8_t* kinds_host,
+                 const double* d_mu3, const double* d_cov33, int cov_per_filter, const double* d_imu);
+
+/* ---- status ------------------------------------------------------------------ */
+
+int ukfb_get_status(ukfb_handle* h, uint32_t* flags); /* B words */
+int ukfb_clear_status(ukfb_handle* h);
+/* number of filters with any status bit set, and the OR of all words */
+int ukfb_status_summary(ukfb_handle* h, int64_t* n_flagged, uint32_t* any_bits);
+/* histogram of sigma_points_mean pass counts since the last clear: hist[k] = number
+ * of state-mean loops that ran k passes (k = 1..7, 7 = "7 or more"; hist[0] unused). */
+int ukfb_get_mean_iter_hist(ukfb_handle* h, uint64_t hist[8]);
+int ukfb_clear_mean_iter_hist(ukfb_handle* h);
+
+/* ---- stream plumbing ------------------------------------------------------- */
+
+int ukfb_synchronize(ukfb_handle* h);
+/* the handle's cudaStream_t, as an opaque pointer */
+void* ukfb_stream(ukfb_handle* h);
+/* CUDA events on the handle's stream, slots 0..15 */
+int ukfb_event_record(ukfb_handle* h, int slot);
+int ukfb_event_elapsed_ms(ukfb_handle* h, int slot_begin, int slot_end, float* ms);
+/* number of engine kernels launched on this handle since creation */
+int64_t ukfb_launch_count(const ukfb_handle* h);
+/* peak of an unrolled independent-DFMA microkernel on the handle's device, in
+ * FLOP/s (FMA = 2), the FP64 roofline denominator. */
+int ukfb_measure_fp64_peak(ukfb_handle* h, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* UKF_BATCH_H */

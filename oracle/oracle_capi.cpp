@@ -1,0 +1,391 @@
+/*
+ * oracle/oracle_capi.cpp -- CPU ORACLE, batch C interface.  TEST INFRASTRUCTURE ONLY
+ * (see the header of ukf_oracle.hpp: parity unpinned; only tests/, smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library).
+ *
+ * B independent oracle filter objects behind the same call shapes as
+ * include/ukf_batch.h (prefix orc_ instead of ukfb_), so that a parity test can
+ * drive the CUDA engine and the oracle with identical arguments.  OpenMP
+ * `parallel for` over filters: this is also the CPU baseline that bench.py times.
+ */
+#include <omp.h>
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "ukf_oracle.hpp"
+
+using namespace orc;
+
+namespace {
+
+struct Batch {
+    int kind;
+    int64_t B;
+    int n, MU;
+    bool initialized = false;
+    bool constructed = false; /* filter objects exist */
+    std::vector<std::unique_ptr<PoseFilter<double>>> pose;
+    std::vector<std::unique_ptr<OrientationFilter<double>>> ori;
+    std::vector<uint32_t> status;
+    /* parameters applied at construction / kept across re-initialisation */
+    std::vector<double> Q; /* n*n or B*n*n */
+    bool q_per_filter = false;
+    bool q_set = false;
+    double min_dt = UKFB_DEFAULT_MIN_DT;
+    double max_dt = std::numeric_limits<double>::max();
+    double tau_g = std::numeric_limits<double>::infinity();
+    double tau_a = std::numeric_limits<double>::infinity();
+    double latitude = 0.0;
+};
+
+template <class F>
+void apply_common(Batch* b, F& f, int64_t i)
+{
+    const int nn = b->n * b->n;
+    if (b->q_set) {
+        const double* q = b->Q.data() + (b->q_per_filter ? i * nn : 0);
+        for (int k = 0; k < nn; ++k) f.process_noise_cov[k] = q[k];
+    }
+    f.min_time_delta = b->min_dt;
+    f.max_time_delta = b->max_dt;
+}
+
+template <class Fn>
+void guarded(Batch* b, int64_t i, Fn fn)
+{
+    try {
+        fn();
+    } catch (const std::runtime_error& e) {
+        const char* w = e.what();
+        if (std::strstr(w, "negative"))
+            b->status[i] |= ST_NEG_DT;
+        else if (std::strstr(w, "allowed maximum"))
+            b->status[i] |= ST_DT_TOO_LARGE;
+        else
+            b->status[i] |= ST_NONFINITE_MEAS;
+    }
+}
+
+} /* namespace */
+
+extern "C" {
+
+void* orc_create(int kind, int64_t B)
+{
+    if ((kind != 0 && kind != 1) || B <= 0) return nullptr;
+    Batch* b = new Batch();
+    b->kind = kind;
+    b->B = B;
+    b->n = kind == 0 ? UKFB_POSE_DOF : UKFB_ORI_DOF;
+    b->MU = kind == 0 ? UKFB_POSE_MU : UKFB_ORI_MU;
+    b->status.assign(B, 0u);
+    return b;
+}
+
+void orc_destroy(void* h) { delete static_cast<Batch*>(h); }
+
+void orc_set_threads(int t)
+{
+    if (t > 0) omp_set_num_threads(t);
+}
+int orc_max_threads(void) { return omp_get_max_threads(); }
+
+int orc_initialize(void* h, const double* mu, const double* sigma)
+{
+    Batch* b = static_cast<Batch*>(h);
+    const int nn = b->n * b->n;
+    if (!b->constructed) {
+        if (b->kind == 0)
+            b->pose.resize(b->B);
+        else
+            b->ori.resize(b->B);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (b->kind == 0) {
+            PoseState<double> s;
+            s.load(mu + i * b->MU);
+            if (!b->constructed) {
+                b->pose[i].reset(new PoseFilter<double>(s, sigma + i * nn));
+                apply_common(b, *b->pose[i], i);
+            } else
+                b->pose[i]->initializeFilter(s, sigma + i * nn);
+        } else {
+            OrientationState<double> s;
+            s.load(mu + i * b->MU);
+            if (!b->constructed) {
+                b->ori[i].reset(new OrientationFilter<double>(s, sigma + i * nn, b->tau_g, b->tau_a, b->latitude));
+                apply_common(b, *b->ori[i], i);
+            } else
+                b->ori[i]->initializeFilter(s, sigma + i * nn);
+        }
+    }
+    b->constructed = true;
+    b->initialized = true;
+    return 0;
+}
+
+int orc_get_state(void* h, double* mu, double* sigma)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+    const int nn = b->n * b->n;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (b->kind == 0) {
+            b->pose[i]->ukf.mu.store(mu + i * b->MU);
+            if (sigma) std::memcpy(sigma + i * nn, b->pose[i]->ukf.sigma, nn * sizeof(double));
+        } else {
+            b->ori[i]->ukf.mu.store(mu + i * b->MU);
+            if (sigma) std::memcpy(sigma + i * nn, b->ori[i]->ukf.sigma, nn * sizeof(double));
+        }
+    }
+    return 0;
+}
+
+int orc_set_process_noise(void* h, const double* Q, int per_filter)
+{
+    Batch* b = static_cast<Batch*>(h);
+    const int nn = b->n * b->n;
+    b->Q.assign(Q, Q + (per_filter ? b->B * nn : nn));
+    b->q_per_filter = per_filter != 0;
+    b->q_set = true;
+    if (b->constructed) {
+        for (int64_t i = 0; i < b->B; ++i) {
+            if (b->kind == 0)
+                apply_common(b, *b->pose[i], i);
+            else
+                apply_common(b, *b->ori[i], i);
+        }
+    }
+    return 0;
+}
+
+int orc_set_time_bounds(void* h, double min_dt, double max_dt)
+{
+    Batch* b = static_cast<Batch*>(h);
+    b->min_dt = min_dt;
+    b->max_dt = max_dt;
+    if (b->constructed)
+        for (int64_t i = 0; i < b->B; ++i) {
+            if (b->kind == 0)
+                b->pose[i]->min_time_delta = min_dt, b->pose[i]->max_time_delta = max_dt;
+            else
+                b->ori[i]->min_time_delta = min_dt, b->ori[i]->max_time_delta = max_dt;
+        }
+    return 0;
+}
+
+int orc_set_orientation_params(void* h, double tau_g, double tau_a, double latitude)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (b->kind != 1) return -1;
+    b->tau_g = tau_g, b->tau_a = tau_a, b->latitude = latitude;
+    if (b->constructed)
+        for (int64_t i = 0; i < b->B; ++i) {
+            b->ori[i]->gyro_bias_tau = tau_g;
+            b->ori[i]->acc_bias_tau = tau_a;
+            b->ori[i]->earth_rotation[0] = UKFB_EARTHW * std::cos(latitude);
+            b->ori[i]->earth_rotation[1] = 0.;
+            b->ori[i]->earth_rotation[2] = UKFB_EARTHW * std::sin(latitude);
+        }
+    return 0;
+}
+
+int orc_set_last_time(void* h, const int64_t* ts, int per_filter)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->constructed) return -2;
+    for (int64_t i = 0; i < b->B; ++i) {
+        const int64_t t = ts[per_filter ? i : 0];
+        if (b->kind == 0)
+            b->pose[i]->last_measurement_time_us = t;
+        else
+            b->ori[i]->last_measurement_time_us = t;
+    }
+    return 0;
+}
+
+int orc_get_last_time(void* h, int64_t* ts)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->constructed) return -2;
+    for (int64_t i = 0; i < b->B; ++i)
+        ts[i] = b->kind == 0 ? b->pose[i]->last_measurement_time_us : b->ori[i]->last_measurement_time_us;
+    return 0;
+}
+
+int orc_predict_dt(void* h, const double* dt, int per_filter)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        const double d = dt[per_filter ? i : 0];
+        guarded(b, i, [&] {
+            if (b->kind == 0)
+                b->pose[i]->predictionStep(d);
+            else
+                b->ori[i]->predictionStep(d);
+        });
+    }
+    return 0;
+}
+
+int orc_predict_time(void* h, const int64_t* ts, int per_filter)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        const int64_t t = ts[per_filter ? i : 0];
+        guarded(b, i, [&] {
+            if (b->kind == 0)
+                b->pose[i]->predictionStepFromSampleTime(t);
+            else
+                b->ori[i]->predictionStepFromSampleTime(t);
+        });
+    }
+    return 0;
+}
+
+int orc_meas_dim(int kind) { return meas_dim(kind); }
+
+int orc_update(void* h, int meas_kind, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+    if (b->kind == 0 && (meas_kind < 0 || meas_kind > MEAS_POSE_ANGULAR_VELOCITY)) return -1;
+    if (b->kind == 1 && meas_kind != MEAS_ORI_VELOCITY) return -1;
+    const int m = meas_dim(meas_kind);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (mask && !mask[i]) continue;
+        const double* zm = mu + i * m;
+        const double* zc = cov + (cov_per_filter ? i * m * m : 0);
+        guarded(b, i, [&] {
+            if (b->kind == 0)
+                b->pose[i]->integrateMeasurement(meas_kind, zm, zc);
+            else
+                b->ori[i]->integrateVelocity(zm, zc);
+        });
+    }
+    return 0;
+}
+
+int orc_update_mixed(void* h, const int8_t* kinds, const double* mu3, const double* cov33)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        const int k = kinds[i];
+        if (k < 0) continue;
+        const int m = meas_dim(k);
+        double zm[3], zc[9];
+        for (int a = 0; a < m; ++a) zm[a] = mu3[i * 3 + a];
+        for (int a = 0; a < m; ++a)
+            for (int c = 0; c < m; ++c) zc[a * m + c] = cov33[i * 9 + a * 3 + c];
+        guarded(b, i, [&] {
+            if (b->kind == 0)
+                b->pose[i]->integrateMeasurement(k, zm, zc);
+            else
+                b->ori[i]->integrateVelocity(zm, zc);
+        });
+    }
+    return 0;
+}
+
+static const double kIdentity3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+int orc_set_acceleration(void* h, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->constructed) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (mask && !mask[i]) continue;
+        const double* c = cov ? cov + (cov_per_filter ? i * 9 : 0) : kIdentity3;
+        guarded(b, i, [&] {
+            if (b->kind == 0)
+                b->pose[i]->setAcceleration(mu + i * 3, c);
+            else
+                b->ori[i]->setAcceleration(mu + i * 3, c);
+        });
+    }
+    return 0;
+}
+
+int orc_set_rotation_rate(void* h, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (b->kind != 1) return -1;
+    if (!b->constructed) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (mask && !mask[i]) continue;
+        const double* c = cov ? cov + (cov_per_filter ? i * 9 : 0) : kIdentity3;
+        guarded(b, i, [&] { b->ori[i]->setRotationRate(mu + i * 3, c); });
+    }
+    return 0;
+}
+
+int orc_get_rotation_rate(void* h, double* out)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (b->kind != 1) return -1;
+    if (!b->initialized) return -2;
+    for (int64_t i = 0; i < b->B; ++i) b->ori[i]->getRotationRate(out + i * 3);
+    return 0;
+}
+
+int orc_step(void* h, const double* dt, int dt_per_filter, int meas_kind, const double* mu, const double* cov,
+             int cov_per_filter, const uint8_t* mask)
+{
+    int rc = orc_predict_dt(h, dt, dt_per_filter);
+    if (rc) return rc;
+    if (meas_kind < 0) return 0;
+    return orc_update(h, meas_kind, mu, cov, cov_per_filter, mask);
+}
+
+int orc_get_status(void* h, uint32_t* flags)
+{
+    Batch* b = static_cast<Batch*>(h);
+    for (int64_t i = 0; i < b->B; ++i) {
+        uint32_t s = b->status[i];
+        if (b->constructed) s |= b->kind == 0 ? b->pose[i]->ukf.status : b->ori[i]->ukf.status;
+        flags[i] = s;
+    }
+    return 0;
+}
+
+int orc_clear_status(void* h)
+{
+    Batch* b = static_cast<Batch*>(h);
+    for (int64_t i = 0; i < b->B; ++i) {
+        b->status[i] = 0;
+        if (b->constructed) {
+            if (b->kind == 0)
+                b->pose[i]->ukf.status = 0;
+            else
+                b->ori[i]->ukf.status = 0;
+        }
+    }
+    return 0;
+}
+
+int orc_get_mean_iter_hist(void* h, uint64_t hist[8])
+{
+    Batch* b = static_cast<Batch*>(h);
+    for (int k = 0; k < 8; ++k) hist[k] = 0;
+    if (!b->constructed) return 0;
+    for (int64_t i = 0; i < b->B; ++i)
+        for (int k = 0; k < 8; ++k)
+            hist[k] += b->kind == 0 ? b->pose[i]->ukf.mean_iters[k] : b->ori[i]->ukf.mean_iters[k];
+    return 0;
+}
+
+} /* extern "C" */
