@@ -6,7 +6,7 @@
  * ONE CUDA device; filter b of the batch behaves exactly like one instance of the
  * reference class.  Every entry point below names the reference interface it
  * replaces (file:line relative to the reference tree).  The reference is a C++
- * class API with no FFI of its own; `include/pose_estimation_b200/*.hpp` re-creates
+ * class API with no FFI of its own; the headers under include/pose_estimation_b200/ re-create
  * those classes (same names, arguments and exceptions) on top of this ABI, and
  * INTEGRATION.md shows the binding a maintainer would add.
  *
