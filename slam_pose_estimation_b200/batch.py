@@ -1,0 +1,268 @@
+"""UkfBatch -- thin Python driver over the C ABI (include/ukf_batch.h).
+
+One UkfBatch is B independent PoseUKF / OrientationUKF filters on one B200.  Method names
+and argument meaning follow the ABI, which in turn follows the reference classes
+(UnscentedKalmanFilter.hpp:27-137, PoseUKF.hpp:32-86, OrientationUKF.hpp:28-48).  Host
+(NumPy) arguments are copied by the library inside the call; `*_dev` methods take device
+pointers (torch CUDA tensors or raw ints) and only enqueue work on the handle's stream.
+PyTorch is used for device memory only -- all filter arithmetic is in lib/libukfb.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+POSE, ORIENTATION = 0, 1
+
+MEAS_NONE = -1
+MEAS_POSE_POSITION, MEAS_POSE_XY, MEAS_POSE_Z, MEAS_POSE_ORIENTATION = 0, 1, 2, 3
+MEAS_POSE_VELOCITY, MEAS_POSE_XY_VELOCITY, MEAS_POSE_Z_VELOCITY = 4, 5, 6
+MEAS_POSE_XVEL_YAWVEL, MEAS_POSE_ANGULAR_VELOCITY, MEAS_ORI_VELOCITY = 7, 8, 9
+
+STATUS_NEG_DT, STATUS_DT_TOO_LARGE, STATUS_NONFINITE_MEAS, STATUS_NOT_SPD, STATUS_MEAN_NO_CONVERGE = 1, 2, 4, 8, 16
+
+ERR_INVALID, ERR_NOT_INITIALIZED, ERR_CUDA, ERR_NOMEM = -1, -2, -3, -4
+
+
+class UkfbError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"ukfb error {code}: {text}")
+        self.code = code
+
+
+def _host(a, dtype):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _dev(t):
+    """device pointer of a torch CUDA tensor (must be contiguous) or a raw int / None"""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("device arguments must be contiguous CUDA tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+class UkfBatch:
+    def __init__(self, kind: int, B: int, device: int = 0):
+        self.lib = _capi.load()
+        self.kind, self.B, self.device = int(kind), int(B), int(device)
+        h = C.c_void_p()
+        self._chk(self.lib.ukfb_create(self.kind, self.B, self.device, C.byref(h)))
+        self.h = h
+        self.n = self.lib.ukfb_dof(h)
+        self.MU = self.lib.ukfb_mu_size(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ukfb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise UkfbError(rc, (self.lib.ukfb_last_error() or b"").decode())
+
+    # ---- lifecycle -----------------------------------------------------------------
+    def initialize(self, mu, sigma):
+        mu, pm = _host(mu, np.float64)
+        sg, ps = _host(sigma, np.float64)
+        if mu.size != self.B * self.MU or sg.size != self.B * self.n * self.n:
+            raise ValueError("initialize: mu must be B x MU and sigma B x n x n")
+        self._chk(self.lib.ukfb_initialize(self.h, pm, ps))
+
+    def is_initialized(self) -> bool:
+        return bool(self.lib.ukfb_is_initialized(self.h))
+
+    def get_state(self, with_sigma: bool = True):
+        mu = np.empty((self.B, self.MU))
+        sg = np.empty((self.B, self.n, self.n)) if with_sigma else None
+        self._chk(self.lib.ukfb_get_state(self.h, mu.ctypes.data_as(C.c_void_p),
+                                          sg.ctypes.data_as(C.c_void_p) if with_sigma else None))
+        return (mu, sg) if with_sigma else mu
+
+    def get_state_into(self, mu: np.ndarray, sigma: np.ndarray | None = None):
+        """getCurrentState into caller-owned (ideally pinned) host arrays."""
+        self._chk(self.lib.ukfb_get_state(self.h, mu.ctypes.data_as(C.c_void_p),
+                                          sigma.ctypes.data_as(C.c_void_p) if sigma is not None else None))
+
+    def get_state_dev(self, d_mu, d_sigma=None):
+        self._chk(self.lib.ukfb_get_state_dev(self.h, _dev(d_mu), _dev(d_sigma)))
+
+    def set_process_noise(self, Q):
+        Q, pq = _host(Q, np.float64)
+        per = 1 if Q.ndim == 3 else 0
+        self._chk(self.lib.ukfb_set_process_noise(self.h, pq, per))
+
+    def get_process_noise(self, per_filter: bool = False):
+        out = np.empty((self.B, self.n, self.n) if per_filter else (self.n, self.n))
+        self._chk(self.lib.ukfb_get_process_noise(self.h, out.ctypes.data_as(C.c_void_p), int(per_filter)))
+        return out
+
+    def set_time_bounds(self, min_dt: float, max_dt: float):
+        self._chk(self.lib.ukfb_set_time_bounds(self.h, min_dt, max_dt))
+
+    def get_time_bounds(self):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.lib.ukfb_get_time_bounds(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_last_time(self, ts):
+        ts = np.atleast_1d(np.asarray(ts, np.int64))
+        ts, pt = _host(ts, np.int64)
+        self._chk(self.lib.ukfb_set_last_time(self.h, pt, int(ts.size == self.B)))
+
+    def get_last_time(self):
+        out = np.empty(self.B, np.int64)
+        self._chk(self.lib.ukfb_get_last_time(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_orientation_params(self, tau_g: float, tau_a: float, latitude: float):
+        self._chk(self.lib.ukfb_set_orientation_params(self.h, tau_g, tau_a, latitude))
+
+    # ---- predict -------------------------------------------------------------------------
+    def predict_dt(self, dt):
+        dt = np.atleast_1d(np.asarray(dt, np.float64))
+        per = int(dt.size == self.B)
+        dt, pd = _host(dt, np.float64)
+        self._chk(self.lib.ukfb_predict_dt(self.h, pd, per))
+
+    def predict_dt_dev(self, d_dt, per_filter: bool):
+        self._chk(self.lib.ukfb_predict_dt_dev(self.h, _dev(d_dt), int(per_filter)))
+
+    def predict_time(self, ts):
+        ts = np.atleast_1d(np.asarray(ts, np.int64))
+        per = int(ts.size == self.B)
+        ts, pt = _host(ts, np.int64)
+        self._chk(self.lib.ukfb_predict_time(self.h, pt, per))
+
+    def predict_time_dev(self, d_ts, per_filter: bool):
+        self._chk(self.lib.ukfb_predict_time_dev(self.h, _dev(d_ts), int(per_filter)))
+
+    # ---- measurements -------------------------------------------------------------------------
+    def meas_dim(self, kind: int) -> int:
+        return self.lib.ukfb_meas_dim(kind)
+
+    def update(self, kind: int, mu, cov, mask=None):
+        m = self.meas_dim(kind)
+        mu, pm = _host(mu, np.float64)
+        cov, pc = _host(cov, np.float64)
+        if mu.size != self.B * m:
+            raise ValueError(f"update: mu must be B x {m}")
+        per = 1 if cov.ndim == 3 else 0
+        mask, pk = _host(mask, np.uint8)
+        self._chk(self.lib.ukfb_update(self.h, kind, pm, pc, per, pk))
+
+    def update_dev(self, kind: int, d_mu, d_cov, cov_per_filter: bool, d_mask=None):
+        self._chk(self.lib.ukfb_update_dev(self.h, kind, _dev(d_mu), _dev(d_cov), int(cov_per_filter), _dev(d_mask)))
+
+    def update_mixed(self, kinds, mu3, cov33):
+        kinds, pk = _host(kinds, np.int8)
+        mu3, pm = _host(mu3, np.float64)
+        cov33, pc = _host(cov33, np.float64)
+        if kinds.size != self.B or mu3.size != self.B * 3 or cov33.size != self.B * 9:
+            raise ValueError("update_mixed: kinds B, mu3 B x 3, cov33 B x 3 x 3")
+        self._chk(self.lib.ukfb_update_mixed(self.h, pk, pm, pc))
+
+    def update_mixed_dev(self, d_kinds, d_mu3, d_cov33):
+        self._chk(self.lib.ukfb_update_mixed_dev(self.h, _dev(d_kinds), _dev(d_mu3), _dev(d_cov33)))
+
+    def set_acceleration(self, mu, cov=None, mask=None):
+        mu, pm = _host(mu, np.float64)
+        cov, pc = _host(cov, np.float64)
+        per = 1 if (cov is not None and cov.ndim == 3) else 0
+        mask, pk = _host(mask, np.uint8)
+        self._chk(self.lib.ukfb_set_acceleration(self.h, pm, pc, per, pk))
+
+    def set_rotation_rate(self, mu, cov=None, mask=None):
+        mu, pm = _host(mu, np.float64)
+        cov, pc = _host(cov, np.float64)
+        per = 1 if (cov is not None and cov.ndim == 3) else 0
+        mask, pk = _host(mask, np.uint8)
+        self._chk(self.lib.ukfb_set_rotation_rate(self.h, pm, pc, per, pk))
+
+    def get_rotation_rate(self):
+        out = np.empty((self.B, 3))
+        self._chk(self.lib.ukfb_get_rotation_rate(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- fused ------------------------------------------------------------------------------------
+    def step(self, dt, kind: int, mu=None, cov=None, mask=None):
+        dt = np.atleast_1d(np.asarray(dt, np.float64))
+        per = int(dt.size == self.B)
+        dt, pd = _host(dt, np.float64)
+        mu, pm = _host(mu, np.float64)
+        cov, pc = _host(cov, np.float64)
+        cper = 1 if (cov is not None and cov.ndim == 3) else 0
+        mask, pk = _host(mask, np.uint8)
+        self._chk(self.lib.ukfb_step(self.h, pd, per, kind, pm, pc, cper, pk))
+
+    def step_dev(self, d_dt, dt_per_filter: bool, kind: int, d_mu=None, d_cov=None, cov_per_filter: bool = False, d_mask=None):
+        self._chk(self.lib.ukfb_step_dev(self.h, _dev(d_dt), int(dt_per_filter), kind, _dev(d_mu), _dev(d_cov),
+                                         int(cov_per_filter), _dev(d_mask)))
+
+    def run_dev(self, K: int, d_dt, dt_per_filter: bool, kinds=None, d_mu3=None, d_cov33=None, cov_per_filter: bool = False,
+                d_imu=None):
+        kinds_arr, pk = _host(kinds, np.int8)
+        if kinds_arr is not None and kinds_arr.size != K:
+            raise ValueError("run_dev: kinds must hold K entries")
+        self._chk(self.lib.ukfb_run_dev(self.h, K, _dev(d_dt), int(dt_per_filter), pk, _dev(d_mu3), _dev(d_cov33),
+                                        int(cov_per_filter), _dev(d_imu)))
+
+    # ---- status --------------------------------------------------------------------------------------
+    def get_status(self):
+        out = np.empty(self.B, np.uint32)
+        self._chk(self.lib.ukfb_get_status(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def clear_status(self):
+        self._chk(self.lib.ukfb_clear_status(self.h))
+
+    def status_summary(self):
+        n, bits = C.c_int64(), C.c_uint32()
+        self._chk(self.lib.ukfb_status_summary(self.h, C.byref(n), C.byref(bits)))
+        return n.value, bits.value
+
+    def get_mean_iter_hist(self):
+        out = np.zeros(8, np.uint64)
+        self._chk(self.lib.ukfb_get_mean_iter_hist(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def clear_mean_iter_hist(self):
+        self._chk(self.lib.ukfb_clear_mean_iter_hist(self.h))
+
+    # ---- stream plumbing ------------------------------------------------------------------------------
+    def synchronize(self):
+        self._chk(self.lib.ukfb_synchronize(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.ukfb_stream(self.h) or 0)
+
+    def event_record(self, slot: int):
+        self._chk(self.lib.ukfb_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.ukfb_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.ukfb_launch_count(self.h))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._chk(self.lib.ukfb_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value

@@ -1,0 +1,1059 @@
+/*
+ * ukf_batch.cu -- the C ABI of include/ukf_batch.h over the sm_100a kernels of
+ * ukf_device.cuh.  CUDA only: there is no CPU path behind these entry points; every
+ * call fails with UKFB_ERR_CUDA when no usable device is present.
+ *
+ * One handle = B filters of one kind on one device, one stream.  Filter records live in
+ * HBM as fixed-size rows (PoseF::REC / OriF::REC doubles: mu padded to 16, then the
+ * packed lower triangle of sigma), so the record of a group of filters is one
+ * contiguous, coalesced read for the warp that owns the group.
+ */
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ukf_device.cuh"
+
+using namespace ukfb;
+
+/* ---- error plumbing ------------------------------------------------------------------ */
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(UKFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* ukfb_last_error(void) { return g_err; }
+
+/* ---- handle ------------------------------------------------------------------------------ */
+struct ukfb_handle {
+    int kind = 0, device = 0;
+    long long B = 0;
+    int n = 0, MU = 0, LP = 0, REC = 0;
+    int G = 4; /* filters per warp */
+    cudaStream_t stream = nullptr;
+    double* state = nullptr;
+    double* Q = nullptr; /* LP (broadcast) or B x LP */
+    int q_per_filter = 0;
+    uint32_t* status = nullptr;
+    long long* t_last = nullptr;
+    unsigned long long* hist = nullptr;
+    double* acc_mu = nullptr;
+    double* acc_cov = nullptr;
+    double* gyro_mu = nullptr;
+    bool initialized = false, first_init = true;
+    double min_dt = UKFB_DEFAULT_MIN_DT, max_dt = DBL_MAX;
+    double tau_g = INFINITY, tau_a = INFINITY, latitude = 0.0;
+    double earth[3] = {UKFB_EARTHW, 0.0, 0.0};
+    /* device staging for host-pointer entry points, grown on demand */
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    long long* summary = nullptr; /* 2 words */
+    cudaEvent_t ev[16] = {};
+    long long launches = 0;
+};
+
+static int stage_reserve(ukfb_handle* h, size_t bytes)
+{
+    if (bytes <= h->stage_bytes) return UKFB_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->stage) CU(cudaFree(h->stage));
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    const size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(&h->stage, want);
+    if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "staging buffer of %zu bytes: %s", want, cudaGetErrorString(e));
+    h->stage_bytes = want;
+    return UKFB_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Bind { /* sets the device for the duration of a call */
+    int prev = -1;
+    bool ok = true;
+    explicit Bind(const ukfb_handle* h)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != h->device) ok = cudaSetDevice(h->device) == cudaSuccess;
+    }
+    ~Bind()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define CHECK_H(h)                                                      \
+    if (!(h)) return fail(UKFB_ERR_INVALID, "%s: null handle", __func__); \
+    Bind bind_(h);                                                      \
+    if (!bind_.ok) return fail(UKFB_ERR_CUDA, "%s: cudaSetDevice(%d) failed", __func__, (h)->device)
+
+/* ---- small kernels ------------------------------------------------------------------------- */
+
+/* host layout (mu B x MU, sigma B x n x n) -> records */
+__global__ void pack_kernel(double* __restrict__ state, const double* __restrict__ mu, const double* __restrict__ sigma,
+                            long long B, int n, int MU, int LP, int REC)
+{
+    const long long total = B * REC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / REC;
+        const int k = int(i - b * REC);
+        double v = 0.0;
+        if (k < MU)
+            v = mu[b * MU + k];
+        else if (k >= REC_MU_PAD && k < REC_MU_PAD + LP) {
+            const int e = k - REC_MU_PAD;
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= e) ++r;
+            const int c = e - r * (r + 1) / 2;
+            v = sigma[(b * n + r) * n + c];
+        }
+        state[i] = v;
+    }
+}
+
+__global__ void unpack_mu_kernel(const double* __restrict__ state, double* __restrict__ mu, long long B, int MU, int REC)
+{
+    const long long total = B * MU;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / MU;
+        const int k = int(i - b * MU);
+        mu[i] = state[b * REC + k];
+    }
+}
+
+__global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __restrict__ sigma, long long B, int n, int REC)
+{
+    const long long total = B * n * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (n * n);
+        const int e = int(i - b * n * n);
+        int r = e / n, c = e - (e / n) * n;
+        if (c > r) {
+            const int t = r;
+            r = c;
+            c = t;
+        }
+        sigma[i] = state[b * REC + REC_MU_PAD + tri(r, c)];
+    }
+}
+
+/* packed lower triangle of Q from full n x n matrices */
+__global__ void pack_q_kernel(double* __restrict__ Qp, const double* __restrict__ Q, long long count, int n, int LP)
+{
+    const long long total = count * LP;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / LP;
+        const int e = int(i - b * LP);
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= e) ++r;
+        const int c = e - r * (r + 1) / 2;
+        Qp[i] = Q[(b * n + r) * n + c];
+    }
+}
+
+__global__ void unpack_q_kernel(const double* __restrict__ Qp, double* __restrict__ Q, long long count, int n, int LP, long long q_stride)
+{
+    const long long total = count * n * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (n * n);
+        const int e = int(i - b * n * n);
+        int r = e / n, c = e - (e / n) * n;
+        if (c > r) {
+            const int t = r;
+            r = c;
+            c = t;
+        }
+        Q[i] = Qp[b * q_stride + tri(r, c)];
+    }
+}
+
+template <typename T>
+__global__ void fill_kernel(T* __restrict__ dst, long long count, T v)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+/* B identity 3x3 matrices (Measurement.hpp:11: cov = Identity) */
+__global__ void eye3_kernel(double* __restrict__ dst, long long count)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = ((i % 9) % 4 == 0) ? 1.0 : 0.0;
+}
+
+/* store a 3-vector measurement (and optionally its 3x3 covariance) per filter, masked;
+ * check = 1: checkMeasurment (UnscentedKalmanFilter.hpp:142-147) -- a non-finite sample is
+ * flagged and not stored, as the throw would have prevented the assignment. */
+__global__ void store_vec3_kernel(double* __restrict__ dst_mu, double* __restrict__ dst_cov, const double* __restrict__ mu,
+                                  const double* __restrict__ cov, long long cov_stride, const uint8_t* __restrict__ mask,
+                                  uint32_t* __restrict__ status, int check, long long B)
+{
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        if (mask && !mask[b]) continue;
+        const double m0 = mu[b * 3], m1 = mu[b * 3 + 1], m2 = mu[b * 3 + 2];
+        double c[9];
+        for (int i = 0; i < 9; ++i) c[i] = cov ? cov[b * cov_stride + i] : ((i % 4 == 0) ? 1.0 : 0.0);
+        if (check) {
+            bool ok = isfinite(m0) && isfinite(m1) && isfinite(m2);
+            for (int i = 0; i < 9; ++i) ok = ok && isfinite(c[i]);
+            if (!ok) {
+                status[b] |= UKFB_STATUS_NONFINITE_MEAS;
+                continue;
+            }
+        }
+        dst_mu[b * 3] = m0, dst_mu[b * 3 + 1] = m1, dst_mu[b * 3 + 2] = m2;
+        if (dst_cov)
+            for (int i = 0; i < 9; ++i) dst_cov[b * 9 + i] = c[i];
+    }
+}
+
+/* OrientationUKF::getRotationRate (OrientationUKF.cpp:74-77) */
+__global__ void rotation_rate_kernel(const double* __restrict__ state, const double* __restrict__ gyro, double e0, double e1,
+                                     double e2, double* __restrict__ out, long long B)
+{
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const double* x = state + b * OriF::REC;
+        const double q[4] = {x[0], x[1], x[2], x[3]};
+        const double e[3] = {e0, e1, e2};
+        double r[3];
+        quat_inv_rotate(q, e, r);
+        for (int i = 0; i < 3; ++i) out[b * 3 + i] = gyro[b * 3 + i] - x[7 + i] - r[i];
+    }
+}
+
+/* initial stored acceleration of OrientationUKF: (0, 0, gravity) (OrientationUKF.cpp:50) */
+__global__ void ori_default_imu_kernel(const double* __restrict__ state, double* __restrict__ acc, double* __restrict__ gyro,
+                                       long long B)
+{
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        acc[b * 3] = 0.0, acc[b * 3 + 1] = 0.0, acc[b * 3 + 2] = state[b * OriF::REC + 13];
+        gyro[b * 3] = gyro[b * 3 + 1] = gyro[b * 3 + 2] = 0.0;
+    }
+}
+
+__global__ void status_summary_kernel(const uint32_t* __restrict__ status, long long B, long long* __restrict__ out)
+{
+    long long n = 0;
+    unsigned bits = 0;
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const uint32_t s = status[b];
+        n += s != 0;
+        bits |= s;
+    }
+    for (int o = 16; o; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)n);
+        if (bits) atomicOr(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)bits);
+    }
+}
+
+/* independent DFMA chains: the FP64 roofline denominator */
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;
+}
+
+static inline int grid_for(long long count, int block = 256)
+{
+    long long g = (count + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return int(g);
+}
+
+/* ---- step launch ------------------------------------------------------------------------------ */
+template <class F, int G>
+static cudaError_t launch_step_t(const ukfb_handle* h, const StepParams& p)
+{
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(double) * WPB * Smem<F, G>::TOTAL;
+    if (!attr_set[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(ukf_step_kernel<F, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_set[h->device & 63] = true;
+    }
+    const long long per_block = (long long)WPB * G;
+    const long long grid = (p.B + per_block - 1) / per_block;
+    ukf_step_kernel<F, G><<<unsigned(grid), WPB * 32, smem, h->stream>>>(p);
+    return cudaGetLastError();
+}
+
+static int launch_step(ukfb_handle* h, const StepParams& p)
+{
+    cudaError_t e;
+    if (h->kind == UKFB_POSE) {
+        switch (h->G) {
+            case 1: e = launch_step_t<PoseF, 1>(h, p); break;
+            case 2: e = launch_step_t<PoseF, 2>(h, p); break;
+            case 8: e = launch_step_t<PoseF, 8>(h, p); break;
+            default: e = launch_step_t<PoseF, 4>(h, p); break;
+        }
+    } else {
+        switch (h->G) {
+            case 1: e = launch_step_t<OriF, 1>(h, p); break;
+            case 2: e = launch_step_t<OriF, 2>(h, p); break;
+            case 8: e = launch_step_t<OriF, 8>(h, p); break;
+            default: e = launch_step_t<OriF, 4>(h, p); break;
+        }
+    }
+    if (e != cudaSuccess) return fail(UKFB_ERR_CUDA, "ukf_step_kernel launch: %s", cudaGetErrorString(e));
+    h->launches++;
+    return UKFB_OK;
+}
+
+static StepParams base_params(const ukfb_handle* h)
+{
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.state = h->state;
+    p.Q = h->Q;
+    p.q_stride = h->q_per_filter ? h->LP : 0;
+    p.B = h->B;
+    p.status = h->status;
+    p.t_last = h->t_last;
+    p.hist = h->hist;
+    p.min_dt = h->min_dt;
+    p.max_dt = h->max_dt;
+    p.acc_mu = h->acc_mu;
+    p.acc_cov = h->acc_cov;
+    p.gyro_mu = h->gyro_mu;
+    p.neg_inv_tau_g = -1.0 / h->tau_g;
+    p.neg_inv_tau_a = -1.0 / h->tau_a;
+    p.earth[0] = h->earth[0], p.earth[1] = h->earth[1], p.earth[2] = h->earth[2];
+    p.kind = -1;
+    p.K = 1;
+    return p;
+}
+
+static bool kind_ok(const ukfb_handle* h, int kind)
+{
+    if (h->kind == UKFB_POSE) return kind >= 0 && kind <= 8;
+    return kind == UKFB_MEAS_ORI_VELOCITY;
+}
+
+#define NEED_INIT(h) \
+    if (!(h)->initialized) return fail(UKFB_ERR_NOT_INITIALIZED, "%s: filter not initialized", __func__)
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_handle** out)
+{
+    if (!out) return fail(UKFB_ERR_INVALID, "ukfb_create: out is null");
+    *out = nullptr;
+    if (filter_kind != UKFB_POSE && filter_kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_create: bad filter kind %d", filter_kind);
+    if (batch < 1) return fail(UKFB_ERR_INVALID, "ukfb_create: batch must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(UKFB_ERR_CUDA, "ukfb_create: no CUDA device (%s); this engine has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(UKFB_ERR_INVALID, "ukfb_create: device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(UKFB_ERR_CUDA, "ukfb_create: device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+
+    ukfb_handle* h = new (std::nothrow) ukfb_handle;
+    if (!h) return fail(UKFB_ERR_NOMEM, "ukfb_create: out of host memory");
+    h->kind = filter_kind;
+    h->device = device;
+    h->B = batch;
+    if (filter_kind == UKFB_POSE)
+        h->n = PoseF::N, h->MU = PoseF::MU, h->LP = PoseF::LP, h->REC = PoseF::REC;
+    else
+        h->n = OriF::N, h->MU = OriF::MU, h->LP = OriF::LP, h->REC = OriF::REC;
+    if (const char* g = getenv("UKFB_GROUP")) {
+        const int G = atoi(g);
+        if (G == 1 || G == 2 || G == 4 || G == 8) h->G = G;
+    }
+    Bind bind_(h);
+    if (!bind_.ok) {
+        delete h;
+        return fail(UKFB_ERR_CUDA, "ukfb_create: cudaSetDevice(%d) failed", device);
+    }
+#define CUH(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            fail(e_ == cudaErrorMemoryAllocation ? UKFB_ERR_NOMEM : UKFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+            ukfb_destroy(h);                                                          \
+            return e_ == cudaErrorMemoryAllocation ? UKFB_ERR_NOMEM : UKFB_ERR_CUDA; \
+        }                                                                             \
+    } while (0)
+    const long long B = batch;
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaMalloc(&h->state, sizeof(double) * B * h->REC));
+    CUH(cudaMalloc(&h->Q, sizeof(double) * h->LP));
+    CUH(cudaMalloc(&h->status, sizeof(uint32_t) * B));
+    CUH(cudaMalloc(&h->t_last, sizeof(long long) * B));
+    CUH(cudaMalloc(&h->hist, sizeof(unsigned long long) * HIST_SLOTS * 8));
+    CUH(cudaMalloc(&h->acc_mu, sizeof(double) * B * 3));
+    CUH(cudaMalloc(&h->acc_cov, sizeof(double) * B * 9));
+    CUH(cudaMalloc(&h->gyro_mu, sizeof(double) * B * 3));
+    CUH(cudaMalloc(&h->summary, sizeof(long long) * 2));
+    CUH(cudaMemsetAsync(h->state, 0, sizeof(double) * B * h->REC, h->stream));
+    CUH(cudaMemsetAsync(h->status, 0, sizeof(uint32_t) * B, h->stream));
+    CUH(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * B, h->stream));
+    CUH(cudaMemsetAsync(h->hist, 0, sizeof(unsigned long long) * HIST_SLOTS * 8, h->stream));
+    CUH(cudaMemsetAsync(h->gyro_mu, 0, sizeof(double) * B * 3, h->stream));
+    /* Q: zero (base ctor) then the PoseUKF default diagonal (PoseUKF.cpp:103-107) */
+    {
+        double q[OriF::LP];
+        for (int i = 0; i < OriF::LP; ++i) q[i] = 0.0;
+        if (filter_kind == UKFB_POSE) {
+            const double d[4] = {UKFB_POSE_Q_POSITION, UKFB_POSE_Q_ORIENTATION, UKFB_POSE_Q_VELOCITY, UKFB_POSE_Q_ANGULAR_VELOCITY};
+            for (int i = 0; i < 12; ++i) q[tri(i, i)] = d[i / 3];
+        }
+        CUH(cudaMemcpyAsync(h->Q, q, sizeof(double) * h->LP, cudaMemcpyHostToDevice, h->stream));
+        CUH(cudaStreamSynchronize(h->stream));
+    }
+    /* stored acceleration: NaN sentinel for PoseUKF (PoseUKF.cpp:109), identity covariance (Measurement.hpp:11) */
+    fill_kernel<double><<<grid_for(B * 3), 256, 0, h->stream>>>(h->acc_mu, B * 3, filter_kind == UKFB_POSE ? double(NAN) : 0.0);
+    eye3_kernel<<<grid_for(B * 9), 256, 0, h->stream>>>(h->acc_cov, B * 9);
+    for (int i = 0; i < 16; ++i) CUH(cudaEventCreate(&h->ev[i]));
+    CUH(cudaGetLastError());
+    CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+    *out = h;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_destroy(ukfb_handle* h)
+{
+    if (!h) return UKFB_OK;
+    Bind bind_(h);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist);
+    cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary);
+    for (int i = 0; i < 16; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return UKFB_OK;
+}
+
+extern "C" int64_t ukfb_batch(const ukfb_handle* h) { return h ? h->B : 0; }
+extern "C" int ukfb_dof(const ukfb_handle* h) { return h ? h->n : 0; }
+extern "C" int ukfb_mu_size(const ukfb_handle* h) { return h ? h->MU : 0; }
+extern "C" int ukfb_device(const ukfb_handle* h) { return h ? h->device : -1; }
+extern "C" int ukfb_is_initialized(const ukfb_handle* h) { return h && h->initialized ? 1 : 0; }
+
+static int initialize_dev(ukfb_handle* h, const double* d_mu, const double* d_sigma)
+{
+    pack_kernel<<<grid_for(h->B * h->REC), 256, 0, h->stream>>>(h->state, d_mu, d_sigma, h->B, h->n, h->MU, h->LP, h->REC);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * h->B, h->stream)); /* :43 */
+    if (h->kind == UKFB_ORIENTATION && h->first_init) {
+        ori_default_imu_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->acc_mu, h->gyro_mu, h->B);
+        CU(cudaGetLastError());
+    }
+    h->first_init = false;
+    h->initialized = true;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_initialize(ukfb_handle* h, const double* mu, const double* sigma)
+{
+    CHECK_H(h);
+    if (!mu || !sigma) return fail(UKFB_ERR_INVALID, "ukfb_initialize: null argument");
+    const size_t bm = align256(sizeof(double) * h->B * h->MU), bs = sizeof(double) * h->B * h->n * h->n;
+    int rc = stage_reserve(h, bm + bs);
+    if (rc) return rc;
+    double* d_mu = reinterpret_cast<double*>(h->stage);
+    double* d_sigma = reinterpret_cast<double*>(h->stage + bm);
+    CU(cudaMemcpyAsync(d_mu, mu, sizeof(double) * h->B * h->MU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_sigma, sigma, bs, cudaMemcpyHostToDevice, h->stream));
+    rc = initialize_dev(h, d_mu, d_sigma);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (d_mu) unpack_mu_kernel<<<grid_for(h->B * h->MU), 256, 0, h->stream>>>(h->state, d_mu, h->B, h->MU, h->REC);
+    if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->REC);
+    CU(cudaGetLastError());
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    const size_t bm = align256(sizeof(double) * h->B * h->MU), bs = sizeof(double) * h->B * h->n * h->n;
+    int rc = stage_reserve(h, bm + (sigma ? bs : 0));
+    if (rc) return rc;
+    double* d_mu = reinterpret_cast<double*>(h->stage);
+    double* d_sigma = reinterpret_cast<double*>(h->stage + bm);
+    rc = ukfb_get_state_dev(h, mu ? d_mu : nullptr, sigma ? d_sigma : nullptr);
+    if (rc) return rc;
+    if (mu) CU(cudaMemcpyAsync(mu, d_mu, sizeof(double) * h->B * h->MU, cudaMemcpyDeviceToHost, h->stream));
+    if (sigma) CU(cudaMemcpyAsync(sigma, d_sigma, bs, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_filter)
+{
+    CHECK_H(h);
+    if (!Q) return fail(UKFB_ERR_INVALID, "ukfb_set_process_noise: null argument");
+    const long long count = per_filter ? h->B : 1;
+    const size_t bytes = sizeof(double) * count * h->n * h->n;
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    if ((per_filter != 0) != (h->q_per_filter != 0)) {
+        CU(cudaStreamSynchronize(h->stream));
+        double* nq = nullptr;
+        cudaError_t e = cudaMalloc(&nq, sizeof(double) * count * h->LP);
+        if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "ukfb_set_process_noise: %s", cudaGetErrorString(e));
+        cudaFree(h->Q);
+        h->Q = nq;
+        h->q_per_filter = per_filter ? 1 : 0;
+    }
+    CU(cudaMemcpyAsync(h->stage, Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    pack_q_kernel<<<grid_for(count * h->LP), 256, 0, h->stream>>>(h->Q, reinterpret_cast<const double*>(h->stage), count, h->n, h->LP);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_process_noise(ukfb_handle* h, double* Q, int per_filter)
+{
+    CHECK_H(h);
+    if (!Q) return fail(UKFB_ERR_INVALID, "ukfb_get_process_noise: null argument");
+    const long long count = per_filter ? h->B : 1;
+    const size_t bytes = sizeof(double) * count * h->n * h->n;
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    unpack_q_kernel<<<grid_for(count * h->n * h->n), 256, 0, h->stream>>>(h->Q, reinterpret_cast<double*>(h->stage), count, h->n, h->LP,
+                                                                         h->q_per_filter ? h->LP : 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(Q, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_time_bounds(ukfb_handle* h, double min_dt, double max_dt)
+{
+    if (!h) return fail(UKFB_ERR_INVALID, "ukfb_set_time_bounds: null handle");
+    h->min_dt = min_dt;
+    h->max_dt = max_dt;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_time_bounds(const ukfb_handle* h, double* min_dt, double* max_dt)
+{
+    if (!h) return fail(UKFB_ERR_INVALID, "ukfb_get_time_bounds: null handle");
+    if (min_dt) *min_dt = h->min_dt;
+    if (max_dt) *max_dt = h->max_dt;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_last_time(ukfb_handle* h, const int64_t* ts_us, int per_filter)
+{
+    CHECK_H(h);
+    if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_set_last_time: null argument");
+    if (per_filter) {
+        CU(cudaMemcpyAsync(h->t_last, ts_us, sizeof(long long) * h->B, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        fill_kernel<long long><<<grid_for(h->B), 256, 0, h->stream>>>(h->t_last, h->B, (long long)ts_us[0]);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us)
+{
+    CHECK_H(h);
+    if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_get_last_time: null argument");
+    CU(cudaMemcpyAsync(ts_us, h->t_last, sizeof(long long) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_orientation_params(ukfb_handle* h, double gyro_bias_tau, double acc_bias_tau, double latitude)
+{
+    if (!h) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params: null handle");
+    if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params: not an ORIENTATION handle");
+    h->tau_g = gyro_bias_tau;
+    h->tau_a = acc_bias_tau;
+    h->latitude = latitude;
+    h->earth[0] = UKFB_EARTHW * cos(latitude);
+    h->earth[1] = 0.0;
+    h->earth[2] = UKFB_EARTHW * sin(latitude);
+    return UKFB_OK;
+}
+
+/* ---- predict --------------------------------------------------------------------------------------- */
+extern "C" int ukfb_predict_dt_dev(ukfb_handle* h, const double* d_dt, int per_filter)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_predict_dt: null argument");
+    StepParams p = base_params(h);
+    p.do_predict = 1;
+    p.time_mode = 0;
+    p.dt = d_dt;
+    p.dt_stride = per_filter ? 1 : 0;
+    return launch_step(h, p);
+}
+
+extern "C" int ukfb_predict_dt(ukfb_handle* h, const double* dt, int per_filter)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!dt) return fail(UKFB_ERR_INVALID, "ukfb_predict_dt: null argument");
+    const size_t bytes = sizeof(double) * (per_filter ? h->B : 1);
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, dt, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = ukfb_predict_dt_dev(h, reinterpret_cast<const double*>(h->stage), per_filter);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_predict_time_dev(ukfb_handle* h, const int64_t* d_ts_us, int per_filter)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!d_ts_us) return fail(UKFB_ERR_INVALID, "ukfb_predict_time: null argument");
+    StepParams p = base_params(h);
+    p.do_predict = 1;
+    p.time_mode = 1;
+    p.ts = reinterpret_cast<const long long*>(d_ts_us);
+    p.ts_stride = per_filter ? 1 : 0;
+    return launch_step(h, p);
+}
+
+extern "C" int ukfb_predict_time(ukfb_handle* h, const int64_t* ts_us, int per_filter)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_predict_time: null argument");
+    const size_t bytes = sizeof(int64_t) * (per_filter ? h->B : 1);
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, ts_us, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = ukfb_predict_time_dev(h, reinterpret_cast<const int64_t*>(h->stage), per_filter);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+/* ---- measurements ------------------------------------------------------------------------------------ */
+extern "C" int ukfb_meas_dim(int meas_kind)
+{
+    if (meas_kind < 0 || meas_kind >= UKFB_MEAS_KIND_COUNT) return 0;
+    return meas_dim(meas_kind);
+}
+
+static void set_update(StepParams& p, int kind, const double* d_mu, const double* d_cov, int cov_per_filter, const uint8_t* d_mask)
+{
+    const int m = meas_dim(kind);
+    p.do_update = 1;
+    p.kind = kind;
+    p.z = d_mu;
+    p.z_stride = m;
+    p.R = d_cov;
+    p.r_stride = cov_per_filter ? m * m : 0;
+    p.r_ld = m;
+    p.mask = d_mask;
+}
+
+extern "C" int ukfb_update_dev(ukfb_handle* h, int meas_kind, const double* d_mu, const double* d_cov, int cov_per_filter,
+                               const uint8_t* d_mask)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_update: measurement kind %d does not belong to this filter kind", meas_kind);
+    if (!d_mu || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
+    StepParams p = base_params(h);
+    set_update(p, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
+    return launch_step(h, p);
+}
+
+/* copies (mu, cov, mask) of one measurement into the staging buffer at `off`; returns device pointers */
+static int stage_meas(ukfb_handle* h, size_t off, int m, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask,
+                      const double** d_mu, const double** d_cov, const uint8_t** d_mask, size_t* end)
+{
+    const size_t bm = align256(sizeof(double) * h->B * m);
+    const size_t bc = cov ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0;
+    const size_t bk = mask ? align256(size_t(h->B)) : 0;
+    int rc = stage_reserve(h, off + bm + bc + bk);
+    if (rc) return rc;
+    char* base = h->stage + off;
+    CU(cudaMemcpyAsync(base, mu, sizeof(double) * h->B * m, cudaMemcpyHostToDevice, h->stream));
+    *d_mu = reinterpret_cast<const double*>(base);
+    *d_cov = nullptr;
+    if (cov) {
+        CU(cudaMemcpyAsync(base + bm, cov, sizeof(double) * (cov_per_filter ? h->B : 1) * m * m, cudaMemcpyHostToDevice, h->stream));
+        *d_cov = reinterpret_cast<const double*>(base + bm);
+    }
+    *d_mask = nullptr;
+    if (mask) {
+        CU(cudaMemcpyAsync(base + bm + bc, mask, size_t(h->B), cudaMemcpyHostToDevice, h->stream));
+        *d_mask = reinterpret_cast<const uint8_t*>(base + bm + bc);
+    }
+    if (end) *end = off + bm + bc + bk;
+    return UKFB_OK;
+}
+
+/* the staging buffer must be large enough BEFORE pointers into it are taken */
+static size_t meas_bytes(const ukfb_handle* h, int m, bool cov, int cov_per_filter, bool mask)
+{
+    return align256(sizeof(double) * h->B * m) + (cov ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0) +
+           (mask ? align256(size_t(h->B)) : 0);
+}
+
+extern "C" int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_update: measurement kind %d does not belong to this filter kind", meas_kind);
+    if (!mu || !cov) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
+    const int m = meas_dim(meas_kind);
+    const double *d_mu, *d_cov;
+    const uint8_t* d_mask;
+    int rc = stage_meas(h, 0, m, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
+    if (rc) return rc;
+    rc = ukfb_update_dev(h, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_update_mixed_dev(ukfb_handle* h, const int8_t* d_kinds, const double* d_mu3, const double* d_cov33)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!d_kinds || !d_mu3 || !d_cov33) return fail(UKFB_ERR_INVALID, "ukfb_update_mixed: null argument");
+    StepParams p = base_params(h);
+    p.do_update = 1;
+    p.kind = -2;
+    p.kinds = d_kinds;
+    p.z = d_mu3;
+    p.z_stride = 3;
+    p.R = d_cov33;
+    p.r_stride = 9;
+    p.r_ld = 3;
+    return launch_step(h, p);
+}
+
+extern "C" int ukfb_update_mixed(ukfb_handle* h, const int8_t* kinds, const double* mu3, const double* cov33)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!kinds || !mu3 || !cov33) return fail(UKFB_ERR_INVALID, "ukfb_update_mixed: null argument");
+    /* a kind of the other filter family is an API error, as calling a non-existent overload would be */
+    for (long long b = 0; b < h->B; ++b)
+        if (kinds[b] != UKFB_MEAS_NONE && !kind_ok(h, kinds[b]))
+            return fail(UKFB_ERR_INVALID, "ukfb_update_mixed: kinds[%lld] = %d does not belong to this filter kind", b, int(kinds[b]));
+    const size_t bk = align256(size_t(h->B)), bm = align256(sizeof(double) * h->B * 3), bc = sizeof(double) * h->B * 9;
+    int rc = stage_reserve(h, bk + bm + bc);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, kinds, size_t(h->B), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bk, mu3, sizeof(double) * h->B * 3, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bk + bm, cov33, bc, cudaMemcpyHostToDevice, h->stream));
+    rc = ukfb_update_mixed_dev(h, reinterpret_cast<const int8_t*>(h->stage), reinterpret_cast<const double*>(h->stage + bk),
+                               reinterpret_cast<const double*>(h->stage + bk + bm));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+static int store_vec3_dev(ukfb_handle* h, double* dst_mu, double* dst_cov, const double* d_mu, const double* d_cov, int cov_per_filter,
+                          const uint8_t* d_mask, int check)
+{
+    store_vec3_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(dst_mu, dst_cov, d_mu, d_cov, cov_per_filter ? 9 : 0, d_mask, h->status, check, h->B);
+    CU(cudaGetLastError());
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_acceleration_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter, const uint8_t* d_mask)
+{
+    CHECK_H(h);
+    if (!d_mu) return fail(UKFB_ERR_INVALID, "ukfb_set_acceleration: null argument");
+    /* PoseUKF stores unchecked (PoseUKF.cpp:175-178); OrientationUKF checks (OrientationUKF.cpp:61) */
+    return store_vec3_dev(h, h->acc_mu, h->acc_cov, d_mu, d_cov, cov_per_filter, d_mask, h->kind == UKFB_ORIENTATION);
+}
+
+extern "C" int ukfb_set_acceleration(ukfb_handle* h, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    CHECK_H(h);
+    if (!mu) return fail(UKFB_ERR_INVALID, "ukfb_set_acceleration: null argument");
+    const double *d_mu, *d_cov;
+    const uint8_t* d_mask;
+    int rc = stage_meas(h, 0, 3, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
+    if (rc) return rc;
+    rc = ukfb_set_acceleration_dev(h, d_mu, d_cov, cov_per_filter, d_mask);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_rotation_rate_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter, const uint8_t* d_mask)
+{
+    CHECK_H(h);
+    if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: not an ORIENTATION handle");
+    if (!d_mu) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: null argument");
+    /* the rotation-rate covariance is never read by the reference (OrientationUKF.cpp:88 passes .mu only) but
+     * checkMeasurment still inspects it */
+    return store_vec3_dev(h, h->gyro_mu, nullptr, d_mu, d_cov, cov_per_filter, d_mask, 1);
+}
+
+extern "C" int ukfb_set_rotation_rate(ukfb_handle* h, const double* mu, const double* cov, int cov_per_filter, const uint8_t* mask)
+{
+    CHECK_H(h);
+    if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: not an ORIENTATION handle");
+    if (!mu) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: null argument");
+    const double *d_mu, *d_cov;
+    const uint8_t* d_mask;
+    int rc = stage_meas(h, 0, 3, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
+    if (rc) return rc;
+    rc = ukfb_set_rotation_rate_dev(h, d_mu, d_cov, cov_per_filter, d_mask);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_rotation_rate(ukfb_handle* h, double* out)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_get_rotation_rate: not an ORIENTATION handle");
+    if (!out) return fail(UKFB_ERR_INVALID, "ukfb_get_rotation_rate: null argument");
+    int rc = stage_reserve(h, sizeof(double) * h->B * 3);
+    if (rc) return rc;
+    rotation_rate_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->gyro_mu, h->earth[0], h->earth[1], h->earth[2],
+                                                               reinterpret_cast<double*>(h->stage), h->B);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, h->stage, sizeof(double) * h->B * 3, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+/* ---- fused step ------------------------------------------------------------------------------------------ */
+extern "C" int ukfb_step_dev(ukfb_handle* h, const double* d_dt, int dt_per_filter, int meas_kind, const double* d_mu, const double* d_cov,
+                             int cov_per_filter, const uint8_t* d_mask)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_step: null dt");
+    StepParams p = base_params(h);
+    p.do_predict = 1;
+    p.dt = d_dt;
+    p.dt_stride = dt_per_filter ? 1 : 0;
+    if (meas_kind != UKFB_MEAS_NONE) {
+        if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step: measurement kind %d does not belong to this filter kind", meas_kind);
+        if (!d_mu || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_step: null measurement");
+        set_update(p, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
+    }
+    return launch_step(h, p);
+}
+
+extern "C" int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, int meas_kind, const double* mu, const double* cov,
+                         int cov_per_filter, const uint8_t* mask)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!dt) return fail(UKFB_ERR_INVALID, "ukfb_step: null dt");
+    const size_t bd = align256(sizeof(double) * (dt_per_filter ? h->B : 1));
+    const bool upd = meas_kind != UKFB_MEAS_NONE;
+    if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step: measurement kind %d does not belong to this filter kind", meas_kind);
+    if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step: null measurement");
+    const int m = upd ? meas_dim(meas_kind) : 0;
+    int rc = stage_reserve(h, bd + (upd ? meas_bytes(h, m, true, cov_per_filter, mask != nullptr) : 0));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, dt, sizeof(double) * (dt_per_filter ? h->B : 1), cudaMemcpyHostToDevice, h->stream));
+    const double *d_mu = nullptr, *d_cov = nullptr;
+    const uint8_t* d_mask = nullptr;
+    if (upd) {
+        rc = stage_meas(h, bd, m, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
+        if (rc) return rc;
+    }
+    rc = ukfb_step_dev(h, reinterpret_cast<const double*>(h->stage), dt_per_filter, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, const int8_t* kinds_host, const double* d_mu3,
+                            const double* d_cov33, int cov_per_filter, const double* d_imu)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run: K must be >= 1");
+    if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_run: null dt");
+    bool any = false;
+    if (kinds_host)
+        for (int k = 0; k < K; ++k) {
+            if (kinds_host[k] == UKFB_MEAS_NONE) continue;
+            if (!kind_ok(h, kinds_host[k])) return fail(UKFB_ERR_INVALID, "ukfb_run: kinds[%d] = %d does not belong to this filter kind", k, int(kinds_host[k]));
+            any = true;
+        }
+    if (any && (!d_mu3 || !d_cov33)) return fail(UKFB_ERR_INVALID, "ukfb_run: null measurement stream");
+    if (d_imu && h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_run: imu stream on a POSE handle");
+    StepParams p = base_params(h);
+    p.K = K;
+    p.do_predict = 1;
+    p.dt = d_dt;
+    p.dt_stride = dt_per_filter ? 1 : 0;
+    p.dt_kstride = dt_per_filter ? h->B : 1;
+    if (any) {
+        /* the K tick kinds ride in a small device array owned by the handle's staging tail */
+        int rc = stage_reserve(h, align256(size_t(K)));
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->stage, kinds_host, size_t(K), cudaMemcpyHostToDevice, h->stream));
+        p.do_update = 1;
+        p.tick_kinds = reinterpret_cast<const int8_t*>(h->stage);
+        p.z = d_mu3;
+        p.z_stride = 3;
+        p.z_kstride = h->B * 3;
+        p.R = d_cov33;
+        p.r_stride = cov_per_filter ? 9 : 0;
+        p.r_kstride = cov_per_filter ? h->B * 9 : 9;
+        p.r_ld = 3;
+    }
+    p.imu = d_imu;
+    p.imu_kstride = h->B * 6;
+    return launch_step(h, p);
+}
+
+/* ---- status ------------------------------------------------------------------------------------------------ */
+extern "C" int ukfb_get_status(ukfb_handle* h, uint32_t* flags)
+{
+    CHECK_H(h);
+    if (!flags) return fail(UKFB_ERR_INVALID, "ukfb_get_status: null argument");
+    CU(cudaMemcpyAsync(flags, h->status, sizeof(uint32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_clear_status(ukfb_handle* h)
+{
+    CHECK_H(h);
+    CU(cudaMemsetAsync(h->status, 0, sizeof(uint32_t) * h->B, h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_status_summary(ukfb_handle* h, int64_t* n_flagged, uint32_t* any_bits)
+{
+    CHECK_H(h);
+    CU(cudaMemsetAsync(h->summary, 0, sizeof(long long) * 2, h->stream));
+    status_summary_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->status, h->B, h->summary);
+    CU(cudaGetLastError());
+    long long out[2] = {0, 0};
+    CU(cudaMemcpyAsync(out, h->summary, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (n_flagged) *n_flagged = out[0];
+    if (any_bits) *any_bits = uint32_t(out[1]);
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_mean_iter_hist(ukfb_handle* h, uint64_t hist[8])
+{
+    CHECK_H(h);
+    if (!hist) return fail(UKFB_ERR_INVALID, "ukfb_get_mean_iter_hist: null argument");
+    unsigned long long tmp[HIST_SLOTS * 8];
+    CU(cudaMemcpyAsync(tmp, h->hist, sizeof(tmp), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 8; ++k) hist[k] = 0;
+    for (int s = 0; s < HIST_SLOTS; ++s)
+        for (int k = 0; k < 8; ++k) hist[k] += tmp[s * 8 + k];
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_clear_mean_iter_hist(ukfb_handle* h)
+{
+    CHECK_H(h);
+    CU(cudaMemsetAsync(h->hist, 0, sizeof(unsigned long long) * HIST_SLOTS * 8, h->stream));
+    return UKFB_OK;
+}
+
+/* ---- stream plumbing ------------------------------------------------------------------------------------------ */
+extern "C" int ukfb_synchronize(ukfb_handle* h)
+{
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" void* ukfb_stream(ukfb_handle* h) { return h ? reinterpret_cast<void*>(h->stream) : nullptr; }
+
+extern "C" int ukfb_event_record(ukfb_handle* h, int slot)
+{
+    CHECK_H(h);
+    if (slot < 0 || slot >= 16) return fail(UKFB_ERR_INVALID, "ukfb_event_record: slot out of range");
+    CU(cudaEventRecord(h->ev[slot], h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_event_elapsed_ms(ukfb_handle* h, int slot_begin, int slot_end, float* ms)
+{
+    CHECK_H(h);
+    if (slot_begin < 0 || slot_begin >= 16 || slot_end < 0 || slot_end >= 16 || !ms) return fail(UKFB_ERR_INVALID, "ukfb_event_elapsed_ms: bad argument");
+    CU(cudaEventSynchronize(h->ev[slot_end]));
+    CU(cudaEventElapsedTime(ms, h->ev[slot_begin], h->ev[slot_end]));
+    return UKFB_OK;
+}
+
+extern "C" int64_t ukfb_launch_count(const ukfb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int ukfb_measure_fp64_peak(ukfb_handle* h, double* flops_per_s)
+{
+    CHECK_H(h);
+    if (!flops_per_s) return fail(UKFB_ERR_INVALID, "ukfb_measure_fp64_peak: null argument");
+    int rc = stage_reserve(h, 256);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(a, h->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(reinterpret_cast<double*>(h->stage), iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(b, h->stream));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
+        if (rep > 0 && ms > 0.f && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *flops_per_s = best;
+    return UKFB_OK;
+}

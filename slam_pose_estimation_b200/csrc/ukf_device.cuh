@@ -68,7 +68,8 @@ struct Smem {
     static constexpr int OFF_B = F::LP;            /* Cholesky factor / updated sigma, packed lower */
     static constexpr int OFF_MU = 2 * F::LP;       /* mu */
     static constexpr int OFF_DELTA = OFF_MU + F::MU;
-    static constexpr int FREC_RAW = OFF_DELTA + F::N;
+    static constexpr int OFF_IMU = OFF_DELTA + F::N; /* stored acceleration [0:3], rotation rate [3:6] */
+    static constexpr int FREC_RAW = OFF_IMU + 6;
     static constexpr int FREC = FREC_RAW | 1;      /* odd stride: lane-per-filter accesses are conflict-free */
     /* per warp scratch */
     static constexpr int OFF_D = G * FREC;         /* deviations: 32 rows x DS ([dx | dz]) */
@@ -106,9 +107,9 @@ struct StepParams {
     const long long* ts;
     long long ts_stride;
     double min_dt, max_dt;
-    const double* acc_mu;   /* B x 3: POSE stored acceleration (NaN = none); ORIENTATION acceleration */
+    double* acc_mu;         /* B x 3: POSE stored acceleration (NaN = none); ORIENTATION acceleration */
     const double* acc_cov;  /* B x 9: POSE only */
-    const double* gyro_mu;  /* B x 3: ORIENTATION only */
+    double* gyro_mu;        /* B x 3: ORIENTATION only (both written back after an imu stream run) */
     double neg_inv_tau_g, neg_inv_tau_a; /* -1.0 / tau */
     double earth[3];
     /* update */
@@ -121,6 +122,13 @@ struct StepParams {
     long long r_stride;
     int r_ld;
     const uint8_t* mask;
+    /* K consecutive ticks in one launch (state stays in shared memory between them):
+     * element strides from tick k to tick k+1 of the per-tick streams */
+    int K;
+    long long dt_kstride, ts_kstride, z_kstride, r_kstride, kinds_kstride, mask_kstride;
+    const int8_t* tick_kinds; /* K uniform kinds, one per tick (overrides `kind`), or null */
+    const double* imu;        /* ORIENTATION: K x B x 6 (gyro xyz, acc xyz) stored before each predict, or null */
+    long long imu_kstride;
 };
 
 UKFB_HD int meas_dim(int kind)
@@ -405,27 +413,19 @@ UKFB_D double q_sym(const double* Qp, int i, int j) { return i >= j ? UKFB_LDG(Q
 
 /* ---- predict of one filter by one warp (ukfom predict, App. A.3) --------------------- */
 template <class F>
-UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, double* A, double* Bs, double* mu, double dt)
+UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, double* A, double* Bs, double* mu,
+                              const double* fimu, double dt)
 {
     const int lane = w.lane;
     const double* Qp = p.Q + b * p.q_stride;
 
     /* acceleration branch of PoseUKF.cpp:188-193 */
     bool has_acc = false;
-    double acc[3] = {0.0, 0.0, 0.0}, omega[3] = {0.0, 0.0, 0.0};
-    if (F::KIND == 0) {
-        acc[0] = UKFB_LDG(p.acc_mu + b * 3 + 0);
-        acc[1] = UKFB_LDG(p.acc_mu + b * 3 + 1);
-        acc[2] = UKFB_LDG(p.acc_mu + b * 3 + 2);
+    const double acc[3] = {fimu[0], fimu[1], fimu[2]};
+    const double omega[3] = {fimu[3], fimu[4], fimu[5]};
+    if (F::KIND == 0)
         has_acc = (fabs(acc[0]) <= 1.79769313486231570e308) && (fabs(acc[1]) <= 1.79769313486231570e308) &&
                   (fabs(acc[2]) <= 1.79769313486231570e308);
-    } else {
-        UKFB_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            acc[i] = UKFB_LDG(p.acc_mu + b * 3 + i);
-            omega[i] = UKFB_LDG(p.gyro_mu + b * 3 + i);
-        }
-    }
 
     /* rotated blocks of Q: rot * Q[blk] * rot^T (PoseUKF.cpp:184-185, OrientationUKF.cpp:84-85) */
     if (!has_acc && lane < 18) {
@@ -501,9 +501,10 @@ UKFB_D uint32_t sigma_apply_delta(Warp<F>& w, double* A, const double* Bs, doubl
 }
 
 /* ---- first half of update of one filter (App. A.4): innovation statistics, gain,
- * sigma' = sigma - K S K^T into Bs (out of place), delta = K innov ----------------------- */
+ * sigma <- sigma - K S K^T (in place), delta = K innov ----------------------- */
 template <class F>
-UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int kind, const double* A, double* Bs,
+UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int tick, int kind, double* A,
+                             const double* Bs,
                              const double* mu, double* delta)
 {
     const int lane = w.lane;
@@ -596,8 +597,8 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int k
     __syncwarp();
 
     /* S = 0.5 sum dz dz^T + R (R padded with identity to 3x3);  Sxz = 0.5 sum dx dz^T */
-    const double* zm = p.z + b * p.z_stride;
-    const double* Rm = p.R + b * p.r_stride;
+    const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+    const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
     if (lane < 9) {
         const int a = lane / 3, c = lane % 3;
         double s = 0.0;
@@ -664,7 +665,7 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int k
         w.KS[e] = ks;
     }
     __syncwarp();
-    /* sigma' = sigma - (K S) K^T, lower triangle, out of place into Bs */
+    /* sigma' = sigma - (K S) K^T, lower triangle, in place (the factor in Bs is no longer needed) */
     for (int e = lane; e < F::LP; e += 32) {
         int i = 0;
         while ((i + 1) * (i + 2) / 2 <= e) ++i;
@@ -672,7 +673,7 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int k
         double s = 0.0;
         UKFB_UNROLL
         for (int k = 0; k < 3; ++k) s += w.KS[i * 3 + k] * w.KM[j * 3 + k];
-        Bs[e] = A[e] - s;
+        A[e] = A[e] - s;
     }
     if (lane < F::N) {
         double s = 0.0;
@@ -727,133 +728,171 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
             else if (k >= REC_MU_PAD && k < REC_MU_PAD + F::LP)
                 fr[SM::OFF_A + (k - REC_MU_PAD)] = v;
         }
-    }
-
-    /* ---- per-filter control: time guards (UnscentedKalmanFilter.hpp:83-125), masks, checks */
-    uint32_t my_status = 0; /* lane g: status bits of filter g */
-    if (lane < G) {
-        int flags = 0, kind = -1;
-        if (lane < cnt) {
-            const long long b = first + lane;
-            flags = CF_VALID;
-            if (p.do_predict) {
-                double dt;
-                bool have_dt = true;
-                if (p.time_mode) {
-                    const long long ts = p.ts[b * p.ts_stride];
-                    const long long tl = p.t_last[b];
-                    if (tl == 0) { /* first call: latch only (:86-90) */
-                        p.t_last[b] = ts;
-                        have_dt = false;
-                        dt = 0.0;
-                    } else {
-                        dt = double(ts - tl) / UKFB_US_PER_S;
-                        if (dt > p.min_dt) p.t_last[b] = ts; /* :96-97 */
-                    }
-                } else {
-                    dt = p.dt[b * p.dt_stride];
-                }
-                if (have_dt) {
-                    if (dt < 0.0)
-                        my_status |= UKFB_STATUS_NEG_DT;
-                    else if (dt <= p.min_dt) {
-                        /* delta time is zero or close to zero: no-op */
-                    } else if (dt > p.max_dt)
-                        my_status |= UKFB_STATUS_DT_TOO_LARGE;
-                    else {
-                        flags |= CF_PRED;
-                        cdt[lane] = dt;
-                    }
-                }
-            }
-            if (p.do_update) {
-                kind = p.kind == -2 ? int(p.kinds[b]) : p.kind;
-                if (p.mask && !p.mask[b]) kind = -1;
-                if (kind >= 0) {
-                    bool ok = true;
-                    if (F::KIND == 1) { /* checkMeasurment, OrientationUKF.cpp:67 */
-                        const int m = meas_dim(kind);
-                        const double* zm = p.z + b * p.z_stride;
-                        const double* Rm = p.R + b * p.r_stride;
-                        for (int a = 0; a < m; ++a) ok = ok && (fabs(zm[a]) <= 1.79769313486231570e308);
-                        for (int a = 0; a < m; ++a)
-                            for (int c = 0; c < m; ++c) ok = ok && (fabs(Rm[a * p.r_ld + c]) <= 1.79769313486231570e308);
-                    }
-                    if (ok)
-                        flags |= CF_UPD;
-                    else {
-                        my_status |= UKFB_STATUS_NONFINITE_MEAS;
-                        kind = -1;
-                    }
-                }
-            }
+        /* the stored IMU sample: acceleration (PoseUKF.cpp:175-178, OrientationUKF.cpp:59-63)
+         * and rotation rate (OrientationUKF.cpp:53-57) */
+        for (int i = lane; i < cnt * 6; i += 32) {
+            const int g = i / 6, k = i - g * 6;
+            double v = 0.0;
+            if (k < 3)
+                v = p.acc_mu[(first + g) * 3 + k];
+            else if (F::KIND == 1)
+                v = p.gyro_mu[(first + g) * 3 + (k - 3)];
+            wsm[g * SM::FREC + SM::OFF_IMU + k] = v;
         }
-        cflag[lane] = flags;
-        ckind[lane] = kind;
     }
+    uint32_t my_status = 0; /* lane g: status bits of filter g */
+    bool dirty = false;     /* lane g: record of filter g changed */
     __syncwarp();
 
-    /* ---- predict ---------------------------------------------------------------------- */
-    if (p.do_predict) {
-        if (lane < G && (cflag[lane] & CF_PRED)) {
-            double* fr = wsm + lane * SM::FREC;
-            if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
-                my_status |= UKFB_STATUS_NOT_SPD;
-                cflag[lane] &= ~(CF_PRED | CF_UPD);
+    UKFB_NOUNROLL
+    for (int tick = 0; tick < p.K; ++tick) {
+        /* ---- per-filter control: time guards (UnscentedKalmanFilter.hpp:83-125), masks, checks */
+        if (lane < G) {
+            int flags = 0, kind = -1;
+            if (lane < cnt) {
+                const long long b = first + lane;
+                flags = CF_VALID;
+                if (F::KIND == 1 && p.imu) { /* integrateMeasurement(RotationRate / Acceleration): check, store */
+                    const double* s6 = p.imu + tick * p.imu_kstride + b * 6;
+                    double* fimu = wsm + lane * SM::FREC + SM::OFF_IMU;
+                    const double g0 = s6[0], g1 = s6[1], g2 = s6[2], a0 = s6[3], a1 = s6[4], a2 = s6[5];
+                    const double big = 1.79769313486231570e308;
+                    if (fabs(g0) <= big && fabs(g1) <= big && fabs(g2) <= big)
+                        fimu[3] = g0, fimu[4] = g1, fimu[5] = g2;
+                    else
+                        my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                    if (fabs(a0) <= big && fabs(a1) <= big && fabs(a2) <= big)
+                        fimu[0] = a0, fimu[1] = a1, fimu[2] = a2;
+                    else
+                        my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                }
+                if (p.do_predict) {
+                    double dt;
+                    bool have_dt = true;
+                    if (p.time_mode) {
+                        const long long ts = p.ts[tick * p.ts_kstride + b * p.ts_stride];
+                        const long long tl = p.t_last[b];
+                        if (tl == 0) { /* first call: latch only (:86-90) */
+                            p.t_last[b] = ts;
+                            have_dt = false;
+                            dt = 0.0;
+                        } else {
+                            dt = double(ts - tl) / UKFB_US_PER_S;
+                            if (dt > p.min_dt) p.t_last[b] = ts; /* :96-97 */
+                        }
+                    } else {
+                        dt = p.dt[tick * p.dt_kstride + b * p.dt_stride];
+                    }
+                    if (have_dt) {
+                        if (dt < 0.0)
+                            my_status |= UKFB_STATUS_NEG_DT;
+                        else if (dt <= p.min_dt) {
+                            /* delta time is zero or close to zero: no-op */
+                        } else if (dt > p.max_dt)
+                            my_status |= UKFB_STATUS_DT_TOO_LARGE;
+                        else {
+                            flags |= CF_PRED;
+                            cdt[lane] = dt;
+                        }
+                    }
+                }
+                if (p.do_update) {
+                    kind = p.tick_kinds ? int(p.tick_kinds[tick])
+                                        : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                    if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+                    if (kind >= 0) {
+                        bool ok = true;
+                        if (F::KIND == 1) { /* checkMeasurment, OrientationUKF.cpp:67 */
+                            const int m = meas_dim(kind);
+                            const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+                            const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
+                            for (int a = 0; a < m; ++a) ok = ok && (fabs(zm[a]) <= 1.79769313486231570e308);
+                            for (int a = 0; a < m; ++a)
+                                for (int c = 0; c < m; ++c) ok = ok && (fabs(Rm[a * p.r_ld + c]) <= 1.79769313486231570e308);
+                        }
+                        if (ok)
+                            flags |= CF_UPD;
+                        else {
+                            my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                            kind = -1;
+                        }
+                    }
+                }
             }
+            cflag[lane] = flags;
+            ckind[lane] = kind;
         }
         __syncwarp();
-        for (int g = 0; g < cnt; ++g) {
-            if (!(cflag[g] & CF_PRED)) continue;
-            double* fr = wsm + g * SM::FREC;
-            const uint32_t st = sigma_predict<F>(w, p, first + g, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU, cdt[g]);
-            if (lane == g) {
-                my_status |= st;
-                cflag[g] |= CF_DIRTY;
+
+        /* ---- predict ------------------------------------------------------------------ */
+        if (p.do_predict) {
+            if (lane < G && (cflag[lane] & CF_PRED)) {
+                double* fr = wsm + lane * SM::FREC;
+                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
+                    my_status |= UKFB_STATUS_NOT_SPD;
+                    cflag[lane] &= ~(CF_PRED | CF_UPD);
+                }
             }
+            __syncwarp();
+            for (int g = 0; g < cnt; ++g) {
+                if (!(cflag[g] & CF_PRED)) continue;
+                double* fr = wsm + g * SM::FREC;
+                const uint32_t st = sigma_predict<F>(w, p, first + g, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU,
+                                                     fr + SM::OFF_IMU, cdt[g]);
+                if (lane == g) {
+                    my_status |= st;
+                    dirty = true;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+
+        /* ---- update --------------------------------------------------------------------- */
+        if (p.do_update) {
+            if (lane < G && (cflag[lane] & CF_UPD)) {
+                double* fr = wsm + lane * SM::FREC;
+                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
+                    my_status |= UKFB_STATUS_NOT_SPD;
+                    cflag[lane] &= ~CF_UPD;
+                }
+            }
+            __syncwarp();
+            for (int g = 0; g < cnt; ++g) {
+                if (!(cflag[g] & CF_UPD)) continue;
+                double* fr = wsm + g * SM::FREC;
+                const uint32_t st = sigma_update<F>(w, p, first + g, tick, ckind[g], fr + SM::OFF_A, fr + SM::OFF_B,
+                                                    fr + SM::OFF_MU, fr + SM::OFF_DELTA);
+                if (lane == g) my_status |= st;
+            }
+            __syncwarp();
+            if (lane < G && (cflag[lane] & CF_UPD)) {
+                double* fr = wsm + lane * SM::FREC;
+                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
+                    /* the reference has already replaced sigma by sigma - K S K^T when MTK's
+                     * assert fires inside apply_delta; keep that matrix, leave mu alone */
+                    my_status |= UKFB_STATUS_NOT_SPD;
+                    cflag[lane] &= ~CF_UPD;
+                    dirty = true;
+                }
+            }
+            __syncwarp();
+            for (int g = 0; g < cnt; ++g) {
+                if (!(cflag[g] & CF_UPD)) continue;
+                double* fr = wsm + g * SM::FREC;
+                const uint32_t st =
+                    sigma_apply_delta<F>(w, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU, fr + SM::OFF_DELTA);
+                if (lane == g) {
+                    my_status |= st;
+                    dirty = true;
+                }
+            }
+            __syncwarp();
+        }
     }
 
-    /* ---- update -------------------------------------------------------------------------- */
-    if (p.do_update) {
-        if (lane < G && (cflag[lane] & CF_UPD)) {
-            double* fr = wsm + lane * SM::FREC;
-            if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
-                my_status |= UKFB_STATUS_NOT_SPD;
-                cflag[lane] &= ~CF_UPD;
-            }
-        }
-        __syncwarp();
-        for (int g = 0; g < cnt; ++g) {
-            if (!(cflag[g] & CF_UPD)) continue;
-            double* fr = wsm + g * SM::FREC;
-            const uint32_t st = sigma_update<F>(w, p, first + g, ckind[g], fr + SM::OFF_A, fr + SM::OFF_B,
-                                                fr + SM::OFF_MU, fr + SM::OFF_DELTA);
-            if (lane == g) my_status |= st;
-        }
-        __syncwarp();
-        if (lane < G && (cflag[lane] & CF_UPD)) {
-            double* fr = wsm + lane * SM::FREC;
-            if (!cholesky_packed<F>(fr + SM::OFF_B, fr + SM::OFF_B)) {
-                my_status |= UKFB_STATUS_NOT_SPD;
-                cflag[lane] &= ~CF_UPD;
-            }
-        }
-        __syncwarp();
-        for (int g = 0; g < cnt; ++g) {
-            if (!(cflag[g] & CF_UPD)) continue;
-            double* fr = wsm + g * SM::FREC;
-            const uint32_t st = sigma_apply_delta<F>(w, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU, fr + SM::OFF_DELTA);
-            if (lane == g) {
-                my_status |= st;
-                cflag[g] |= CF_DIRTY;
-            }
-        }
-        __syncwarp();
-    }
-
-    /* ---- store dirty records (coalesced), status, histogram ------------------------------- */
+    /* ---- store dirty records (coalesced), stored IMU sample, status, histogram --------------- */
+    if (lane < G) cflag[lane] = dirty ? CF_DIRTY : 0;
+    __syncwarp();
     {
         double* dst = p.state + first * F::REC;
         for (int i = lane; i < cnt * F::REC; i += 32) {
@@ -864,6 +903,16 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
                 dst[i] = fr[SM::OFF_MU + k];
             else if (k >= REC_MU_PAD && k < REC_MU_PAD + F::LP)
                 dst[i] = fr[SM::OFF_A + (k - REC_MU_PAD)];
+        }
+        if (F::KIND == 1 && p.imu) {
+            for (int i = lane; i < cnt * 6; i += 32) {
+                const int g = i / 6, k = i - g * 6;
+                const double v = wsm[g * SM::FREC + SM::OFF_IMU + k];
+                if (k < 3)
+                    p.acc_mu[(first + g) * 3 + k] = v;
+                else
+                    p.gyro_mu[(first + g) * 3 + (k - 3)] = v;
+            }
         }
     }
     if (lane < cnt && my_status) p.status[first + lane] |= my_status;

@@ -27,6 +27,9 @@ class StepParams(C.Structure):
         ("neg_inv_tau_g", C.c_double), ("neg_inv_tau_a", C.c_double), ("earth", C.c_double * 3),
         ("do_update", C.c_int), ("kind", C.c_int), ("kinds", C.c_void_p), ("z", C.c_void_p), ("z_stride", C.c_int),
         ("R", C.c_void_p), ("r_stride", C.c_longlong), ("r_ld", C.c_int), ("mask", C.c_void_p),
+        ("K", C.c_int), ("dt_kstride", C.c_longlong), ("ts_kstride", C.c_longlong), ("z_kstride", C.c_longlong),
+        ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
+        ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
     ]
 
 
@@ -132,6 +135,7 @@ class EmuBatch:
         p.Q = _ptr(self._Q)
         p.q_stride = self.q_stride
         p.B = self.B
+        p.K = 1
         p.status = _ptr(self.status)
         p.t_last = _ptr(self.t_last)
         p.hist = _ptr(self.hist)

@@ -1,0 +1,85 @@
+"""The C-ABI library loads and exports every symbol include/ukf_batch.h declares; without a
+GPU every compute entry point refuses to run (there is no CPU path)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "ukf_batch.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ukfb_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from slam_pose_estimation_b200 import _build, _capi
+
+    _build.build()
+    return _capi.load()
+
+
+def test_header_and_binding_agree(lib):
+    from slam_pose_estimation_b200 import _capi
+
+    names = declared_functions()
+    assert len(names) >= 40
+    assert sorted(_capi.SIGNATURES) == names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ukf_batch.h but not exported by libukfb.so"
+
+
+def test_no_torch_or_python_types_in_signatures():
+    text = open(os.path.join(ROOT, "include", "ukf_batch.h")).read()
+    assert "torch" not in text.lower() and "at::" not in text and "PyObject" not in text
+
+
+def test_meas_dims(lib):
+    want = {0: 3, 1: 2, 2: 1, 3: 3, 4: 3, 5: 2, 6: 1, 7: 2, 8: 3, 9: 3}
+    for k, m in want.items():
+        assert lib.ukfb_meas_dim(k) == m
+    assert lib.ukfb_meas_dim(-1) == 0 and lib.ukfb_meas_dim(10) == 0
+
+
+def test_fails_loudly_without_gpu(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.ukfb_create(0, 4, 0, C.byref(h))
+    assert rc == -3 and not h.value  # UKFB_ERR_CUDA
+    assert b"no CPU path" in lib.ukfb_last_error() or b"CUDA" in lib.ukfb_last_error()
+    from slam_pose_estimation_b200 import UkfBatch, UkfbError
+
+    with pytest.raises(UkfbError):
+        UkfBatch(0, 4)
+
+
+def test_bad_arguments(lib):
+    h = C.c_void_p()
+    assert lib.ukfb_create(7, 4, 0, C.byref(h)) == -1
+    assert lib.ukfb_create(0, 0, 0, C.byref(h)) == -1
+    assert lib.ukfb_create(0, 4, 0, None) == -1
+    assert lib.ukfb_batch(None) == 0 and lib.ukfb_dof(None) == 0
+    assert lib.ukfb_predict_dt(None, None, 0) == -1
+
+
+def test_product_never_touches_the_oracle():
+    """nothing under the package or include/ imports, includes or links oracle/"""
+    pkg = os.path.join(ROOT, "slam_pose_estimation_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(base, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"

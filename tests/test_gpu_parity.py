@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (lib/libukfb.so), against the
+CPU oracle on identical seeded inputs.  Tolerance: 1e-9 (north star), norm-wise metrics
+of SURVEY.md section 8(d) -- see tests/parity.py.  Run with `pytest -m gpu` on a B200.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import parity as P
+from oracle.oracle_lib import OracleBatch
+from slam_pose_estimation_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Ukf():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from slam_pose_estimation_b200 import UkfBatch
+
+    return UkfBatch
+
+
+def both(Ukf, kind, B, **kw):
+    if kind == 0:
+        return P.make_pose(Ukf, B, **kw), P.make_pose(OracleBatch, B, **kw)
+    return P.make_ori(Ukf, B), P.make_ori(OracleBatch, B)
+
+
+# ---- single operations -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 33, 1000])
+def test_pose_predict(Ukf, B):
+    g, o = both(Ukf, 0, B)
+    for x in (g, o):
+        x.predict_dt(0.01)
+    P.assert_parity(0, g.get_state(), o.get_state(), what=f"pose predict B={B}")
+    assert P.spd_ok(g.get_state()[1])
+
+
+def test_pose_predict_per_filter_dt(Ukf):
+    B = 70
+    g, o = both(Ukf, 0, B)
+    dt = np.linspace(1e-3, 0.5, B)
+    for x in (g, o):
+        x.predict_dt(dt)
+    P.assert_parity(0, g.get_state(), o.get_state(), what="per-filter dt")
+
+
+@pytest.mark.parametrize("kind", list(range(9)))
+def test_pose_update_kinds(Ukf, kind):
+    B = 37
+    g, o = both(Ukf, 0, B)
+    z, R = syn.pose_measurement(kind, B, 7)
+    for x in (g, o):
+        x.predict_dt(0.05)
+        x.update(kind, z, R)
+    P.assert_parity(0, g.get_state(), o.get_state(), what=f"pose update kind {kind}")
+
+
+def test_pose_update_per_filter_cov_and_mask(Ukf):
+    B = 50
+    g, o = both(Ukf, 0, B)
+    z, R = syn.pose_measurement(4, B, 3, r_scale=np.linspace(0.25, 4.0, B))
+    mask = (np.arange(B) % 3 != 0).astype(np.uint8)
+    before = None
+    for x in (g, o):
+        x.predict_dt(0.02)
+        before = x.get_state()
+        x.update(4, z, R, mask)
+    gs, os_ = g.get_state(), o.get_state()
+    P.assert_parity(0, gs, os_, what="masked update")
+    # masked-out filters are untouched by the update
+    assert np.array_equal(os_[0][mask == 0], before[0][mask == 0])
+
+
+def test_pose_acceleration_branch(Ukf):
+    """finite stored acceleration: the shadowed process noise of PoseUKF.cpp:188-193"""
+    B = 19
+    g, o = both(Ukf, 0, B)
+    acc = 0.01 * syn.noise(np.arange(B), 1, 13, 3)
+    cov = np.eye(3) * 1e-4
+    part = (np.arange(B) % 2).astype(np.uint8)  # half the filters keep the NaN sentinel
+    for x in (g, o):
+        x.set_acceleration(acc, cov, part)
+        x.predict_dt(0.01)
+        x.predict_dt(0.01)
+    P.assert_parity(0, g.get_state(), o.get_state(), what="acceleration branch")
+
+
+def test_orientation_predict_and_update(Ukf):
+    B = 41
+    g, o = both(Ukf, 1, B)
+    for k in range(1, 4):
+        gyro, acc = syn.orientation_imu(B, k)
+        z, R = syn.orientation_velocity(B, k)
+        for x in (g, o):
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(acc)
+            x.predict_dt(syn.DT)
+            x.update(9, z, R)
+    P.assert_parity(1, g.get_state(), o.get_state(), what="orientation predict+update")
+    assert np.allclose(g.get_rotation_rate(), o.get_rotation_rate(), rtol=0, atol=1e-15)
+
+
+def test_fused_step_equals_predict_then_update(Ukf):
+    B = 21
+    a, _ = both(Ukf, 0, B)
+    b = P.make_pose(Ukf, B)
+    z, R = syn.pose_measurement(8, B, 2)
+    a.step(0.01, 8, z, R)
+    b.predict_dt(0.01)
+    b.update(8, z, R)
+    sa, sb = a.get_state(), b.get_state()
+    assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+
+
+def test_update_mixed(Ukf):
+    B = 64
+    g, o = both(Ukf, 0, B)
+    kinds = (np.arange(B) % 10 - 1).astype(np.int8)  # -1 .. 8
+    mu3 = np.zeros((B, 3))
+    cov33 = np.tile(np.eye(3), (B, 1, 1))
+    for b in range(B):
+        k = int(kinds[b])
+        if k < 0:
+            continue
+        z, R = syn.pose_measurement(k, B, 5)
+        m = z.shape[1]
+        mu3[b, :m] = z[b]
+        cov33[b, :m, :m] = R
+    for x in (g, o):
+        x.predict_dt(0.01)
+        x.update_mixed(kinds, mu3, cov33)
+    P.assert_parity(0, g.get_state(), o.get_state(), what="mixed kinds")
+
+
+# ---- guards (UnscentedKalmanFilter.hpp:83-125, :142-147) ----------------------------------------
+
+def test_time_guards(Ukf):
+    B = 6
+    g, o = both(Ukf, 0, B)
+    dt = np.array([-1.0, 0.0, 1e-10, 0.01, 5.0, 0.02])
+    for x in (g, o):
+        x.set_time_bounds(1e-9, 1.0)
+        x.predict_dt(dt)
+    sg, so = g.get_status(), o.get_status()
+    assert np.array_equal(sg, so)
+    assert sg[0] == 1 and sg[4] == 2 and sg[1] == 0 and sg[2] == 0
+    P.assert_parity(0, g.get_state(), o.get_state(), what="time guards")
+    n, bits = g.status_summary()
+    assert n == 2 and bits == 3
+
+
+def test_sample_time_latching(Ukf):
+    B = 5
+    g, o = both(Ukf, 0, B)
+    seq = [syn.T0_US, syn.T0_US + 1000, syn.T0_US + 1000, syn.T0_US + 500, syn.T0_US + 3000]
+    for ts in seq:
+        for x in (g, o):
+            x.predict_time(np.array([ts], np.int64))
+    assert np.array_equal(g.get_last_time(), o.get_last_time())
+    assert np.array_equal(g.get_status(), o.get_status())
+    assert (g.get_status() == 1).all()  # one negative delta each
+    P.assert_parity(0, g.get_state(), o.get_state(), what="sample-time path")
+
+
+def test_nonfinite_measurement_orientation(Ukf):
+    B = 4
+    g, o = both(Ukf, 1, B)
+    z, R = syn.orientation_velocity(B, 1)
+    z[1, 0] = np.nan
+    gyro, acc = syn.orientation_imu(B, 1)
+    gyro[2, 1] = np.inf
+    for x in (g, o):
+        x.set_rotation_rate(gyro)
+        x.set_acceleration(acc)
+        x.predict_dt(syn.DT)
+        x.update(9, z, R)
+    assert np.array_equal(g.get_status(), o.get_status())
+    assert g.get_status()[1] == 4 and g.get_status()[2] == 4
+    P.assert_parity(1, g.get_state(), o.get_state(), what="non-finite measurement")
+
+
+def test_not_initialized_and_wrong_kind(Ukf):
+    from slam_pose_estimation_b200 import UkfbError
+
+    x = Ukf(0, 4)
+    with pytest.raises(UkfbError) as e:
+        x.get_state()
+    assert e.value.code == -2
+    mu, sg = syn.pose_initial(4)
+    x.initialize(mu, sg)
+    with pytest.raises(UkfbError) as e:
+        x.update(9, np.zeros((4, 3)), np.eye(3))
+    assert e.value.code == -1
+
+
+def test_reinitialize_resets_time(Ukf):
+    B = 3
+    g, o = both(Ukf, 0, B)
+    mu, sg = syn.pose_initial(B)
+    for x in (g, o):
+        x.predict_time(np.array([syn.T0_US], np.int64))
+        x.initialize(mu, sg)
+    assert (g.get_last_time() == 0).all() and np.array_equal(g.get_last_time(), o.get_last_time())
+
+
+def test_process_noise_roundtrip_and_per_filter(Ukf):
+    B = 9
+    g, o = both(Ukf, 0, B)
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(B, 12, 12)) * 0.01
+    Q = A @ np.transpose(A, (0, 2, 1))
+    for x in (g, o):
+        x.set_process_noise(Q)
+        x.predict_dt(0.1)
+    assert np.allclose(g.get_process_noise(per_filter=True), Q, rtol=0, atol=0)
+    P.assert_parity(0, g.get_state(), o.get_state(), what="per-filter Q")
+
+
+# ---- streams ---------------------------------------------------------------------------------------
+
+def test_pose_c3_200_steps(Ukf):
+    B = 256
+    g, o = both(Ukf, 0, B)
+    P.run_pose_c3(g, B, 200)
+    P.run_pose_c3(o, B, 200)
+    em, es = P.assert_parity(0, g.get_state(), o.get_state(), what="C3 200 steps")
+    assert np.array_equal(g.get_status(), o.get_status()) and not g.get_status().any()
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+def test_orientation_c1_10k_steps(Ukf):
+    """BASELINE config 1: a single OrientationUKF on a 1 kHz IMU stream for 10k steps."""
+    g, o = both(Ukf, 1, 1)
+    P.run_ori_c1(g, 1, 10_000)
+    P.run_ori_c1(o, 1, 10_000)
+    P.assert_parity(1, g.get_state(), o.get_state(), what="C1 10k steps")
+    assert not g.get_status().any()
+
+
+def test_pose_10k_steps_run_dev(Ukf):
+    """10k fused predict+update ticks advanced on-chip K at a time (ukfb_run_dev) vs the oracle."""
+    import torch
+
+    B, steps, K = 8, 10_000, 100
+    g, o = both(Ukf, 0, B)
+    dev = torch.device("cuda:0")
+    d_dt = torch.full((K,), syn.DT, dtype=torch.float64, device=dev)
+    kinds = np.full(K, 8, np.int8)
+    R = np.eye(3) * syn.SIGMA_GYRO**2
+    d_R = torch.from_numpy(np.tile(R, (K, 1, 1))).to(dev)
+    for c in range(steps // K):
+        zs = np.stack([syn.pose_measurement(8, B, c * K + j + 1)[0] for j in range(K)])
+        d_z = torch.from_numpy(zs).to(dev)
+        g.run_dev(K, d_dt, False, kinds, d_z, d_R, False)
+        g.synchronize()
+        for j in range(K):
+            o.step(syn.DT, 8, zs[j], R)
+    P.assert_parity(0, g.get_state(), o.get_state(), what="10k steps run_dev")
+    assert not g.get_status().any()
+
+
+def test_shard_invariance(Ukf):
+    """a filter's result does not depend on the batch it is in or its position in it (section 8e)"""
+    B = 101
+    whole = P.make_pose(Ukf, B)
+    P.run_pose_c3(whole, B, 12)
+    mu_w, sg_w = whole.get_state()
+    lo, hi = 37, 64
+    part = P.make_pose(Ukf, hi - lo, first=lo)
+    P.run_pose_c3(part, hi - lo, 12, first=lo)
+    mu_p, sg_p = part.get_state()
+    assert np.array_equal(mu_w[lo:hi], mu_p) and np.array_equal(sg_w[lo:hi], sg_p)
+
+
+def test_large_batch_invariants(Ukf):
+    """full BASELINE size (65,536 PoseUKF): finite, symmetric PSD, unit quaternions; a strided sample matches the oracle."""
+    B = 65_536
+    g = P.make_pose(Ukf, B)
+    P.run_pose_c3(g, B, 10)
+    mu, sg = g.get_state()
+    assert np.isfinite(mu).all() and np.isfinite(sg).all()
+    assert np.abs(np.linalg.norm(mu[:, 3:7], axis=1) - 1.0).max() < 1e-12
+    assert P.spd_ok(sg[::257])
+    assert not g.get_status().any()
+    idx = np.arange(0, B, 4099)
+    for i in idx:
+        o = P.make_pose(OracleBatch, 1, first=int(i))
+        P.run_pose_c3(o, 1, 10, first=int(i))
+        P.assert_parity(0, (mu[i:i + 1], sg[i:i + 1]), o.get_state(), what=f"filter {i} of 65536")
