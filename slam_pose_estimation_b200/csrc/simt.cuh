@@ -1,15 +1,19 @@
 /*
- * simt.cuh -- the few macros the device code is written against.
+ * simt.cuh -- the few macros and warp primitives the device code is written against.
  *
- * Product build: nvcc, sm_100a; everything maps to the CUDA builtins.
+ * Product build: nvcc, sm_100a; everything maps to the CUDA builtins / PTX:
+ *   warp_shfl        shfl.sync.idx (two 32-bit halves of a double)
+ *   warp_dmma        mma.sync.aligned.m8n8k4.row.col.f64 (FP64 tensor-core tile, SASS DMMA.8x8x4)
+ *   rcp_seed/rsq_seed  rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64 (MUFU.RCP64H / MUFU.RSQ64H)
  *
  * UKFB_SIMT_EMU build (tests/simt_emu only, never linked into the product library):
  * the same kernel source is compiled by g++ and each CUDA thread of a block is run as
- * a real host thread, with __syncwarp()/__syncthreads() as barriers.  It exists so
- * that the warp-cooperative indexing (shared-memory maps, tile ownership, hazards)
- * can be exercised under -fsanitize=address,undefined in the GPU-less build
- * container.  It is a development/test harness, not a CPU fallback: the C ABI
- * (ukf_batch.cu) is CUDA-only and fails loudly without a device.
+ * a real host thread, with __syncwarp() as a barrier and the warp primitives emulated
+ * through a per-warp exchange buffer.  It exists so that the warp-cooperative indexing
+ * (shared-memory maps, tile ownership, hazards) can be exercised under
+ * -fsanitize=address,undefined in the GPU-less build container.  It is a
+ * development/test harness, not a CPU fallback: the C ABI (ukf_batch.cu) is CUDA-only
+ * and fails loudly without a device.
  */
 #ifndef UKFB_SIMT_CUH
 #define UKFB_SIMT_CUH
@@ -31,15 +35,61 @@
 #define UKFB_NOUNROLL _Pragma("unroll 1")
 
 namespace ukfb {
-UKFB_HD void ukfb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+
+UKFB_D void ukfb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+
+/* value of `v` held by lane `src` (all 32 lanes must call) */
+UKFB_D double warp_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+/* C(8x8) += A(8x4) * B(4x8) on the FP64 tensor-core path.  Fragment layout (PTX m8n8k4.f64):
+ * lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4)] and C[l/4][2*(l%4)+1]. */
+UKFB_D void warp_dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
+
+/* 1/x and 1/sqrt(x) for normal, positive-or-negative (rcp) / positive (rsq) x: hardware seed
+ * (about 20 bits) refined by Newton steps in FMA arithmetic; error below 1 ulp, no
+ * special-case branches (callers guarantee the operand range). */
+UKFB_D double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+/* s = sqrt(x), r = 1/sqrt(x) (Goldschmidt from the hardware seed, one correction of s) */
+UKFB_D void fast_sqrt_rsqrt(double x, double& s, double& r)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double e = fma(-g, h, 0.5);
+    g = fma(g, e, g), h = fma(h, e, h);
+    e = fma(-g, h, 0.5);
+    g = fma(g, e, g), h = fma(h, e, h);
+    e = fma(-g, h, 0.5);
+    g = fma(g, e, g), h = fma(h, e, h);
+    const double d = fma(-g, g, x);
+    s = fma(d, h, g);
+    r = h + h;
+}
+
+} /* namespace ukfb */
 
 #else /* ---------------------------- host emulation ---------------------------- */
 
 #include <cmath>
 #include <cstdint>
 
-#include "simt_emu_rt.hpp" /* tests/simt_emu: threadIdx, __syncwarp, atomicAdd, ... */
+#include "simt_emu_rt.hpp" /* tests/simt_emu: threadIdx, __syncwarp, atomicAdd, warp exchange buffer */
 
 #define UKFB_HD inline
 #define UKFB_D inline
@@ -53,14 +103,45 @@ UKFB_HD void ukfb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 
 namespace ukfb {
 using std::atan;
-using std::sqrt;
 using std::fabs;
+using std::fma;
+using std::sqrt;
 inline void ukfb_sincos(double x, double* s, double* c)
 {
     *s = std::sin(x);
     *c = std::cos(x);
 }
+inline double warp_shfl(double v, int src)
+{
+    double* x = ::simt_emu::warp_xchg();
+    const int lane = threadIdx.x & 31;
+    x[lane] = v;
+    __syncwarp();
+    const double r = x[src & 31];
+    __syncwarp();
+    return r;
 }
+inline void warp_dmma(double& c0, double& c1, double a, double b)
+{
+    double* x = ::simt_emu::warp_xchg();
+    const int lane = threadIdx.x & 31;
+    x[lane] = a;
+    x[32 + lane] = b;
+    __syncwarp();
+    const int row = lane >> 2, col = 2 * (lane & 3);
+    for (int k = 0; k < 4; ++k) {
+        c0 += x[row * 4 + k] * x[32 + col * 4 + k];
+        c1 += x[row * 4 + k] * x[32 + (col + 1) * 4 + k];
+    }
+    __syncwarp();
+}
+inline double fast_rcp(double x) { return 1.0 / x; }
+inline void fast_sqrt_rsqrt(double x, double& s, double& r)
+{
+    s = std::sqrt(x);
+    r = 1.0 / s;
+}
+}  // namespace ukfb
 
 #endif
 

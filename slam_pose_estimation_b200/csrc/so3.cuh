@@ -5,6 +5,15 @@
  * quaternion operations the reference calls (PoseUKF.cpp:80-81,135,182;
  * OrientationUKF.cpp:19-22,38,81); conventions come from include/ukfb_constants.h.
  * Quaternions are double[4] stored x,y,z,w.
+ *
+ * exp and log are the hot special functions of the filter (about 100 exp and 125 log
+ * per predict+update).  On the GPU the common case -- rotation vectors of at most about
+ * one radian in exp, relative rotations of at most about 33 degrees in log -- is
+ * evaluated by near-minimax polynomials in the SQUARED argument (tools/gen_poly.py;
+ * truncation below 1e-19), which needs no square root, no sin/cos/atan call and a
+ * single reciprocal.  They evaluate the same functions as MTK's expressions
+ * (cos x, sin x / x, 2 atan(|v|/w)/|v|) to within an ulp or two, well inside the
+ * 1e-9 parity tolerance; outside that range the literal MTK expressions are used.
  */
 #ifndef UKFB_SO3_CUH
 #define UKFB_SO3_CUH
@@ -15,7 +24,7 @@
 namespace ukfb {
 
 /* r = a * b (Hamilton product).  r may alias neither a nor b. */
-UKFB_HD void quat_mul(const double* a, const double* b, double* r)
+UKFB_D void quat_mul(const double* a, const double* b, double* r)
 {
     r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
     r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
@@ -24,7 +33,7 @@ UKFB_HD void quat_mul(const double* a, const double* b, double* r)
 }
 
 /* r = a * conj(b) */
-UKFB_HD void quat_mul_conj(const double* a, const double* b, double* r)
+UKFB_D void quat_mul_conj(const double* a, const double* b, double* r)
 {
     r[3] = a[3] * b[3] + a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
     r[0] = -a[3] * b[0] + a[0] * b[3] - a[1] * b[2] + a[2] * b[1];
@@ -33,7 +42,7 @@ UKFB_HD void quat_mul_conj(const double* a, const double* b, double* r)
 }
 
 /* r = conj(a) * b */
-UKFB_HD void quat_conj_mul(const double* a, const double* b, double* r)
+UKFB_D void quat_conj_mul(const double* a, const double* b, double* r)
 {
     r[3] = a[3] * b[3] + a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
     r[0] = a[3] * b[0] - a[0] * b[3] - a[1] * b[2] + a[2] * b[1];
@@ -42,7 +51,7 @@ UKFB_HD void quat_conj_mul(const double* a, const double* b, double* r)
 }
 
 /* out = q * v, Eigen _transformVector: uv = 2 (q.vec x v); v + w uv + q.vec x uv */
-UKFB_HD void quat_rotate(const double* q, const double* v, double* out)
+UKFB_D void quat_rotate(const double* q, const double* v, double* out)
 {
     double ux = q[1] * v[2] - q[2] * v[1];
     double uy = q[2] * v[0] - q[0] * v[2];
@@ -56,7 +65,7 @@ UKFB_HD void quat_rotate(const double* q, const double* v, double* out)
 }
 
 /* out = q.inverse() * v with Eigen's inverse() = conj / squaredNorm (OrientationUKF.cpp:38) */
-UKFB_HD void quat_inv_rotate(const double* q, const double* v, double* out)
+UKFB_D void quat_inv_rotate(const double* q, const double* v, double* out)
 {
     const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     const double r = 1.0 / n2;
@@ -65,7 +74,7 @@ UKFB_HD void quat_inv_rotate(const double* q, const double* v, double* out)
 }
 
 /* Eigen toRotationMatrix, row-major */
-UKFB_HD void quat_matrix(const double* q, double* R)
+UKFB_D void quat_matrix(const double* q, double* R)
 {
     const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
     const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
@@ -82,8 +91,45 @@ UKFB_HD void quat_matrix(const double* q, double* R)
     R[8] = 1.0 - (txx + tyy);
 }
 
-/* MTK cos_sinc_sqrt: (cos sqrt(x2), sinc sqrt(x2)); Taylor pair below 2^-13. */
-UKFB_HD void cos_sinc_sqrt(double x2, double& c, double& sinc)
+/* ---- polynomial kernels (tools/gen_poly.py), Estrin form for instruction-level parallelism ---- */
+constexpr double SO3_EXP_FAST_X2 = 0.25; /* (half angle)^2 bound of the cos/sinc polynomials */
+constexpr double SO3_LOG_FAST_U = 0.09;  /* (|q.vec| / w)^2 bound of the atan polynomial */
+
+UKFB_D double poly6(double v, double c0, double c1, double c2, double c3, double c4, double c5, double c6)
+{
+    const double v2 = v * v;
+    const double p01 = fma(c1, v, c0), p23 = fma(c3, v, c2), p45 = fma(c5, v, c4);
+    const double q0 = fma(p23, v2, p01), q1 = fma(c6, v2, p45);
+    return fma(q1, v2 * v2, q0);
+}
+
+UKFB_D double cos_sqrt_poly(double v)
+{
+    return poly6(v, 1.0, -0x1.fffffffffffffp-2, 0x1.5555555555421p-5, -0x1.6c16c16bdd04ep-10, 0x1.a01a00fb1bc6fp-16,
+                 -0x1.27e40964b47d4p-22, 0x1.1d8d32755f8fbp-29);
+}
+
+UKFB_D double sinc_sqrt_poly(double v)
+{
+    return poly6(v, 1.0, -0x1.5555555555555p-3, 0x1.11111111110bfp-7, -0x1.a01a019ffb337p-13, 0x1.71de39fd64b1fp-19,
+                 -0x1.ae63543245d1fp-26, 0x1.5fac6e0083f22p-33);
+}
+
+/* atan(t)/t as a function of u = t*t, u <= 0.09 */
+UKFB_D double atan_over_t_poly(double u)
+{
+    const double u2 = u * u, u4 = u2 * u2;
+    const double p01 = fma(-0x1.5555555555500p-2, u, 1.0);
+    const double p23 = fma(-0x1.2492491c0c582p-3, u, 0x1.999999998a517p-3);
+    const double p45 = fma(-0x1.745c4ca68d45dp-4, u, 0x1.c71c6cf04ff82p-4);
+    const double p67 = fma(-0x1.0fcd05c851591p-4, u, 0x1.3aff6b481f0f7p-4);
+    const double p89 = fma(-0x1.229f36308eeefp-5, u, 0x1.c90783e417298p-5);
+    const double q0 = fma(p23, u2, p01), q1 = fma(p67, u2, p45);
+    return fma(fma(p89, u4, q1), u4, q0);
+}
+
+/* MTK cos_sinc_sqrt: (cos sqrt(x2), sinc sqrt(x2)), the literal expressions (Taylor pair below 2^-13). */
+UKFB_D void cos_sinc_sqrt(double x2, double& c, double& sinc)
 {
     if (x2 >= UKFB_TAYLOR_N_BOUND) {
         const double x = sqrt(x2);
@@ -111,13 +157,19 @@ UKFB_HD void cos_sinc_sqrt(double x2, double& c, double& sinc)
     }
 }
 
-/* MTK::SO3::exp(v, scale) */
-UKFB_HD void so3_exp(const double* v, double scale, double* q)
+/* MTK::SO3::exp(v, scale): w = cos(|v| scale/2), vec = sinc(|v| scale/2) (scale/2) v */
+UKFB_D void so3_exp(const double* v, double scale, double* q)
 {
     const double half = scale / 2.0;
     const double norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double x2 = half * half * norm2;
     double c, sinc;
-    cos_sinc_sqrt(half * half * norm2, c, sinc);
+    if (x2 <= SO3_EXP_FAST_X2) {
+        c = cos_sqrt_poly(x2);
+        sinc = sinc_sqrt_poly(x2);
+    } else {
+        cos_sinc_sqrt(x2, c, sinc);
+    }
     const double mult = sinc * half;
     q[0] = mult * v[0];
     q[1] = mult * v[1];
@@ -125,19 +177,29 @@ UKFB_HD void so3_exp(const double* v, double scale, double* q)
     q[3] = c;
 }
 
-/* MTK::SO3::log(q) = (2/nv) atan(nv/w) q.vec, nv floored at MTK::tolerance */
-UKFB_HD void so3_log(const double* q, double* out)
+/* MTK::SO3::log(q) = (2/nv) atan(nv/w) q.vec, nv = |q.vec| floored at MTK::tolerance.
+ * Fast path: (2/nv) atan(nv/w) = 2 P((nv/w)^2) / w. */
+UKFB_D void so3_log(const double* q, double* out)
 {
-    double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-    if (nv < UKFB_MTK_TOLERANCE) nv = UKFB_MTK_TOLERANCE;
-    const double s = 2.0 / nv * atan(nv / q[3]);
+    const double nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const double w = q[3];
+    double s;
+    if (nv2 <= SO3_LOG_FAST_U * (w * w)) {
+        const double rw = fast_rcp(w);
+        const double t = nv2 * rw;
+        s = (2.0 * rw) * atan_over_t_poly(t * rw);
+    } else {
+        double nv = sqrt(nv2);
+        if (nv < UKFB_MTK_TOLERANCE) nv = UKFB_MTK_TOLERANCE;
+        s = 2.0 / nv * atan(nv / w);
+    }
     out[0] = s * q[0];
     out[1] = s * q[1];
     out[2] = s * q[2];
 }
 
 /* q <- q [+] v*scale */
-UKFB_HD void so3_boxplus(double* q, const double* v, double scale)
+UKFB_D void so3_boxplus(double* q, const double* v, double scale)
 {
     double e[4], r[4];
     so3_exp(v, scale, e);
@@ -150,7 +212,7 @@ UKFB_HD void so3_boxplus(double* q, const double* v, double scale)
 }
 
 /* res = q [-] o */
-UKFB_HD void so3_boxminus(const double* q, const double* o, double* res)
+UKFB_D void so3_boxminus(const double* q, const double* o, double* res)
 {
     double r[4];
 #if UKFB_SO3_BOXPLUS_LEFT

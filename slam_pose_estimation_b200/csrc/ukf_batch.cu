@@ -4,8 +4,8 @@
  * call fails with UKFB_ERR_CUDA when no usable device is present.
  *
  * One handle = B filters of one kind on one device, one stream.  Filter records live in
- * HBM as fixed-size rows (PoseF::REC / OriF::REC doubles: mu padded to 16, then the
- * packed lower triangle of sigma), so the record of a group of filters is one
+ * HBM as fixed-size rows (PoseF::REC = 91 / OriF::REC = 105 doubles: mu, then the packed
+ * lower triangle of sigma), so the record of a group of filters is one
  * contiguous, coalesced read for the warp that owns the group.
  */
 #include <cuda_runtime.h>
@@ -46,7 +46,7 @@ struct ukfb_handle {
     int kind = 0, device = 0;
     long long B = 0;
     int n = 0, MU = 0, LP = 0, REC = 0;
-    int G = 4; /* filters per warp */
+    int G = 8, WPB = 4, MINB = 4; /* launch shape: filters per warp, warps per block, resident blocks per SM */
     cudaStream_t stream = nullptr;
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
@@ -117,8 +117,8 @@ __global__ void pack_kernel(double* __restrict__ state, const double* __restrict
         double v = 0.0;
         if (k < MU)
             v = mu[b * MU + k];
-        else if (k >= REC_MU_PAD && k < REC_MU_PAD + LP) {
-            const int e = k - REC_MU_PAD;
+        else {
+            const int e = k - MU;
             int r = 0;
             while ((r + 1) * (r + 2) / 2 <= e) ++r;
             const int c = e - r * (r + 1) / 2;
@@ -138,7 +138,7 @@ __global__ void unpack_mu_kernel(const double* __restrict__ state, double* __res
     }
 }
 
-__global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __restrict__ sigma, long long B, int n, int REC)
+__global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __restrict__ sigma, long long B, int n, int MU, int REC)
 {
     const long long total = B * n * n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -150,7 +150,7 @@ __global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __
             r = c;
             c = t;
         }
-        sigma[i] = state[b * REC + REC_MU_PAD + tri(r, c)];
+        sigma[i] = state[b * REC + MU + tri(r, c)];
     }
 }
 
@@ -290,40 +290,40 @@ static inline int grid_for(long long count, int block = 256)
 }
 
 /* ---- step launch ------------------------------------------------------------------------------ */
-template <class F, int G>
+template <class F, int G, int WPB, int MINB>
 static cudaError_t launch_step_t(const ukfb_handle* h, const StepParams& p)
 {
     static bool attr_set[64] = {};
     const size_t smem = sizeof(double) * WPB * Smem<F, G>::TOTAL;
     if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(ukf_step_kernel<F, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(ukf_step_kernel<F, G, WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         attr_set[h->device & 63] = true;
     }
     const long long per_block = (long long)WPB * G;
     const long long grid = (p.B + per_block - 1) / per_block;
-    ukf_step_kernel<F, G><<<unsigned(grid), WPB * 32, smem, h->stream>>>(p);
+    ukf_step_kernel<F, G, WPB, MINB><<<unsigned(grid), WPB * 32, smem, h->stream>>>(p);
     return cudaGetLastError();
+}
+
+/* launch shapes: G filters per warp (32/G lanes per filter in the Cholesky phases), WPB warps per block */
+template <class F>
+static cudaError_t launch_step_f(const ukfb_handle* h, const StepParams& p)
+{
+    switch (h->G * 100 + h->WPB * 10 + h->MINB) {
+        case 443: return launch_step_t<F, 4, 4, 3>(h, p);
+        case 444: return launch_step_t<F, 4, 4, 4>(h, p);
+        case 1642: return launch_step_t<F, 16, 4, 2>(h, p);
+        case 1652: return launch_step_t<F, 16, 5, 2>(h, p);
+        case 842: return launch_step_t<F, 8, 4, 2>(h, p);
+        case 843: return launch_step_t<F, 8, 4, 3>(h, p);
+        default: return launch_step_t<F, 8, 4, 4>(h, p);
+    }
 }
 
 static int launch_step(ukfb_handle* h, const StepParams& p)
 {
-    cudaError_t e;
-    if (h->kind == UKFB_POSE) {
-        switch (h->G) {
-            case 1: e = launch_step_t<PoseF, 1>(h, p); break;
-            case 2: e = launch_step_t<PoseF, 2>(h, p); break;
-            case 8: e = launch_step_t<PoseF, 8>(h, p); break;
-            default: e = launch_step_t<PoseF, 4>(h, p); break;
-        }
-    } else {
-        switch (h->G) {
-            case 1: e = launch_step_t<OriF, 1>(h, p); break;
-            case 2: e = launch_step_t<OriF, 2>(h, p); break;
-            case 8: e = launch_step_t<OriF, 8>(h, p); break;
-            default: e = launch_step_t<OriF, 4>(h, p); break;
-        }
-    }
+    const cudaError_t e = h->kind == UKFB_POSE ? launch_step_f<PoseF>(h, p) : launch_step_f<OriF>(h, p);
     if (e != cudaSuccess) return fail(UKFB_ERR_CUDA, "ukf_step_kernel launch: %s", cudaGetErrorString(e));
     h->launches++;
     return UKFB_OK;
@@ -389,8 +389,10 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         h->n = OriF::N, h->MU = OriF::MU, h->LP = OriF::LP, h->REC = OriF::REC;
     if (const char* g = getenv("UKFB_GROUP")) {
         const int G = atoi(g);
-        if (G == 1 || G == 2 || G == 4 || G == 8) h->G = G;
+        if (G == 4 || G == 8 || G == 16) h->G = G;
     }
+    if (const char* g = getenv("UKFB_WPB")) h->WPB = atoi(g);
+    if (const char* g = getenv("UKFB_MINB")) h->MINB = atoi(g);
     Bind bind_(h);
     if (!bind_.ok) {
         delete h;
@@ -499,7 +501,7 @@ extern "C" int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma)
     CHECK_H(h);
     NEED_INIT(h);
     if (d_mu) unpack_mu_kernel<<<grid_for(h->B * h->MU), 256, 0, h->stream>>>(h->state, d_mu, h->B, h->MU, h->REC);
-    if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->REC);
+    if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->MU, h->REC);
     CU(cudaGetLastError());
     return UKFB_OK;
 }

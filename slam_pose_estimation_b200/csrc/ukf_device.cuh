@@ -9,14 +9,20 @@
  *   time guards          UnscentedKalmanFilter.hpp:83-125
  *   ukf predict / update / apply_delta   (ukfom/ukf.hpp, App. A.2-A.4)
  *
- * Mapping: one warp owns a group of G filters.  Work that is
- * serial per filter (the Cholesky factorisations) runs LANE-PER-FILTER so the
- * sqrt / reciprocal chains of G filters share one warp instruction; work that is
- * parallel over the 2n+1 sigma points (boxplus, models, boxminus, the manifold
- * mean) runs LANE-PER-SIGMA-POINT, one filter at a time; the covariance
- * contractions run lane-per-2x2-tile of the lower triangle.  State and covariance
- * of the group live in shared memory between phases; HBM sees one coalesced read
- * and one coalesced write of each filter record per launch.
+ * Mapping.  One warp owns a group of G filters whose records stay in
+ * shared memory for the whole launch (K ticks).  Three thread mappings alternate:
+ *   - T = 32/G LANES PER FILTER for the Cholesky factorisations: each lane keeps its rows
+ *     of the factor in registers, the pivot row travels by warp shuffle, nothing touches
+ *     shared memory until the factor is complete (so a failed factorisation leaves the
+ *     covariance intact, as the reference's early return does);
+ *   - ONE LANE PER SIGMA POINT (25 / 27 of 32 lanes), one filter at a time, for boxplus,
+ *     the process / measurement models, boxminus and the manifold mean;
+ *   - the FP64 TENSOR-CORE path (mma.sync m8n8k4, SASS DMMA) for the contractions over the
+ *     sigma points: the deviations are written once as a [component][point] matrix and the
+ *     covariance, cross-covariance and innovation covariance come out of 14-21 DMMA tiles
+ *     instead of ~100 shared-memory-bound FMA rounds.
+ * HBM sees one coalesced read and one coalesced write of each filter record per launch
+ * (plus one L2-resident spill of the predicted covariance inside an update).
  */
 #ifndef UKFB_DEVICE_CUH
 #define UKFB_DEVICE_CUH
@@ -30,14 +36,13 @@ namespace ukfb {
 
 struct PoseF { /* PoseWithVelocity.hpp:18-23 */
     static constexpr int KIND = 0;
-    static constexpr int N = UKFB_POSE_DOF;   /* tangent dimension */
-    static constexpr int MU = UKFB_POSE_MU;   /* stored state size */
-    static constexpr int NS = 2 * N + 1;      /* sigma points */
-    static constexpr int LP = N * (N + 1) / 2;/* packed lower triangle */
-    static constexpr int ROT = 3;             /* offset of the SO(3) block (tangent and mu) */
-    static constexpr int REC = 96;            /* HBM record: mu padded to 16, then packed sigma, padded to 16 */
-    static constexpr int DS = 15;             /* row stride of the deviation matrix (odd: conflict-free) */
-    static constexpr int QB0 = 0, QB1 = 3;    /* rotated blocks of Q: position, orientation (PoseUKF.cpp:184-185) */
+    static constexpr int N = UKFB_POSE_DOF;    /* tangent dimension */
+    static constexpr int MU = UKFB_POSE_MU;    /* stored state size */
+    static constexpr int NS = 2 * N + 1;       /* sigma points */
+    static constexpr int LP = N * (N + 1) / 2; /* packed lower triangle */
+    static constexpr int ROT = 3;              /* offset of the SO(3) block (tangent and mu) */
+    static constexpr int REC = MU + LP;        /* HBM record: mu, then packed sigma (91 doubles, odd) */
+    static constexpr int QB0 = 0, QB1 = 3;     /* rotated blocks of Q: position, orientation (PoseUKF.cpp:184-185) */
 };
 
 struct OriF { /* OrientationState.hpp:20-26 */
@@ -47,12 +52,9 @@ struct OriF { /* OrientationState.hpp:20-26 */
     static constexpr int NS = 2 * N + 1;
     static constexpr int LP = N * (N + 1) / 2;
     static constexpr int ROT = 0;
-    static constexpr int REC = 112;
-    static constexpr int DS = 17;
-    static constexpr int QB0 = 0, QB1 = 3;    /* orientation, velocity (OrientationUKF.cpp:84-85) */
+    static constexpr int REC = MU + LP;        /* 105 doubles, odd */
+    static constexpr int QB0 = 0, QB1 = 3;     /* orientation, velocity (OrientationUKF.cpp:84-85) */
 };
-
-constexpr int REC_MU_PAD = 16; /* sigma starts at this offset inside an HBM record */
 
 template <class F>
 UKFB_HD constexpr int mu_of(int t) { return t < F::ROT ? t : t + 1; } /* vector tangent index -> mu index */
@@ -61,28 +63,30 @@ UKFB_HD constexpr int mu_of(int t) { return t < F::ROT ? t : t + 1; } /* vector 
 UKFB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 /* ---- shared-memory layout (doubles) ------------------------------------------- */
+constexpr int DT_ROWS = 16; /* deviation matrix: tangent components (<= 13) then measurement components (3) */
+constexpr int DT_COLS = 28; /* sigma points padded to a multiple of the DMMA k = 4 */
+constexpr int DT_LD = 36;   /* = 4 mod 16: the DMMA fragment loads hit 16 distinct 8-byte banks */
+
 template <class F, int G>
 struct Smem {
-    /* per filter of the group */
-    static constexpr int OFF_A = 0;                /* sigma, packed lower */
-    static constexpr int OFF_B = F::LP;            /* Cholesky factor / updated sigma, packed lower */
-    static constexpr int OFF_MU = 2 * F::LP;       /* mu */
-    static constexpr int OFF_DELTA = OFF_MU + F::MU;
-    static constexpr int OFF_IMU = OFF_DELTA + F::N; /* stored acceleration [0:3], rotation rate [3:6] */
-    static constexpr int FREC_RAW = OFF_IMU + 6;
-    static constexpr int FREC = FREC_RAW | 1;      /* odd stride: lane-per-filter accesses are conflict-free */
+    /* per filter of the group; [mu | sigma] is a straight copy of the HBM record */
+    static constexpr int OFF_MU = 0;
+    static constexpr int OFF_SIG = F::MU;               /* sigma, packed lower -- or its Cholesky factor */
+    static constexpr int OFF_DELTA = OFF_SIG + F::LP;   /* K * innovation */
+    static constexpr int OFF_IMU = OFF_DELTA + F::N;    /* stored acceleration [0:3], rotation rate [3:6] */
+    static constexpr int OFF_DT = OFF_IMU + 6;          /* this tick's delta time */
+    static constexpr int FS = (OFF_DT + 1) | 1;         /* odd stride: lane-per-filter accesses are conflict-free */
     /* per warp scratch */
-    static constexpr int OFF_D = G * FREC;         /* deviations: 32 rows x DS ([dx | dz]) */
-    static constexpr int OFF_SXZ = OFF_D + 32 * F::DS;
+    static constexpr int OFF_D = G * FS + ((G * FS) & 1); /* deviation matrix [DT_ROWS][DT_LD] */
+    static constexpr int OFF_SXZ = OFF_D + DT_ROWS * DT_LD;
     static constexpr int OFF_KM = OFF_SXZ + 40;
     static constexpr int OFF_KS = OFF_KM + 40;
     static constexpr int OFF_SM = OFF_KS + 40;     /* S, 3x3 */
     static constexpr int OFF_MD = OFF_SM + 10;     /* mean delta broadcast */
     static constexpr int OFF_BC = OFF_MD + 16;     /* state broadcast */
     static constexpr int OFF_QR = OFF_BC + 16;     /* two rotated 3x3 blocks of Q */
-    static constexpr int OFF_DT = OFF_QR + 18;     /* per filter dt */
-    static constexpr int OFF_CTL = OFF_DT + G;     /* per filter: flags, kind (ints, 2 per double slot) */
-    static constexpr int TOTAL_RAW = OFF_CTL + G + 4; /* + 8 ints: mean-pass histogram */
+    static constexpr int OFF_CTL = OFF_QR + 18;    /* ints: flags[G], kind[G], status[G], mean-pass histogram[8] */
+    static constexpr int TOTAL_RAW = OFF_CTL + (3 * G + 8 + 1) / 2;
     static constexpr int TOTAL = (TOTAL_RAW + 1) & ~1;
 };
 
@@ -164,28 +168,69 @@ UKFB_D void state_boxminus(const double* x, const double* o, double* res)
     so3_boxminus(x + F::ROT, o + F::ROT, res + F::ROT);
 }
 
-/* ---- lane-per-filter Cholesky, packed lower, src may alias dst ---------------------- */
-/* LAPACK dpotf2('L') order: dot-product update, sqrt, scale by the reciprocal. */
-template <class F>
-UKFB_D bool cholesky_packed(const double* src, double* dst)
+/* ---- Cholesky, T lanes per filter, rows in registers -------------------------------------- */
+/* LAPACK dpotf2('L') order per column: dot-product update of the pivot, sqrt, update of the
+ * rows below scaled by the reciprocal of the pivot.  Lane t of a filter's T lanes owns rows
+ * i = r*T + t.  `sig` (packed lower, shared memory) is read at entry and overwritten by the
+ * factor only when every pivot was positive and finite; all 32 lanes must call (shuffles). */
+template <class F, int T>
+UKFB_D bool cholesky_rows(double* sig, int lane, bool active)
 {
-    UKFB_NOUNROLL
-    for (int j = 0; j < F::N; ++j) {
-        const int jj = tri(j, 0);
-        double ajj = src[jj + j];
-        for (int k = 0; k < j; ++k) ajj -= dst[jj + k] * dst[jj + k];
-        if (!(ajj > 0.0) || !(ajj < 1.0e300)) return false;
-        const double d = sqrt(ajj);
-        dst[jj + j] = d;
-        const double r = 1.0 / d;
-        for (int i = j + 1; i < F::N; ++i) {
-            const int ii = tri(i, 0);
-            double s = src[ii + j];
-            for (int k = 0; k < j; ++k) s -= dst[ii + k] * dst[jj + k];
-            dst[ii + j] = s * r;
+    constexpr int N = F::N, R = (N + T - 1) / T;
+    const int t = lane & (T - 1);
+    double a[R][N];
+    UKFB_UNROLL
+    for (int r = 0; r < R; ++r) {
+        const int i = r * T + t;
+        UKFB_UNROLL
+        for (int k = 0; k < N; ++k) {
+            if (k > r * T + T - 1) continue; /* beyond the longest row of this register row */
+            const bool in = i < N && k <= i;
+            a[r][k] = in ? sig[tri(in ? i : 0, in ? k : 0)] : 0.0;
         }
     }
-    return true;
+    bool ok = true;
+    UKFB_UNROLL
+    for (int j = 0; j < N; ++j) {
+        const int rj = j / T, src = (lane & ~(T - 1)) | (j % T);
+        double pj[N];
+        double ajj = warp_shfl(a[rj][j], src);
+        UKFB_UNROLL
+        for (int k = 0; k < j; ++k) {
+            pj[k] = warp_shfl(a[rj][k], src);
+            ajj -= pj[k] * pj[k];
+        }
+        if (!(ajj > 0.0) || !(ajj < 1.0e300)) {
+            ok = false;
+            ajj = 1.0; /* keep the arithmetic finite; nothing is written back */
+        }
+        double d, rinv;
+        fast_sqrt_rsqrt(ajj, d, rinv);
+        UKFB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            if (r * T + T - 1 < j) continue; /* all rows of this register row are above the pivot */
+            const int i = r * T + t;
+            double s = a[r][j];
+            if (r * T + T - 1 > j) { /* some lane's row is below the pivot */
+                UKFB_UNROLL
+                for (int k = 0; k < j; ++k) s -= a[r][k] * pj[k];
+                s *= rinv;
+            }
+            a[r][j] = (i == j) ? d : s;
+        }
+    }
+    if (ok && active) {
+        UKFB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int i = r * T + t;
+            UKFB_UNROLL
+            for (int k = 0; k < N; ++k) {
+                if (k > r * T + T - 1) continue;
+                if (i < N && k <= i) sig[tri(i, k)] = a[r][k];
+            }
+        }
+    }
+    return ok;
 }
 
 /* ---- sigma points: X0 = mu + delta, X(2j+1) = mu + (delta + L[:,j]), X(2j+2) = mu + (delta - L[:,j]) */
@@ -195,12 +240,13 @@ UKFB_D void sigma_generate(const double* L, const double* mu, const double* delt
     UKFB_UNROLL
     for (int i = 0; i < F::MU; ++i) x[i] = mu[i];
     const bool col = lane >= 1 && lane < F::NS;
-    const int j = (lane - 1) >> 1;
+    const int j = col ? (lane - 1) >> 1 : 0;
     const bool plus = (lane & 1) != 0;
     double d[F::N];
     UKFB_UNROLL
     for (int i = 0; i < F::N; ++i) {
-        const double l = (col && i >= j) ? L[tri(i, j)] : 0.0;
+        const bool in = col && i >= j;
+        const double l = in ? L[tri(i, in ? j : 0)] : 0.0;
         const double dl = delta ? delta[i] : 0.0;
         d[i] = plus ? dl + l : dl - l;
     }
@@ -302,7 +348,7 @@ UKFB_D void meas_boxminus(const double* z, const double* o, bool rot, double* re
 /* ---- warp context ----------------------------------------------------------------- */
 template <class F>
 struct Warp {
-    double* D;
+    double* D;   /* deviation matrix D[c * DT_LD + p]: component c of sigma point p */
     double* SXZ;
     double* KM;
     double* KS;
@@ -313,6 +359,32 @@ struct Warp {
     int* HP; /* mean-pass histogram of this warp, 8 ints */
     int lane;
 };
+
+/* sum over the sigma points of row c of the deviation matrix.  Lane c starts at column c so
+ * that the N lanes of one load hit distinct banks (row stride 36: 5c + s mod 16); the padding
+ * columns NS..27 hold zeros. */
+UKFB_D double row_sum(const double* D, int c)
+{
+    const double* row = D + c * DT_LD;
+    double a = 0.0;
+    UKFB_UNROLL
+    for (int s = 0; s < DT_COLS; ++s) {
+        int p = s + c;
+        if (p >= DT_COLS) p -= DT_COLS;
+        a += row[p];
+    }
+    return a;
+}
+
+/* x / NS as the reference's `mean_delta /= X.size()` computes it (a true division), through
+ * one reciprocal multiply and a residual correction */
+template <int NS>
+UKFB_D double div_ns(double x)
+{
+    constexpr double rinv = 1.0 / double(NS);
+    const double q = x * rinv;
+    return fma(fma(-double(NS), q, x), rinv, q);
+}
 
 /* ukfom sigma_points_mean on the state manifold: ref = X0; loop { md = mean(X_i [-] ref);
  * ref [+]= md } while (|md| > tol && ++i < max_it).  Every lane ends with the same ref. */
@@ -334,14 +406,10 @@ UKFB_D uint32_t manifold_mean(Warp<F>& w, const double* x, double* ref)
         state_boxminus<F>(x, ref, d);
         if (lane < F::NS) {
             UKFB_UNROLL
-            for (int i = 0; i < F::N; ++i) w.D[lane * F::DS + i] = d[i];
+            for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = d[i];
         }
         __syncwarp();
-        if (lane < F::N) {
-            double a = 0.0;
-            for (int p = 0; p < F::NS; ++p) a += w.D[p * F::DS + lane];
-            w.MD[lane] = a / double(F::NS);
-        }
+        if (lane < F::N) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, lane));
         __syncwarp();
         double md[F::N];
         double n2 = 0.0;
@@ -353,7 +421,7 @@ UKFB_D uint32_t manifold_mean(Warp<F>& w, const double* x, double* ref)
         state_boxplus<F>(ref, md, 1.0);
         ++passes;
         __syncwarp();
-        if (!(sqrt(n2) > UKFB_MEAN_TOL)) break;
+        if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break; /* |md| > tol */
         if (++it >= UKFB_MEAN_MAX_IT) {
             st = UKFB_STATUS_MEAN_NO_CONVERGE;
             break;
@@ -363,40 +431,7 @@ UKFB_D uint32_t manifold_mean(Warp<F>& w, const double* x, double* ref)
     return st;
 }
 
-/* covariance of the deviations in D[:, 0:N] (already written, synced): each lane owns one
- * 2x2 tile of the lower triangle;  out(i,j) = 0.5 * sum_p d_i d_j + noise(i,j). */
-template <class F, class Noise>
-UKFB_D void cov_store(Warp<F>& w, double* out, Noise noise)
-{
-    constexpr int NT1 = (F::N + 1) / 2;
-    constexpr int NT = NT1 * (NT1 + 1) / 2;
-    static_assert(NT <= 32, "one tile per lane");
-    const int lane = w.lane;
-    if (lane < NT) {
-        int ta = 0;
-        while ((ta + 1) * (ta + 2) / 2 <= lane) ++ta;
-        const int tb = lane - ta * (ta + 1) / 2;
-        const int i0 = 2 * ta, j0 = 2 * tb;
-        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-        for (int p = 0; p < F::NS; ++p) {
-            const double* row = w.D + p * F::DS;
-            const double a0 = row[i0], a1 = row[i0 + 1];
-            const double b0 = row[j0], b1 = row[j0 + 1];
-            c00 += a0 * b0;
-            c01 += a0 * b1;
-            c10 += a1 * b0;
-            c11 += a1 * b1;
-        }
-        out[tri(i0, j0)] = 0.5 * c00 + noise(i0, j0);
-        if (j0 + 1 <= i0) out[tri(i0, j0 + 1)] = 0.5 * c01 + noise(i0, j0 + 1);
-        if (i0 + 1 < F::N) {
-            out[tri(i0 + 1, j0)] = 0.5 * c10 + noise(i0 + 1, j0);
-            out[tri(i0 + 1, j0 + 1)] = 0.5 * c11 + noise(i0 + 1, j0 + 1);
-        }
-    }
-}
-
-/* deviations of every sigma point from `ref` into D[:, 0:N] */
+/* deviations of every sigma point from `ref` into rows 0..N-1 of the deviation matrix */
 template <class F>
 UKFB_D void write_deviations(Warp<F>& w, const double* x, const double* ref)
 {
@@ -404,7 +439,34 @@ UKFB_D void write_deviations(Warp<F>& w, const double* x, const double* ref)
     state_boxminus<F>(x, ref, d);
     if (w.lane < F::NS) {
         UKFB_UNROLL
-        for (int i = 0; i < F::N; ++i) w.D[w.lane * F::DS + i] = d[i];
+        for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + w.lane] = d[i];
+    }
+}
+
+/* DMMA fragment of component tile I (rows 8I..8I+7 of D) and sigma points 4s..4s+3: serves as the
+ * A operand (component x point) of tile I and as the B operand (point x component) of tile I. */
+UKFB_D double frag(const double* D, int lane, int I, int s) { return D[(8 * I + (lane >> 2)) * DT_LD + 4 * s + (lane & 3)]; }
+
+/* covariance of the deviations in rows 0..N-1 of D (already written, synced):
+ * out(i,j) = 0.5 * sum_p d_i d_j + noise(i,j), lower triangle, three 8x8 tiles on the DMMA path. */
+template <class F, class Noise>
+UKFB_D void cov_store(Warp<F>& w, double* out, Noise noise)
+{
+    const int lane = w.lane;
+    double c00[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    UKFB_UNROLL
+    for (int s = 0; s < DT_COLS / 4; ++s) {
+        const double f0 = frag(w.D, lane, 0, s), f1 = frag(w.D, lane, 1, s);
+        warp_dmma(c00[0], c00[1], f0, f0);
+        warp_dmma(c10[0], c10[1], f1, f0);
+        warp_dmma(c11[0], c11[1], f1, f1);
+    }
+    const int r = lane >> 2, c = 2 * (lane & 3);
+    UKFB_UNROLL
+    for (int e = 0; e < 2; ++e) {
+        if (c + e <= r) out[tri(r, c + e)] = 0.5 * c00[e] + noise(r, c + e);
+        if (8 + r < F::N) out[tri(8 + r, c + e)] = 0.5 * c10[e] + noise(8 + r, c + e);
+        if (8 + r < F::N && c + e <= r) out[tri(8 + r, 8 + c + e)] = 0.5 * c11[e] + noise(8 + r, 8 + c + e);
     }
 }
 
@@ -412,9 +474,9 @@ UKFB_D void write_deviations(Warp<F>& w, const double* x, const double* ref)
 UKFB_D double q_sym(const double* Qp, int i, int j) { return i >= j ? UKFB_LDG(Qp + tri(i, j)) : UKFB_LDG(Qp + tri(j, i)); }
 
 /* ---- predict of one filter by one warp (ukfom predict, App. A.3) --------------------- */
+/* sig holds the Cholesky factor at entry and the predicted covariance at exit. */
 template <class F>
-UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, double* A, double* Bs, double* mu,
-                              const double* fimu, double dt)
+UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, double* sig, double* mu, const double* fimu, double dt)
 {
     const int lane = w.lane;
     const double* Qp = p.Q + b * p.q_stride;
@@ -446,7 +508,7 @@ UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, doub
     }
 
     double x[F::MU];
-    sigma_generate<F>(Bs, mu, nullptr, lane, x);
+    sigma_generate<F>(sig, mu, nullptr, lane, x);
     if (F::KIND == 0)
         process_model_pose(x, dt, has_acc, acc);
     else
@@ -460,7 +522,7 @@ UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, doub
     const double scale = F::KIND == 0 ? dt : dt * dt; /* PoseUKF.cpp:186 vs OrientationUKF.cpp:86 */
     const double* QR = w.QR;
     const double* acov = p.acc_cov ? p.acc_cov + b * 9 : nullptr;
-    cov_store<F>(w, A, [=](int i, int j) -> double {
+    cov_store<F>(w, sig, [=](int i, int j) -> double {
         if (F::KIND == 0 && has_acc) {
             /* shadowing local of PoseUKF.cpp:190-191: unrotated, unscaled Q, velocity block = 2 acc.cov */
             if (i >= 6 && i < 9 && j >= 6 && j < 9) return 2.0 * UKFB_LDG(acov + (i - 6) * 3 + (j - 6));
@@ -481,17 +543,17 @@ UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, doub
 }
 
 /* ---- apply_delta of one filter (App. A.4): sigma points around mu [+] delta from the
- * factor in Bs, manifold mean, covariance (no additive noise) ------------------------- */
+ * factor in sig, manifold mean, covariance (no additive noise) back into sig ------------- */
 template <class F>
-UKFB_D uint32_t sigma_apply_delta(Warp<F>& w, double* A, const double* Bs, double* mu, const double* delta)
+UKFB_D uint32_t sigma_apply_delta(Warp<F>& w, double* sig, double* mu, const double* delta)
 {
     double x[F::MU];
-    sigma_generate<F>(Bs, mu, delta, w.lane, x);
+    sigma_generate<F>(sig, mu, delta, w.lane, x);
     double ref[F::MU];
     uint32_t st = manifold_mean<F>(w, x, ref);
     write_deviations<F>(w, x, ref);
     __syncwarp();
-    cov_store<F>(w, A, [](int, int) -> double { return 0.0; });
+    cov_store<F>(w, sig, [](int, int) -> double { return 0.0; });
     if (w.lane == 0) {
         UKFB_UNROLL
         for (int i = 0; i < F::MU; ++i) mu[i] = ref[i];
@@ -501,19 +563,20 @@ UKFB_D uint32_t sigma_apply_delta(Warp<F>& w, double* A, const double* Bs, doubl
 }
 
 /* ---- first half of update of one filter (App. A.4): innovation statistics, gain,
- * sigma <- sigma - K S K^T (in place), delta = K innov ----------------------- */
+ * sigma <- sigma_prior - K S K^T, delta = K innov.  sig holds the Cholesky factor at entry;
+ * sigma_prior is the covariance spilled to the filter's HBM record before the factorisation. */
 template <class F>
-UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int tick, int kind, double* A,
-                             const double* Bs,
-                             const double* mu, double* delta)
+UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int tick, int kind, double* sig,
+                             const double* sigma_prior, const double* mu, double* delta)
 {
+    constexpr int ZC = F::N; /* rows of D holding the measurement deviations */
     const int lane = w.lane;
     const bool rot = (F::KIND == 0) && kind == UKFB_MEAS_POSE_ORIENTATION;
     const int m = meas_dim(kind);
     uint32_t st = 0;
 
     double x[F::MU];
-    sigma_generate<F>(Bs, mu, nullptr, lane, x);
+    sigma_generate<F>(sig, mu, nullptr, lane, x);
     double z[4];
     measure<F>(x, kind, z);
 
@@ -527,16 +590,11 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
 #if UKFB_EUCLID_MEAS_DIRECT_MEAN
     if (!rot) {
         if (lane < F::NS) {
-            w.D[lane * F::DS + F::N + 0] = z[0];
-            w.D[lane * F::DS + F::N + 1] = z[1];
-            w.D[lane * F::DS + F::N + 2] = z[2];
+            UKFB_UNROLL
+            for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = z[c];
         }
         __syncwarp();
-        if (lane < 3) {
-            double a = 0.0;
-            for (int q = 0; q < F::NS; ++q) a += w.D[q * F::DS + F::N + lane];
-            w.MD[lane] = a / double(F::NS);
-        }
+        if (lane < 3) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, ZC + lane));
         __syncwarp();
         zref[0] = w.MD[0], zref[1] = w.MD[1], zref[2] = w.MD[2];
         __syncwarp();
@@ -548,16 +606,11 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
             double dz[3];
             meas_boxminus(z, zref, rot, dz);
             if (lane < F::NS) {
-                w.D[lane * F::DS + F::N + 0] = dz[0];
-                w.D[lane * F::DS + F::N + 1] = dz[1];
-                w.D[lane * F::DS + F::N + 2] = dz[2];
+                UKFB_UNROLL
+                for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
             }
             __syncwarp();
-            if (lane < 3) {
-                double a = 0.0;
-                for (int q = 0; q < F::NS; ++q) a += w.D[q * F::DS + F::N + lane];
-                w.MD[lane] = a / double(F::NS);
-            }
+            if (lane < 3) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, ZC + lane));
             __syncwarp();
             const double md[3] = {w.MD[0], w.MD[1], w.MD[2]};
             const double n2 = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
@@ -569,7 +622,7 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
                 zref[2] += md[2];
             }
             __syncwarp();
-            if (!(sqrt(n2) > UKFB_MEAN_TOL)) break;
+            if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
             if (++it >= UKFB_MEAN_MAX_IT) {
                 st = UKFB_STATUS_MEAN_NO_CONVERGE;
                 break;
@@ -588,29 +641,38 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
         state_boxminus<F>(x, mur, dx);
         if (lane < F::NS) {
             UKFB_UNROLL
-            for (int i = 0; i < F::N; ++i) w.D[lane * F::DS + i] = dx[i];
-            w.D[lane * F::DS + F::N + 0] = dz[0];
-            w.D[lane * F::DS + F::N + 1] = dz[1];
-            w.D[lane * F::DS + F::N + 2] = dz[2];
+            for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = dx[i];
+            UKFB_UNROLL
+            for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
         }
     }
     __syncwarp();
 
-    /* S = 0.5 sum dz dz^T + R (R padded with identity to 3x3);  Sxz = 0.5 sum dx dz^T */
-    const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-    const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
-    if (lane < 9) {
-        const int a = lane / 3, c = lane % 3;
-        double s = 0.0;
-        for (int q = 0; q < F::NS; ++q) s += w.D[q * F::DS + F::N + a] * w.D[q * F::DS + F::N + c];
-        const double r = (a < m && c < m) ? UKFB_LDG(Rm + a * p.r_ld + c) : (a == c ? 1.0 : 0.0);
-        w.SM[lane] = 0.5 * s + r;
-    }
-    for (int e = lane; e < 3 * F::N; e += 32) {
-        const int i = e / 3, c = e % 3;
-        double s = 0.0;
-        for (int q = 0; q < F::NS; ++q) s += w.D[q * F::DS + i] * w.D[q * F::DS + F::N + c];
-        w.SXZ[e] = 0.5 * s;
+    /* S = 0.5 sum dz dz^T + R (R padded with identity to 3x3);  Sxz = 0.5 sum dx dz^T:
+     * component tile 1 (rows 8..15 of D) holds dz; two DMMA tiles per 4 sigma points */
+    {
+        double c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+        UKFB_UNROLL
+        for (int s = 0; s < DT_COLS / 4; ++s) {
+            const double f0 = frag(w.D, lane, 0, s), f1 = frag(w.D, lane, 1, s);
+            warp_dmma(c01[0], c01[1], f0, f1);
+            warp_dmma(c11[0], c11[1], f1, f1);
+        }
+        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
+        const int r = lane >> 2;
+        UKFB_UNROLL
+        for (int e = 0; e < 2; ++e) {
+            const int cz = 8 + 2 * (lane & 3) + e - ZC; /* measurement component of this column */
+            if (cz >= 0 && cz < 3) {
+                w.SXZ[r * 3 + cz] = 0.5 * c01[e];
+                if (8 + r < F::N) w.SXZ[(8 + r) * 3 + cz] = 0.5 * c11[e];
+                const int az = 8 + r - ZC;
+                if (az >= 0 && az < 3) {
+                    const double rr = (az < m && cz < m) ? UKFB_LDG(Rm + az * p.r_ld + cz) : (az == cz ? 1.0 : 0.0);
+                    w.SM[az * 3 + cz] = 0.5 * c11[e] + rr;
+                }
+            }
+        }
     }
     __syncwarp();
 
@@ -637,6 +699,7 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
     /* innovation z [-] zbar */
     double innov[3];
     {
+        const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
         double zin[4] = {0.0, 0.0, 0.0, 1.0};
         if (rot) {
             const double v[3] = {UKFB_LDG(zm + 0), UKFB_LDG(zm + 1), UKFB_LDG(zm + 2)};
@@ -665,15 +728,22 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
         w.KS[e] = ks;
     }
     __syncwarp();
-    /* sigma' = sigma - (K S) K^T, lower triangle, in place (the factor in Bs is no longer needed) */
-    for (int e = lane; e < F::LP; e += 32) {
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        const int j = e - i * (i + 1) / 2;
-        double s = 0.0;
-        UKFB_UNROLL
-        for (int k = 0; k < 3; ++k) s += w.KS[i * 3 + k] * w.KM[j * 3 + k];
-        A[e] = A[e] - s;
+    /* sigma <- sigma_prior - (K S) K^T, lower triangle; overwrites the factor, which is no longer needed.
+     * sigma_prior[e] was stored by this same lane (same e = lane + 32 q mapping). */
+    UKFB_UNROLL
+    for (int q = 0; q < (F::LP + 31) / 32; ++q) {
+        const int e = lane + 32 * q;
+        if (e < F::LP) {
+            /* row of packed index e: i (i + 1) / 2 <= e */
+            int i = int((sqrtf(8.0f * float(e) + 1.0f) - 1.0f) * 0.5f);
+            if ((i + 1) * (i + 2) / 2 <= e) ++i;
+            if (i * (i + 1) / 2 > e) --i;
+            const int j = e - i * (i + 1) / 2;
+            double s = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) s += w.KS[i * 3 + k] * w.KM[j * 3 + k];
+            sig[e] = sigma_prior[e] - s;
+        }
     }
     if (lane < F::N) {
         double s = 0.0;
@@ -686,10 +756,26 @@ UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int t
 }
 
 /* ---- the kernel ------------------------------------------------------------------- */
-constexpr int WPB = 4; /* warps per block; warps are independent (no block-level sync) */
-
+/* Cholesky phase for every filter of the group whose flag has `bit`: T = 32/G lanes each. */
 template <class F, int G>
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParams p)
+UKFB_D void cholesky_phase(double* wsm, int* cflag, int* cstat, int lane, int cnt, int bit, int clear_bits, bool dirty_on_fail)
+{
+    typedef Smem<F, G> SM;
+    constexpr int T = 32 / G;
+    const int g = lane / T;
+    const bool active = g < cnt && (cflag[g < cnt ? g : 0] & bit);
+    double* sig = wsm + (g < cnt ? g : 0) * SM::FS + SM::OFF_SIG;
+    const bool ok = cholesky_rows<F, T>(sig, lane, active);
+    __syncwarp();
+    if (active && !ok && (lane & (T - 1)) == 0) {
+        cstat[g] |= int(UKFB_STATUS_NOT_SPD);
+        cflag[g] = (cflag[g] & ~clear_bits) | (dirty_on_fail ? CF_DIRTY : 0);
+    }
+    __syncwarp();
+}
+
+template <class F, int G, int WPB, int MINB>
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepParams p)
 {
     typedef Smem<F, G> SM;
     UKFB_SMEM_DECL
@@ -710,23 +796,20 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
     w.BC = wsm + SM::OFF_BC;
     w.QR = wsm + SM::OFF_QR;
     w.lane = lane;
-    double* cdt = wsm + SM::OFF_DT;
     int* cflag = reinterpret_cast<int*>(wsm + SM::OFF_CTL);
     int* ckind = cflag + G;
-    w.HP = ckind + G;
+    int* cstat = ckind + G;
+    w.HP = cstat + G;
     if (lane < 8) w.HP[lane] = 0;
+    if (lane < G) cstat[lane] = 0, cflag[lane] = 0;
+    for (int i = lane; i < DT_ROWS * DT_LD; i += 32) w.D[i] = 0.0; /* padding columns / rows stay zero */
 
-    /* ---- load the group's records (coalesced), scatter into the per-filter layout */
+    /* ---- load the group's records (coalesced) into the per-filter layout */
+    double* rec = p.state + first * F::REC;
     {
-        const double* src = p.state + first * F::REC;
         for (int i = lane; i < cnt * F::REC; i += 32) {
             const int g = i / F::REC, k = i - g * F::REC;
-            const double v = src[i];
-            double* fr = wsm + g * SM::FREC;
-            if (k < F::MU)
-                fr[SM::OFF_MU + k] = v;
-            else if (k >= REC_MU_PAD && k < REC_MU_PAD + F::LP)
-                fr[SM::OFF_A + (k - REC_MU_PAD)] = v;
+            wsm[g * SM::FS + k] = rec[i];
         }
         /* the stored IMU sample: acceleration (PoseUKF.cpp:175-178, OrientationUKF.cpp:59-63)
          * and rotation rate (OrientationUKF.cpp:53-57) */
@@ -737,34 +820,33 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
                 v = p.acc_mu[(first + g) * 3 + k];
             else if (F::KIND == 1)
                 v = p.gyro_mu[(first + g) * 3 + (k - 3)];
-            wsm[g * SM::FREC + SM::OFF_IMU + k] = v;
+            wsm[g * SM::FS + SM::OFF_IMU + k] = v;
         }
     }
-    uint32_t my_status = 0; /* lane g: status bits of filter g */
-    bool dirty = false;     /* lane g: record of filter g changed */
     __syncwarp();
 
     UKFB_NOUNROLL
     for (int tick = 0; tick < p.K; ++tick) {
         /* ---- per-filter control: time guards (UnscentedKalmanFilter.hpp:83-125), masks, checks */
         if (lane < G) {
-            int flags = 0, kind = -1;
+            int flags = cflag[lane] & CF_DIRTY, kind = -1, st = 0;
             if (lane < cnt) {
                 const long long b = first + lane;
-                flags = CF_VALID;
+                double* fr = wsm + lane * SM::FS;
+                flags |= CF_VALID;
                 if (F::KIND == 1 && p.imu) { /* integrateMeasurement(RotationRate / Acceleration): check, store */
                     const double* s6 = p.imu + tick * p.imu_kstride + b * 6;
-                    double* fimu = wsm + lane * SM::FREC + SM::OFF_IMU;
+                    double* fimu = fr + SM::OFF_IMU;
                     const double g0 = s6[0], g1 = s6[1], g2 = s6[2], a0 = s6[3], a1 = s6[4], a2 = s6[5];
                     const double big = 1.79769313486231570e308;
                     if (fabs(g0) <= big && fabs(g1) <= big && fabs(g2) <= big)
                         fimu[3] = g0, fimu[4] = g1, fimu[5] = g2;
                     else
-                        my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                        st |= UKFB_STATUS_NONFINITE_MEAS;
                     if (fabs(a0) <= big && fabs(a1) <= big && fabs(a2) <= big)
                         fimu[0] = a0, fimu[1] = a1, fimu[2] = a2;
                     else
-                        my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                        st |= UKFB_STATUS_NONFINITE_MEAS;
                 }
                 if (p.do_predict) {
                     double dt;
@@ -785,14 +867,14 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
                     }
                     if (have_dt) {
                         if (dt < 0.0)
-                            my_status |= UKFB_STATUS_NEG_DT;
+                            st |= UKFB_STATUS_NEG_DT;
                         else if (dt <= p.min_dt) {
                             /* delta time is zero or close to zero: no-op */
                         } else if (dt > p.max_dt)
-                            my_status |= UKFB_STATUS_DT_TOO_LARGE;
+                            st |= UKFB_STATUS_DT_TOO_LARGE;
                         else {
                             flags |= CF_PRED;
-                            cdt[lane] = dt;
+                            fr[SM::OFF_DT] = dt;
                         }
                     }
                 }
@@ -813,7 +895,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
                         if (ok)
                             flags |= CF_UPD;
                         else {
-                            my_status |= UKFB_STATUS_NONFINITE_MEAS;
+                            st |= UKFB_STATUS_NONFINITE_MEAS;
                             kind = -1;
                         }
                     }
@@ -821,27 +903,20 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
             }
             cflag[lane] = flags;
             ckind[lane] = kind;
+            cstat[lane] |= st;
         }
         __syncwarp();
 
         /* ---- predict ------------------------------------------------------------------ */
         if (p.do_predict) {
-            if (lane < G && (cflag[lane] & CF_PRED)) {
-                double* fr = wsm + lane * SM::FREC;
-                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
-                    my_status |= UKFB_STATUS_NOT_SPD;
-                    cflag[lane] &= ~(CF_PRED | CF_UPD);
-                }
-            }
-            __syncwarp();
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_PRED, CF_PRED | CF_UPD, false);
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_PRED)) continue;
-                double* fr = wsm + g * SM::FREC;
-                const uint32_t st = sigma_predict<F>(w, p, first + g, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU,
-                                                     fr + SM::OFF_IMU, cdt[g]);
-                if (lane == g) {
-                    my_status |= st;
-                    dirty = true;
+                double* fr = wsm + g * SM::FS;
+                const uint32_t st = sigma_predict<F>(w, p, first + g, fr + SM::OFF_SIG, fr + SM::OFF_MU, fr + SM::OFF_IMU, fr[SM::OFF_DT]);
+                if (lane == 0) {
+                    cstat[g] |= int(st);
+                    cflag[g] |= CF_DIRTY;
                 }
             }
             __syncwarp();
@@ -849,41 +924,33 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
 
         /* ---- update --------------------------------------------------------------------- */
         if (p.do_update) {
-            if (lane < G && (cflag[lane] & CF_UPD)) {
-                double* fr = wsm + lane * SM::FREC;
-                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
-                    my_status |= UKFB_STATUS_NOT_SPD;
-                    cflag[lane] &= ~CF_UPD;
-                }
-            }
-            __syncwarp();
+            /* spill the prior covariance of the updating filters to their HBM records: the factor is about to
+             * overwrite it in shared memory and sigma - K S K^T needs it back (read by the lane that wrote it) */
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
-                double* fr = wsm + g * SM::FREC;
-                const uint32_t st = sigma_update<F>(w, p, first + g, tick, ckind[g], fr + SM::OFF_A, fr + SM::OFF_B,
+                const double* sig = wsm + g * SM::FS + SM::OFF_SIG;
+                double* dst = rec + g * F::REC + F::MU;
+                for (int e = lane; e < F::LP; e += 32) dst[e] = sig[e];
+            }
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, false);
+            for (int g = 0; g < cnt; ++g) {
+                if (!(cflag[g] & CF_UPD)) continue;
+                double* fr = wsm + g * SM::FS;
+                const uint32_t st = sigma_update<F>(w, p, first + g, tick, ckind[g], fr + SM::OFF_SIG, rec + g * F::REC + F::MU,
                                                     fr + SM::OFF_MU, fr + SM::OFF_DELTA);
-                if (lane == g) my_status |= st;
+                if (lane == 0) cstat[g] |= int(st);
             }
             __syncwarp();
-            if (lane < G && (cflag[lane] & CF_UPD)) {
-                double* fr = wsm + lane * SM::FREC;
-                if (!cholesky_packed<F>(fr + SM::OFF_A, fr + SM::OFF_B)) {
-                    /* the reference has already replaced sigma by sigma - K S K^T when MTK's
-                     * assert fires inside apply_delta; keep that matrix, leave mu alone */
-                    my_status |= UKFB_STATUS_NOT_SPD;
-                    cflag[lane] &= ~CF_UPD;
-                    dirty = true;
-                }
-            }
-            __syncwarp();
+            /* the reference has already replaced sigma by sigma - K S K^T when MTK's assert fires inside
+             * apply_delta: on failure keep that matrix (dirty), leave mu alone */
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, true);
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
-                double* fr = wsm + g * SM::FREC;
-                const uint32_t st =
-                    sigma_apply_delta<F>(w, fr + SM::OFF_A, fr + SM::OFF_B, fr + SM::OFF_MU, fr + SM::OFF_DELTA);
-                if (lane == g) {
-                    my_status |= st;
-                    dirty = true;
+                double* fr = wsm + g * SM::FS;
+                const uint32_t st = sigma_apply_delta<F>(w, fr + SM::OFF_SIG, fr + SM::OFF_MU, fr + SM::OFF_DELTA);
+                if (lane == 0) {
+                    cstat[g] |= int(st);
+                    cflag[g] |= CF_DIRTY;
                 }
             }
             __syncwarp();
@@ -891,23 +958,17 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
     }
 
     /* ---- store dirty records (coalesced), stored IMU sample, status, histogram --------------- */
-    if (lane < G) cflag[lane] = dirty ? CF_DIRTY : 0;
-    __syncwarp();
     {
-        double* dst = p.state + first * F::REC;
         for (int i = lane; i < cnt * F::REC; i += 32) {
             const int g = i / F::REC, k = i - g * F::REC;
+            /* a spilled-but-not-updated covariance equals the shared-memory copy, so clean records can be skipped */
             if (!(cflag[g] & CF_DIRTY)) continue;
-            const double* fr = wsm + g * SM::FREC;
-            if (k < F::MU)
-                dst[i] = fr[SM::OFF_MU + k];
-            else if (k >= REC_MU_PAD && k < REC_MU_PAD + F::LP)
-                dst[i] = fr[SM::OFF_A + (k - REC_MU_PAD)];
+            rec[i] = wsm[g * SM::FS + k];
         }
         if (F::KIND == 1 && p.imu) {
             for (int i = lane; i < cnt * 6; i += 32) {
                 const int g = i / 6, k = i - g * 6;
-                const double v = wsm[g * SM::FREC + SM::OFF_IMU + k];
+                const double v = wsm[g * SM::FS + SM::OFF_IMU + k];
                 if (k < 3)
                     p.acc_mu[(first + g) * 3 + k] = v;
                 else
@@ -915,7 +976,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, 1) ukf_step_kernel(const StepParam
             }
         }
     }
-    if (lane < cnt && my_status) p.status[first + lane] |= my_status;
+    if (lane < cnt && cstat[lane]) p.status[first + lane] |= uint32_t(cstat[lane]);
     __syncwarp();
     if (lane >= 1 && lane < 8 && p.hist && w.HP[lane])
         atomicAdd(p.hist + (blockIdx.x % HIST_SLOTS) * 8 + lane, (unsigned long long)w.HP[lane]);

@@ -40,7 +40,8 @@ def load(sanitize: bool = False):
     out = os.path.join(_DIR, "libukfb_emu.so")
     srcs = [os.path.join(_DIR, "emu_harness.cpp"), os.path.join(_DIR, "simt_emu_rt.hpp"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"),
-            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh")]
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh"),
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/simt.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", _DIR,
                "-o", out, srcs[0]]
@@ -60,7 +61,7 @@ class EmuBatch:
     def __init__(self, kind: int, B: int, G: int = 4):
         self.lib = load()
         self.kind, self.B, self.G = kind, B, G
-        self.n, self.MU, self.REC = (12, 13, 96) if kind == 0 else (13, 14, 112)
+        self.n, self.MU, self.REC = (12, 13, 91) if kind == 0 else (13, 14, 105)
         self.LP = self.n * (self.n + 1) // 2
         self.tril = np.tril_indices(self.n)
         self.state = np.zeros((B, self.REC))
@@ -85,7 +86,7 @@ class EmuBatch:
         sigma = np.asarray(sigma, float).reshape(self.B, self.n, self.n)
         self.state[:] = 0
         self.state[:, : self.MU] = mu
-        self.state[:, 16 : 16 + self.LP] = sigma[:, self.tril[0], self.tril[1]]
+        self.state[:, self.MU : self.MU + self.LP] = sigma[:, self.tril[0], self.tril[1]]
         self.t_last[:] = 0
         if self.kind == 1 and self._first_init:
             self.acc_mu[:] = 0
@@ -95,7 +96,7 @@ class EmuBatch:
     def get_state(self):
         mu = self.state[:, : self.MU].copy()
         sg = np.zeros((self.B, self.n, self.n))
-        sg[:, self.tril[0], self.tril[1]] = self.state[:, 16 : 16 + self.LP]
+        sg[:, self.tril[0], self.tril[1]] = self.state[:, self.MU : self.MU + self.LP]
         sg = sg + np.transpose(np.tril(sg, -1), (0, 2, 1))
         return mu, sg
 

@@ -24,6 +24,8 @@ inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 namespace simt_emu {
 inline thread_local std::barrier<>* warp_barrier = nullptr;
 inline thread_local double* smem_ptr = nullptr;
+inline thread_local double* xchg_ptr = nullptr; /* 64 doubles per warp: shuffle / mma operand exchange */
+inline double* warp_xchg() { return xchg_ptr; }
 inline double* smem_base() { return smem_ptr; }
 
 template <class Kernel, class Params>
@@ -37,6 +39,7 @@ void launch(Kernel kernel, unsigned grid, unsigned block, std::size_t smem_bytes
             const unsigned cnt = (w + 1) * 32 <= block ? 32 : block - w * 32;
             bars.emplace_back(new std::barrier<>(cnt));
         }
+        std::vector<double> xchg(64 * nwarps, 0.0);
         std::vector<std::thread> th;
         th.reserve(block);
         for (unsigned t = 0; t < block; ++t) {
@@ -47,6 +50,7 @@ void launch(Kernel kernel, unsigned grid, unsigned block, std::size_t smem_bytes
                 gridDim.x = grid;
                 warp_barrier = bars[t / 32].get();
                 smem_ptr = smem.data();
+                xchg_ptr = xchg.data() + 64 * (t / 32);
                 kernel(params);
             });
         }
