@@ -28,6 +28,9 @@
 #define UKFB_D __device__ __forceinline__
 #define UKFB_DNI __device__ __noinline__
 #define UKFB_GLOBAL __global__
+#define UKFB_GRID_CONSTANT __grid_constant__
+#define UKFB_CONSTANT __constant__
+#define UKFB_LDCG(p) __ldcg(p)
 #define UKFB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define UKFB_SMEM_DECL extern __shared__ __align__(16) double ukfb_smem[];
 #define UKFB_LDG(p) __ldg(p)
@@ -95,6 +98,9 @@ UKFB_D void fast_sqrt_rsqrt(double x, double& s, double& r)
 #define UKFB_D inline
 #define UKFB_DNI inline
 #define UKFB_GLOBAL
+#define UKFB_GRID_CONSTANT
+#define UKFB_CONSTANT static const
+#define UKFB_LDCG(p) (*(p))
 #define UKFB_LAUNCH_BOUNDS(t, b)
 #define UKFB_SMEM_DECL double* ukfb_smem = ::simt_emu::smem_base();
 #define UKFB_LDG(p) (*(p))

@@ -95,47 +95,44 @@ UKFB_D void quat_matrix(const double* q, double* R)
 constexpr double SO3_EXP_FAST_X2 = 0.25; /* (half angle)^2 bound of the cos/sinc polynomials */
 constexpr double SO3_LOG_FAST_U = 0.09;  /* (|q.vec| / w)^2 bound of the atan polynomial */
 
-UKFB_D double poly6(double v, double c0, double c1, double c2, double c3, double c4, double c5, double c6)
+/* coefficients live in constant memory so that each FMA takes its coefficient as a
+ * constant-bank operand instead of two 32-bit immediates moved into registers */
+UKFB_CONSTANT double SO3_COS_C[7] = {1.0, -0x1.fffffffffffffp-2, 0x1.5555555555421p-5, -0x1.6c16c16bdd04ep-10,
+                                     0x1.a01a00fb1bc6fp-16, -0x1.27e40964b47d4p-22, 0x1.1d8d32755f8fbp-29};
+UKFB_CONSTANT double SO3_SINC_C[7] = {1.0, -0x1.5555555555555p-3, 0x1.11111111110bfp-7, -0x1.a01a019ffb337p-13,
+                                      0x1.71de39fd64b1fp-19, -0x1.ae63543245d1fp-26, 0x1.5fac6e0083f22p-33};
+UKFB_CONSTANT double SO3_ATAN_C[10] = {1.0, -0x1.5555555555500p-2, 0x1.999999998a517p-3, -0x1.2492491c0c582p-3,
+                                       0x1.c71c6cf04ff82p-4, -0x1.745c4ca68d45dp-4, 0x1.3aff6b481f0f7p-4,
+                                       -0x1.0fcd05c851591p-4, 0x1.c90783e417298p-5, -0x1.229f36308eeefp-5};
+
+UKFB_D double poly6(double v, double v2, const double* c)
 {
-    const double v2 = v * v;
-    const double p01 = fma(c1, v, c0), p23 = fma(c3, v, c2), p45 = fma(c5, v, c4);
-    const double q0 = fma(p23, v2, p01), q1 = fma(c6, v2, p45);
+    const double p01 = fma(c[1], v, c[0]), p23 = fma(c[3], v, c[2]), p45 = fma(c[5], v, c[4]);
+    const double q0 = fma(p23, v2, p01), q1 = fma(c[6], v2, p45);
     return fma(q1, v2 * v2, q0);
-}
-
-UKFB_D double cos_sqrt_poly(double v)
-{
-    return poly6(v, 1.0, -0x1.fffffffffffffp-2, 0x1.5555555555421p-5, -0x1.6c16c16bdd04ep-10, 0x1.a01a00fb1bc6fp-16,
-                 -0x1.27e40964b47d4p-22, 0x1.1d8d32755f8fbp-29);
-}
-
-UKFB_D double sinc_sqrt_poly(double v)
-{
-    return poly6(v, 1.0, -0x1.5555555555555p-3, 0x1.11111111110bfp-7, -0x1.a01a019ffb337p-13, 0x1.71de39fd64b1fp-19,
-                 -0x1.ae63543245d1fp-26, 0x1.5fac6e0083f22p-33);
 }
 
 /* atan(t)/t as a function of u = t*t, u <= 0.09 */
 UKFB_D double atan_over_t_poly(double u)
 {
+    const double* c = SO3_ATAN_C;
     const double u2 = u * u, u4 = u2 * u2;
-    const double p01 = fma(-0x1.5555555555500p-2, u, 1.0);
-    const double p23 = fma(-0x1.2492491c0c582p-3, u, 0x1.999999998a517p-3);
-    const double p45 = fma(-0x1.745c4ca68d45dp-4, u, 0x1.c71c6cf04ff82p-4);
-    const double p67 = fma(-0x1.0fcd05c851591p-4, u, 0x1.3aff6b481f0f7p-4);
-    const double p89 = fma(-0x1.229f36308eeefp-5, u, 0x1.c90783e417298p-5);
+    const double p01 = fma(c[1], u, c[0]), p23 = fma(c[3], u, c[2]), p45 = fma(c[5], u, c[4]);
+    const double p67 = fma(c[7], u, c[6]), p89 = fma(c[9], u, c[8]);
     const double q0 = fma(p23, u2, p01), q1 = fma(p67, u2, p45);
     return fma(fma(p89, u4, q1), u4, q0);
 }
 
-/* MTK cos_sinc_sqrt: (cos sqrt(x2), sinc sqrt(x2)), the literal expressions (Taylor pair below 2^-13). */
-UKFB_D void cos_sinc_sqrt(double x2, double& c, double& sinc)
+/* MTK cos_sinc_sqrt: (cos sqrt(x2), sinc sqrt(x2)), the literal expressions (Taylor pair below 2^-13).
+ * Out of line: only reached for half angles above 0.5 rad. */
+UKFB_DNI void cos_sinc_sqrt(double x2, double* c_out, double* sinc_out)
 {
     if (x2 >= UKFB_TAYLOR_N_BOUND) {
         const double x = sqrt(x2);
-        double s;
+        double s, c;
         ukfb_sincos(x, &s, &c);
-        sinc = s / x;
+        *c_out = c;
+        *sinc_out = s / x;
     } else {
         /* 1 - x2/2 + x2^2/24 - x2^3/720 and 1 - x2/6 + x2^2/120 - x2^3/5040, term by term
          * as mtkmath.hpp does */
@@ -152,9 +149,18 @@ UKFB_D void cos_sinc_sqrt(double x2, double& c, double& sinc)
         cosi += term;
         term *= (1.0 / 7.0);
         si += term;
-        c = cosi;
-        sinc = si;
+        *c_out = cosi;
+        *sinc_out = si;
     }
+}
+
+/* the literal MTK::SO3::log scale (2/nv) atan(nv/w), nv floored at MTK::tolerance.  Out of line: only
+ * reached for relative rotations above about 33 degrees. */
+UKFB_DNI double so3_log_scale_slow(double nv2, double w)
+{
+    double nv = sqrt(nv2);
+    if (nv < UKFB_MTK_TOLERANCE) nv = UKFB_MTK_TOLERANCE;
+    return 2.0 / nv * atan(nv / w);
 }
 
 /* MTK::SO3::exp(v, scale): w = cos(|v| scale/2), vec = sinc(|v| scale/2) (scale/2) v */
@@ -165,10 +171,11 @@ UKFB_D void so3_exp(const double* v, double scale, double* q)
     const double x2 = half * half * norm2;
     double c, sinc;
     if (x2 <= SO3_EXP_FAST_X2) {
-        c = cos_sqrt_poly(x2);
-        sinc = sinc_sqrt_poly(x2);
+        const double x4 = x2 * x2;
+        c = poly6(x2, x4, SO3_COS_C);
+        sinc = poly6(x2, x4, SO3_SINC_C);
     } else {
-        cos_sinc_sqrt(x2, c, sinc);
+        cos_sinc_sqrt(x2, &c, &sinc);
     }
     const double mult = sinc * half;
     q[0] = mult * v[0];
@@ -189,9 +196,7 @@ UKFB_D void so3_log(const double* q, double* out)
         const double t = nv2 * rw;
         s = (2.0 * rw) * atan_over_t_poly(t * rw);
     } else {
-        double nv = sqrt(nv2);
-        if (nv < UKFB_MTK_TOLERANCE) nv = UKFB_MTK_TOLERANCE;
-        s = 2.0 / nv * atan(nv / w);
+        s = so3_log_scale_slow(nv2, w);
     }
     out[0] = s * q[0];
     out[1] = s * q[1];

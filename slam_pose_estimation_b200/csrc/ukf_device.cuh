@@ -75,7 +75,9 @@ struct Smem {
     static constexpr int OFF_DELTA = OFF_SIG + F::LP;   /* K * innovation */
     static constexpr int OFF_IMU = OFF_DELTA + F::N;    /* stored acceleration [0:3], rotation rate [3:6] */
     static constexpr int OFF_DT = OFF_IMU + 6;          /* this tick's delta time */
-    static constexpr int FS = (OFF_DT + 1) | 1;         /* odd stride: lane-per-filter accesses are conflict-free */
+    static constexpr int OFF_Z = OFF_DT + 1;            /* this tick's measurement, zero padded to 3 */
+    static constexpr int OFF_R = OFF_Z + 3;             /* its covariance, identity padded to 3x3 */
+    static constexpr int FS = (OFF_R + 9) | 1;          /* odd stride: lane-per-filter accesses are conflict-free */
     /* per warp scratch */
     static constexpr int OFF_D = G * FS + ((G * FS) & 1); /* deviation matrix [DT_ROWS][DT_LD] */
     static constexpr int OFF_SXZ = OFF_D + DT_ROWS * DT_LD;
@@ -233,26 +235,6 @@ UKFB_D bool cholesky_rows(double* sig, int lane, bool active)
     return ok;
 }
 
-/* ---- sigma points: X0 = mu + delta, X(2j+1) = mu + (delta + L[:,j]), X(2j+2) = mu + (delta - L[:,j]) */
-template <class F>
-UKFB_D void sigma_generate(const double* L, const double* mu, const double* delta, int lane, double* x)
-{
-    UKFB_UNROLL
-    for (int i = 0; i < F::MU; ++i) x[i] = mu[i];
-    const bool col = lane >= 1 && lane < F::NS;
-    const int j = col ? (lane - 1) >> 1 : 0;
-    const bool plus = (lane & 1) != 0;
-    double d[F::N];
-    UKFB_UNROLL
-    for (int i = 0; i < F::N; ++i) {
-        const bool in = col && i >= j;
-        const double l = in ? L[tri(i, in ? j : 0)] : 0.0;
-        const double dl = delta ? delta[i] : 0.0;
-        d[i] = plus ? dl + l : dl - l;
-    }
-    state_boxplus<F>(x, d, 1.0);
-}
-
 /* ---- process models ------------------------------------------------------------- */
 
 /* PoseUKF.cpp:75-83 / :88-97 */
@@ -346,7 +328,6 @@ UKFB_D void meas_boxminus(const double* z, const double* o, bool rot, double* re
 }
 
 /* ---- warp context ----------------------------------------------------------------- */
-template <class F>
 struct Warp {
     double* D;   /* deviation matrix D[c * DT_LD + p]: component c of sigma point p */
     double* SXZ;
@@ -360,20 +341,34 @@ struct Warp {
     int lane;
 };
 
-/* sum over the sigma points of row c of the deviation matrix.  Lane c starts at column c so
- * that the N lanes of one load hit distinct banks (row stride 36: 5c + s mod 16); the padding
- * columns NS..27 hold zeros. */
-UKFB_D double row_sum(const double* D, int c)
+/* Row sums of the deviation matrix over the sigma points: rows 0..15 by lanes (c = lane & 15), each row split
+ * between the two half-warps (columns 0..15 and 16..27) and combined by one shuffle.  Within a half-warp lane c
+ * visits the columns of each aligned group of four in the order s ^ (c >> 2), which puts the 16 lanes on 16
+ * distinct 8-byte banks (row stride 36 = 4 mod 16).  The padding columns NS..27 hold zeros. */
+UKFB_D double row_sum(const double* D, int lane)
 {
-    const double* row = D + c * DT_LD;
-    double a = 0.0;
+    const int c = lane & 15, h = lane >> 4, k = c >> 2;
+    const double* base = D + c * DT_LD + 16 * h;
+    const double* b0 = base + (0 ^ k);
+    const double* b1 = base + (1 ^ k);
+    const double* b2 = base + (2 ^ k);
+    const double* b3 = base + (3 ^ k);
+    double a0 = 0.0, a1 = 0.0;
     UKFB_UNROLL
-    for (int s = 0; s < DT_COLS; ++s) {
-        int p = s + c;
-        if (p >= DT_COLS) p -= DT_COLS;
-        a += row[p];
+    for (int g4 = 0; g4 < 3; ++g4) {
+        a0 += b0[4 * g4];
+        a1 += b1[4 * g4];
+        a0 += b2[4 * g4];
+        a1 += b3[4 * g4];
     }
-    return a;
+    if (h == 0) { /* the first half-warp has one more group: columns 12..15 */
+        a0 += b0[12];
+        a1 += b1[12];
+        a0 += b2[12];
+        a1 += b3[12];
+    }
+    const double a = a0 + a1;
+    return a + warp_shfl(a, lane ^ 16);
 }
 
 /* x / NS as the reference's `mean_delta /= X.size()` computes it (a true division), through
@@ -386,12 +381,280 @@ UKFB_D double div_ns(double x)
     return fma(fma(-double(NS), q, x), rinv, q);
 }
 
-/* ukfom sigma_points_mean on the state manifold: ref = X0; loop { md = mean(X_i [-] ref);
- * ref [+]= md } while (|md| > tol && ++i < max_it).  Every lane ends with the same ref. */
-template <class F>
-UKFB_D uint32_t manifold_mean(Warp<F>& w, const double* x, double* ref)
+/* DMMA fragment of component tile I (rows 8I..8I+7 of D) and sigma points 4s..4s+3: serves as the
+ * A operand (component x point) of tile I and as the B operand (point x component) of tile I. */
+UKFB_D double frag(const double* D, int lane, int I, int s) { return D[(8 * I + (lane >> 2)) * DT_LD + 4 * s + (lane & 3)]; }
+
+/* symmetric lookup into packed-lower Q */
+UKFB_D double q_sym(const double* Qp, int i, int j) { return i >= j ? UKFB_LDG(Qp + tri(i, j)) : UKFB_LDG(Qp + tri(j, i)); }
+
+/* ---- one sigma-point pass over one filter by one warp --------------------------------------------
+ * MODE_PREDICT  ukfom predict (App. A.3): sigma points from the factor, process model, manifold mean,
+ *               covariance + process noise.
+ * MODE_UPDATE   first half of ukfom update (App. A.4): sigma points, measurement model, innovation statistics,
+ *               gain, sigma <- sigma_prior - K S K^T, delta = K innov.
+ * MODE_APPLY    apply_delta (App. A.4): sigma points around mu [+] delta, manifold mean, covariance.
+ * `fr` is the filter's shared-memory record; its sigma slot holds the Cholesky factor at entry and the new
+ * covariance at exit.  MODE is a compile-time constant: three specialised copies, no mode branches at run time. */
+constexpr int MODE_PREDICT = 0, MODE_UPDATE = 1, MODE_APPLY = 2;
+
+template <class F, int G, int MODE>
+UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b, const int kind, double* fr,
+                           const double* sigma_prior)
 {
+    constexpr int mode = MODE;
+    typedef Smem<F, G> SM;
+    constexpr int ZC = F::N; /* rows of D holding the measurement deviations */
+    const StepParams& p = *pp;
     const int lane = w.lane;
+    double* sig = fr + SM::OFF_SIG;
+    double* mu = fr + SM::OFF_MU;
+    double* delta = fr + SM::OFF_DELTA;
+    uint32_t st = 0;
+
+    /* ---- sigma points: X0 = mu + delta, X(2j+1) = mu + (delta + L[:,j]), X(2j+2) = mu + (delta - L[:,j]) */
+    double x[F::MU];
+    {
+        UKFB_UNROLL
+        for (int i = 0; i < F::MU; ++i) x[i] = mu[i];
+        const bool col = lane >= 1 && lane < F::NS;
+        const int j = col ? (lane - 1) >> 1 : 0;
+        const double sgn = col ? ((lane & 1) ? 1.0 : -1.0) : 0.0;
+        const double* Lc = sig + j; /* column j of the packed factor: element (i, j) at tri(i, 0) + j */
+        double d[F::N];
+        UKFB_UNROLL
+        for (int i = 0; i < F::N; ++i) {
+            const double l = (i >= j) ? Lc[tri(i, 0)] : 0.0; /* i < j never reads past row i */
+            d[i] = sgn * l;
+        }
+        if (mode == MODE_APPLY) {
+            UKFB_UNROLL
+            for (int i = 0; i < F::N; ++i) d[i] += delta[i];
+        }
+        state_boxplus<F>(x, d, 1.0);
+    }
+
+    double dt = 0.0;
+    bool has_acc = false;
+    const double* Qp = p.Q + b * p.q_stride;
+    if (mode == MODE_PREDICT) {
+        /* ---- process model; acceleration branch of PoseUKF.cpp:188-193 */
+        const double* fimu = fr + SM::OFF_IMU;
+        dt = fr[SM::OFF_DT];
+        const double acc[3] = {fimu[0], fimu[1], fimu[2]};
+        if (F::KIND == 0)
+            has_acc = (fabs(acc[0]) <= 1.79769313486231570e308) && (fabs(acc[1]) <= 1.79769313486231570e308) &&
+                      (fabs(acc[2]) <= 1.79769313486231570e308);
+        /* rotated blocks of Q: rot * Q[blk] * rot^T with the PRIOR orientation (PoseUKF.cpp:182-185,
+         * OrientationUKF.cpp:81-85) */
+        if (!has_acc && lane < 18) {
+            double Rm[9];
+            quat_matrix(mu + F::ROT, Rm);
+            const int off = lane < 9 ? F::QB0 : F::QB1;
+            const int e = lane < 9 ? lane : lane - 9;
+            const int r = e / 3, c = e % 3;
+            double acc_rc = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                double t = 0.0;
+                UKFB_UNROLL
+                for (int l = 0; l < 3; ++l) t += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
+                acc_rc += t * Rm[c * 3 + k];
+            }
+            w.QR[lane] = acc_rc;
+        }
+        if (F::KIND == 0) {
+            process_model_pose(x, dt, has_acc, acc);
+        } else {
+            const double omega[3] = {fimu[3], fimu[4], fimu[5]};
+            process_model_ori(x, dt, acc, omega, p.neg_inv_tau_g, p.neg_inv_tau_a, p.earth);
+        }
+    }
+
+    if (mode == MODE_UPDATE) {
+        const bool rot = (F::KIND == 0) && kind == UKFB_MEAS_POSE_ORIENTATION;
+        /* prior covariance entries this lane will downdate (fragment-shaped ownership, see below); issued
+         * early so that the L2 round trip hides behind the measurement statistics */
+        const int fr_r = lane >> 2, fr_c = 2 * (lane & 3);
+        double sp00[2], sp10[2], sp11[2];
+        UKFB_UNROLL
+        for (int e = 0; e < 2; ++e) {
+            sp00[e] = (fr_c + e <= fr_r) ? UKFB_LDCG(sigma_prior + tri(fr_r, fr_c + e)) : 0.0;
+            sp10[e] = (8 + fr_r < F::N) ? UKFB_LDCG(sigma_prior + tri(8 + fr_r, fr_c + e)) : 0.0;
+            sp11[e] = (8 + fr_r < F::N && fr_c + e <= fr_r) ? UKFB_LDCG(sigma_prior + tri(8 + fr_r, 8 + fr_c + e)) : 0.0;
+        }
+
+        double z[4];
+        measure<F>(x, kind, z);
+
+        /* mean of Z (ukfom sigma_points_mean on the measurement space) */
+        double zref[4];
+        if (lane == 0) {
+            w.BC[0] = z[0], w.BC[1] = z[1], w.BC[2] = z[2], w.BC[3] = z[3];
+        }
+        __syncwarp();
+        zref[0] = w.BC[0], zref[1] = w.BC[1], zref[2] = w.BC[2], zref[3] = w.BC[3];
+        {
+            int it = 0;
+            while (true) {
+                double dz[3];
+#if UKFB_EUCLID_MEAS_DIRECT_MEAN
+                if (!rot)
+                    dz[0] = z[0], dz[1] = z[1], dz[2] = z[2];
+                else
+#endif
+                    meas_boxminus(z, zref, rot, dz);
+                if (lane < F::NS) {
+                    UKFB_UNROLL
+                    for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
+                }
+                __syncwarp();
+                const double rs = row_sum(w.D, lane);
+                if (lane >= ZC && lane < ZC + 3) w.MD[lane - ZC] = div_ns<F::NS>(rs);
+                __syncwarp();
+                const double md[3] = {w.MD[0], w.MD[1], w.MD[2]};
+                const double n2 = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
+                __syncwarp();
+#if UKFB_EUCLID_MEAS_DIRECT_MEAN
+                if (!rot) {
+                    zref[0] = md[0], zref[1] = md[1], zref[2] = md[2];
+                    break;
+                }
+#endif
+                if (rot) {
+                    so3_boxplus(zref, md, 1.0);
+                } else {
+                    zref[0] += md[0];
+                    zref[1] += md[1];
+                    zref[2] += md[2];
+                }
+                if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
+                if (++it >= UKFB_MEAN_MAX_IT) {
+                    st = UKFB_STATUS_MEAN_NO_CONVERGE;
+                    break;
+                }
+            }
+        }
+
+        /* deviations: dz = Z_i [-] zbar, dx = X_i [-] mu (the PRIOR mu, App. A.4) */
+        {
+            double dz[3];
+            meas_boxminus(z, zref, rot, dz);
+            double mur[F::MU];
+            UKFB_UNROLL
+            for (int i = 0; i < F::MU; ++i) mur[i] = mu[i];
+            double dx[F::N];
+            state_boxminus<F>(x, mur, dx);
+            if (lane < F::NS) {
+                UKFB_UNROLL
+                for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = dx[i];
+                UKFB_UNROLL
+                for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
+            }
+        }
+        __syncwarp();
+
+        /* S = 0.5 sum dz dz^T + R (R padded with identity to 3x3);  Sxz = 0.5 sum dx dz^T:
+         * component tile 1 (rows 8..15 of D) holds dz; two DMMA tiles per 4 sigma points */
+        {
+            double c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+            UKFB_UNROLL
+            for (int s = 0; s < DT_COLS / 4; ++s) {
+                const double f0 = frag(w.D, lane, 0, s), f1 = frag(w.D, lane, 1, s);
+                warp_dmma(c01[0], c01[1], f0, f1);
+                warp_dmma(c11[0], c11[1], f1, f1);
+            }
+            const double* Rm = fr + SM::OFF_R;
+            UKFB_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                const int cz = 8 + fr_c + e - ZC; /* measurement component of this column */
+                if (cz >= 0 && cz < 3) {
+                    w.SXZ[fr_r * 3 + cz] = 0.5 * c01[e];
+                    if (8 + fr_r < F::N) w.SXZ[(8 + fr_r) * 3 + cz] = 0.5 * c11[e];
+                    const int az = 8 + fr_r - ZC;
+                    if (az >= 0 && az < 3) w.SM[az * 3 + cz] = 0.5 * c11[e] + Rm[az * 3 + cz];
+                }
+            }
+        }
+        __syncwarp();
+
+        /* S^-1 by cofactors (Eigen fixed-size inverse), every lane redundantly */
+        double S[9], Si[9];
+        UKFB_UNROLL
+        for (int i = 0; i < 9; ++i) S[i] = w.SM[i];
+        {
+            const double c00 = S[4] * S[8] - S[5] * S[7];
+            const double c10 = S[7] * S[2] - S[8] * S[1];
+            const double c20 = S[1] * S[5] - S[2] * S[4];
+            const double det = c00 * S[0] + c10 * S[3] + c20 * S[6];
+            const double invdet = 1.0 / det;
+            Si[0] = c00 * invdet;
+            Si[1] = c10 * invdet;
+            Si[2] = c20 * invdet;
+            Si[3] = (S[5] * S[6] - S[3] * S[8]) * invdet;
+            Si[4] = (S[8] * S[0] - S[6] * S[2]) * invdet;
+            Si[5] = (S[2] * S[3] - S[0] * S[5]) * invdet;
+            Si[6] = (S[3] * S[7] - S[4] * S[6]) * invdet;
+            Si[7] = (S[6] * S[1] - S[7] * S[0]) * invdet;
+            Si[8] = (S[0] * S[4] - S[1] * S[3]) * invdet;
+        }
+        /* innovation z [-] zbar */
+        double innov[3];
+        {
+            const double* zm = fr + SM::OFF_Z;
+            double zin[4] = {zm[0], zm[1], zm[2], 1.0};
+            if (rot) {
+                const double v[3] = {zm[0], zm[1], zm[2]};
+                so3_exp(v, 1.0, zin); /* PoseUKF.cpp:135 */
+            }
+            meas_boxminus(zin, zref, rot, innov);
+        }
+        /* K = Sxz S^-1, KS = K S */
+        for (int e = lane; e < 3 * F::N; e += 32) {
+            const int i = e / 3, c = e % 3;
+            double k3[3];
+            UKFB_UNROLL
+            for (int cc = 0; cc < 3; ++cc) {
+                double s = 0.0;
+                UKFB_UNROLL
+                for (int k = 0; k < 3; ++k) s += w.SXZ[i * 3 + k] * Si[k * 3 + cc];
+                k3[cc] = s;
+            }
+            double ks = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + c];
+            w.KM[e] = k3[c];
+            w.KS[e] = ks;
+        }
+        __syncwarp();
+        /* sigma <- sigma_prior - (K S) K^T, lower triangle; overwrites the factor, which is no longer needed */
+        UKFB_UNROLL
+        for (int e = 0; e < 2; ++e) {
+            const int i0 = fr_r, i1 = 8 + fr_r, j0 = fr_c + e, j1 = 8 + fr_c + e;
+            double s00 = 0.0, s10 = 0.0, s11 = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                s00 += w.KS[i0 * 3 + k] * w.KM[j0 * 3 + k];
+                if (i1 < F::N) s10 += w.KS[i1 * 3 + k] * w.KM[j0 * 3 + k];
+                if (i1 < F::N && j1 < F::N) s11 += w.KS[i1 * 3 + k] * w.KM[j1 * 3 + k];
+            }
+            if (j0 <= i0) sig[tri(i0, j0)] = sp00[e] - s00;
+            if (i1 < F::N) sig[tri(i1, j0)] = sp10[e] - s10;
+            if (i1 < F::N && j0 <= i0) sig[tri(i1, j1)] = sp11[e] - s11;
+        }
+        if (lane < F::N) {
+            double s = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) s += w.KM[lane * 3 + k] * innov[k];
+            delta[lane] = s;
+        }
+        __syncwarp();
+        return st;
+    }
+
+    /* ---- ukfom sigma_points_mean on the state manifold: ref = X0; loop { md = mean(X_i [-] ref);
+     * ref [+]= md } while (|md| > tol && ++i < max_it).  Every lane ends with the same ref. */
+    double ref[F::MU];
     if (lane == 0) {
         UKFB_UNROLL
         for (int i = 0; i < F::MU; ++i) w.BC[i] = x[i];
@@ -399,366 +662,98 @@ UKFB_D uint32_t manifold_mean(Warp<F>& w, const double* x, double* ref)
     __syncwarp();
     UKFB_UNROLL
     for (int i = 0; i < F::MU; ++i) ref[i] = w.BC[i];
-    uint32_t st = 0;
-    int it = 0, passes = 0;
-    while (true) {
-        double d[F::N];
-        state_boxminus<F>(x, ref, d);
-        if (lane < F::NS) {
-            UKFB_UNROLL
-            for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = d[i];
-        }
-        __syncwarp();
-        if (lane < F::N) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, lane));
-        __syncwarp();
-        double md[F::N];
-        double n2 = 0.0;
-        UKFB_UNROLL
-        for (int i = 0; i < F::N; ++i) {
-            md[i] = w.MD[i];
-            n2 += md[i] * md[i];
-        }
-        state_boxplus<F>(ref, md, 1.0);
-        ++passes;
-        __syncwarp();
-        if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break; /* |md| > tol */
-        if (++it >= UKFB_MEAN_MAX_IT) {
-            st = UKFB_STATUS_MEAN_NO_CONVERGE;
-            break;
-        }
-    }
-    if (lane == 0) w.HP[passes < 7 ? passes : 7]++;
-    return st;
-}
-
-/* deviations of every sigma point from `ref` into rows 0..N-1 of the deviation matrix */
-template <class F>
-UKFB_D void write_deviations(Warp<F>& w, const double* x, const double* ref)
-{
-    double d[F::N];
-    state_boxminus<F>(x, ref, d);
-    if (w.lane < F::NS) {
-        UKFB_UNROLL
-        for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + w.lane] = d[i];
-    }
-}
-
-/* DMMA fragment of component tile I (rows 8I..8I+7 of D) and sigma points 4s..4s+3: serves as the
- * A operand (component x point) of tile I and as the B operand (point x component) of tile I. */
-UKFB_D double frag(const double* D, int lane, int I, int s) { return D[(8 * I + (lane >> 2)) * DT_LD + 4 * s + (lane & 3)]; }
-
-/* covariance of the deviations in rows 0..N-1 of D (already written, synced):
- * out(i,j) = 0.5 * sum_p d_i d_j + noise(i,j), lower triangle, three 8x8 tiles on the DMMA path. */
-template <class F, class Noise>
-UKFB_D void cov_store(Warp<F>& w, double* out, Noise noise)
-{
-    const int lane = w.lane;
-    double c00[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-    UKFB_UNROLL
-    for (int s = 0; s < DT_COLS / 4; ++s) {
-        const double f0 = frag(w.D, lane, 0, s), f1 = frag(w.D, lane, 1, s);
-        warp_dmma(c00[0], c00[1], f0, f0);
-        warp_dmma(c10[0], c10[1], f1, f0);
-        warp_dmma(c11[0], c11[1], f1, f1);
-    }
-    const int r = lane >> 2, c = 2 * (lane & 3);
-    UKFB_UNROLL
-    for (int e = 0; e < 2; ++e) {
-        if (c + e <= r) out[tri(r, c + e)] = 0.5 * c00[e] + noise(r, c + e);
-        if (8 + r < F::N) out[tri(8 + r, c + e)] = 0.5 * c10[e] + noise(8 + r, c + e);
-        if (8 + r < F::N && c + e <= r) out[tri(8 + r, 8 + c + e)] = 0.5 * c11[e] + noise(8 + r, 8 + c + e);
-    }
-}
-
-/* symmetric lookup into packed-lower Q */
-UKFB_D double q_sym(const double* Qp, int i, int j) { return i >= j ? UKFB_LDG(Qp + tri(i, j)) : UKFB_LDG(Qp + tri(j, i)); }
-
-/* ---- predict of one filter by one warp (ukfom predict, App. A.3) --------------------- */
-/* sig holds the Cholesky factor at entry and the predicted covariance at exit. */
-template <class F>
-UKFB_D uint32_t sigma_predict(Warp<F>& w, const StepParams& p, long long b, double* sig, double* mu, const double* fimu, double dt)
-{
-    const int lane = w.lane;
-    const double* Qp = p.Q + b * p.q_stride;
-
-    /* acceleration branch of PoseUKF.cpp:188-193 */
-    bool has_acc = false;
-    const double acc[3] = {fimu[0], fimu[1], fimu[2]};
-    const double omega[3] = {fimu[3], fimu[4], fimu[5]};
-    if (F::KIND == 0)
-        has_acc = (fabs(acc[0]) <= 1.79769313486231570e308) && (fabs(acc[1]) <= 1.79769313486231570e308) &&
-                  (fabs(acc[2]) <= 1.79769313486231570e308);
-
-    /* rotated blocks of Q: rot * Q[blk] * rot^T (PoseUKF.cpp:184-185, OrientationUKF.cpp:84-85) */
-    if (!has_acc && lane < 18) {
-        double Rm[9];
-        quat_matrix(mu + F::ROT, Rm);
-        const int off = lane < 9 ? F::QB0 : F::QB1;
-        const int e = lane < 9 ? lane : lane - 9;
-        const int r = e / 3, c = e % 3;
-        double acc_rc = 0.0;
-        UKFB_UNROLL
-        for (int k = 0; k < 3; ++k) {
-            double t = 0.0;
-            UKFB_UNROLL
-            for (int l = 0; l < 3; ++l) t += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
-            acc_rc += t * Rm[c * 3 + k];
-        }
-        w.QR[lane] = acc_rc;
-    }
-
-    double x[F::MU];
-    sigma_generate<F>(sig, mu, nullptr, lane, x);
-    if (F::KIND == 0)
-        process_model_pose(x, dt, has_acc, acc);
-    else
-        process_model_ori(x, dt, acc, omega, p.neg_inv_tau_g, p.neg_inv_tau_a, p.earth);
-
-    double ref[F::MU];
-    uint32_t st = manifold_mean<F>(w, x, ref);
-    write_deviations<F>(w, x, ref);
-    __syncwarp();
-
-    const double scale = F::KIND == 0 ? dt : dt * dt; /* PoseUKF.cpp:186 vs OrientationUKF.cpp:86 */
-    const double* QR = w.QR;
-    const double* acov = p.acc_cov ? p.acc_cov + b * 9 : nullptr;
-    cov_store<F>(w, sig, [=](int i, int j) -> double {
-        if (F::KIND == 0 && has_acc) {
-            /* shadowing local of PoseUKF.cpp:190-191: unrotated, unscaled Q, velocity block = 2 acc.cov */
-            if (i >= 6 && i < 9 && j >= 6 && j < 9) return 2.0 * UKFB_LDG(acov + (i - 6) * 3 + (j - 6));
-            return q_sym(Qp, i, j);
-        }
-        if (i >= F::QB0 && i < F::QB0 + 3 && j >= F::QB0 && j < F::QB0 + 3)
-            return scale * QR[(i - F::QB0) * 3 + (j - F::QB0)];
-        if (i >= F::QB1 && i < F::QB1 + 3 && j >= F::QB1 && j < F::QB1 + 3)
-            return scale * QR[9 + (i - F::QB1) * 3 + (j - F::QB1)];
-        return scale * q_sym(Qp, i, j);
-    });
-    if (lane == 0) {
-        UKFB_UNROLL
-        for (int i = 0; i < F::MU; ++i) mu[i] = ref[i];
-    }
-    __syncwarp();
-    return st;
-}
-
-/* ---- apply_delta of one filter (App. A.4): sigma points around mu [+] delta from the
- * factor in sig, manifold mean, covariance (no additive noise) back into sig ------------- */
-template <class F>
-UKFB_D uint32_t sigma_apply_delta(Warp<F>& w, double* sig, double* mu, const double* delta)
-{
-    double x[F::MU];
-    sigma_generate<F>(sig, mu, delta, w.lane, x);
-    double ref[F::MU];
-    uint32_t st = manifold_mean<F>(w, x, ref);
-    write_deviations<F>(w, x, ref);
-    __syncwarp();
-    cov_store<F>(w, sig, [](int, int) -> double { return 0.0; });
-    if (w.lane == 0) {
-        UKFB_UNROLL
-        for (int i = 0; i < F::MU; ++i) mu[i] = ref[i];
-    }
-    __syncwarp();
-    return st;
-}
-
-/* ---- first half of update of one filter (App. A.4): innovation statistics, gain,
- * sigma <- sigma_prior - K S K^T, delta = K innov.  sig holds the Cholesky factor at entry;
- * sigma_prior is the covariance spilled to the filter's HBM record before the factorisation. */
-template <class F>
-UKFB_D uint32_t sigma_update(Warp<F>& w, const StepParams& p, long long b, int tick, int kind, double* sig,
-                             const double* sigma_prior, const double* mu, double* delta)
-{
-    constexpr int ZC = F::N; /* rows of D holding the measurement deviations */
-    const int lane = w.lane;
-    const bool rot = (F::KIND == 0) && kind == UKFB_MEAS_POSE_ORIENTATION;
-    const int m = meas_dim(kind);
-    uint32_t st = 0;
-
-    double x[F::MU];
-    sigma_generate<F>(sig, mu, nullptr, lane, x);
-    double z[4];
-    measure<F>(x, kind, z);
-
-    /* mean of Z */
-    double zref[4];
-    if (lane == 0) {
-        w.BC[0] = z[0], w.BC[1] = z[1], w.BC[2] = z[2], w.BC[3] = z[3];
-    }
-    __syncwarp();
-    zref[0] = w.BC[0], zref[1] = w.BC[1], zref[2] = w.BC[2], zref[3] = w.BC[3];
-#if UKFB_EUCLID_MEAS_DIRECT_MEAN
-    if (!rot) {
-        if (lane < F::NS) {
-            UKFB_UNROLL
-            for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = z[c];
-        }
-        __syncwarp();
-        if (lane < 3) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, ZC + lane));
-        __syncwarp();
-        zref[0] = w.MD[0], zref[1] = w.MD[1], zref[2] = w.MD[2];
-        __syncwarp();
-    } else
-#endif
     {
-        int it = 0;
+        int it = 0, passes = 0;
+        bool converged = false;
         while (true) {
-            double dz[3];
-            meas_boxminus(z, zref, rot, dz);
+            /* deviations from the current reference; after convergence the same code produces the
+             * deviations from the final mean for the covariance */
+            double d[F::N];
+            state_boxminus<F>(x, ref, d);
             if (lane < F::NS) {
                 UKFB_UNROLL
-                for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
+                for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = d[i];
             }
             __syncwarp();
-            if (lane < 3) w.MD[lane] = div_ns<F::NS>(row_sum(w.D, ZC + lane));
+            if (converged) break;
+            const double rs = row_sum(w.D, lane);
+            if (lane < F::N) w.MD[lane] = div_ns<F::NS>(rs);
             __syncwarp();
-            const double md[3] = {w.MD[0], w.MD[1], w.MD[2]};
-            const double n2 = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
-            if (rot) {
-                so3_boxplus(zref, md, 1.0);
-            } else {
-                zref[0] += md[0];
-                zref[1] += md[1];
-                zref[2] += md[2];
+            double md[F::N];
+            double n2 = 0.0;
+            UKFB_UNROLL
+            for (int i = 0; i < F::N; ++i) {
+                md[i] = w.MD[i];
+                n2 += md[i] * md[i];
             }
+            state_boxplus<F>(ref, md, 1.0);
+            ++passes;
             __syncwarp();
-            if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
-            if (++it >= UKFB_MEAN_MAX_IT) {
+            if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) converged = true; /* |md| <= tol */
+            else if (++it >= UKFB_MEAN_MAX_IT) {
                 st = UKFB_STATUS_MEAN_NO_CONVERGE;
-                break;
+                converged = true;
             }
         }
+        if (lane == 0) w.HP[passes < 7 ? passes : 7]++;
     }
 
-    /* deviations: dz = Z_i [-] zbar, dx = X_i [-] mu (the PRIOR mu, App. A.4) */
+    /* ---- covariance of the deviations: out(i,j) = 0.5 * sum_p d_i d_j + noise(i,j), lower triangle,
+     * three 8x8 tiles on the DMMA path */
     {
-        double dz[3];
-        meas_boxminus(z, zref, rot, dz);
-        double mur[F::MU];
-        UKFB_UNROLL
-        for (int i = 0; i < F::MU; ++i) mur[i] = mu[i];
-        double dx[F::N];
-        state_boxminus<F>(x, mur, dx);
-        if (lane < F::NS) {
+        const int r = lane >> 2, c = 2 * (lane & 3);
+        double nz00[2] = {0.0, 0.0}, nz10[2] = {0.0, 0.0}, nz11[2] = {0.0, 0.0};
+        if (mode == MODE_PREDICT) {
+            const double scale = F::KIND == 0 ? dt : dt * dt; /* PoseUKF.cpp:186 vs OrientationUKF.cpp:86 */
+            const double* QR = w.QR;
+            const double* acov = p.acc_cov ? p.acc_cov + b * 9 : nullptr;
+            auto noise = [&](int i, int j) -> double {
+                if (F::KIND == 0 && has_acc) {
+                    /* shadowing local of PoseUKF.cpp:190-191: unrotated, unscaled Q, velocity block = 2 acc.cov */
+                    if (i >= 6 && i < 9 && j >= 6 && j < 9) return 2.0 * UKFB_LDG(acov + (i - 6) * 3 + (j - 6));
+                    return q_sym(Qp, i, j);
+                }
+                if (i >= F::QB0 && i < F::QB0 + 3 && j >= F::QB0 && j < F::QB0 + 3)
+                    return scale * QR[(i - F::QB0) * 3 + (j - F::QB0)];
+                if (i >= F::QB1 && i < F::QB1 + 3 && j >= F::QB1 && j < F::QB1 + 3)
+                    return scale * QR[9 + (i - F::QB1) * 3 + (j - F::QB1)];
+                return scale * q_sym(Qp, i, j);
+            };
             UKFB_UNROLL
-            for (int i = 0; i < F::N; ++i) w.D[i * DT_LD + lane] = dx[i];
-            UKFB_UNROLL
-            for (int c = 0; c < 3; ++c) w.D[(ZC + c) * DT_LD + lane] = dz[c];
+            for (int e = 0; e < 2; ++e) {
+                if (c + e <= r) nz00[e] = noise(r, c + e);
+                if (8 + r < F::N) nz10[e] = noise(8 + r, c + e);
+                if (8 + r < F::N && c + e <= r) nz11[e] = noise(8 + r, 8 + c + e);
+            }
         }
-    }
-    __syncwarp();
-
-    /* S = 0.5 sum dz dz^T + R (R padded with identity to 3x3);  Sxz = 0.5 sum dx dz^T:
-     * component tile 1 (rows 8..15 of D) holds dz; two DMMA tiles per 4 sigma points */
-    {
-        double c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+        double c00[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
         UKFB_UNROLL
         for (int s = 0; s < DT_COLS / 4; ++s) {
             const double f0 = frag(w.D, lane, 0, s), f1 = frag(w.D, lane, 1, s);
-            warp_dmma(c01[0], c01[1], f0, f1);
+            warp_dmma(c00[0], c00[1], f0, f0);
+            warp_dmma(c10[0], c10[1], f1, f0);
             warp_dmma(c11[0], c11[1], f1, f1);
         }
-        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
-        const int r = lane >> 2;
         UKFB_UNROLL
         for (int e = 0; e < 2; ++e) {
-            const int cz = 8 + 2 * (lane & 3) + e - ZC; /* measurement component of this column */
-            if (cz >= 0 && cz < 3) {
-                w.SXZ[r * 3 + cz] = 0.5 * c01[e];
-                if (8 + r < F::N) w.SXZ[(8 + r) * 3 + cz] = 0.5 * c11[e];
-                const int az = 8 + r - ZC;
-                if (az >= 0 && az < 3) {
-                    const double rr = (az < m && cz < m) ? UKFB_LDG(Rm + az * p.r_ld + cz) : (az == cz ? 1.0 : 0.0);
-                    w.SM[az * 3 + cz] = 0.5 * c11[e] + rr;
-                }
-            }
+            if (c + e <= r) sig[tri(r, c + e)] = fma(0.5, c00[e], nz00[e]);
+            if (8 + r < F::N) sig[tri(8 + r, c + e)] = fma(0.5, c10[e], nz10[e]);
+            if (8 + r < F::N && c + e <= r) sig[tri(8 + r, 8 + c + e)] = fma(0.5, c11[e], nz11[e]);
         }
     }
-    __syncwarp();
-
-    /* S^-1 by cofactors (Eigen fixed-size inverse), every lane redundantly */
-    double S[9], Si[9];
-    UKFB_UNROLL
-    for (int i = 0; i < 9; ++i) S[i] = w.SM[i];
-    {
-        const double c00 = S[4] * S[8] - S[5] * S[7];
-        const double c10 = S[7] * S[2] - S[8] * S[1];
-        const double c20 = S[1] * S[5] - S[2] * S[4];
-        const double det = c00 * S[0] + c10 * S[3] + c20 * S[6];
-        const double invdet = 1.0 / det;
-        Si[0] = c00 * invdet;
-        Si[1] = c10 * invdet;
-        Si[2] = c20 * invdet;
-        Si[3] = (S[5] * S[6] - S[3] * S[8]) * invdet;
-        Si[4] = (S[8] * S[0] - S[6] * S[2]) * invdet;
-        Si[5] = (S[2] * S[3] - S[0] * S[5]) * invdet;
-        Si[6] = (S[3] * S[7] - S[4] * S[6]) * invdet;
-        Si[7] = (S[6] * S[1] - S[7] * S[0]) * invdet;
-        Si[8] = (S[0] * S[4] - S[1] * S[3]) * invdet;
-    }
-    /* innovation z [-] zbar */
-    double innov[3];
-    {
-        const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-        double zin[4] = {0.0, 0.0, 0.0, 1.0};
-        if (rot) {
-            const double v[3] = {UKFB_LDG(zm + 0), UKFB_LDG(zm + 1), UKFB_LDG(zm + 2)};
-            so3_exp(v, 1.0, zin); /* PoseUKF.cpp:135 */
-        } else {
-            UKFB_UNROLL
-            for (int c = 0; c < 3; ++c) zin[c] = c < m ? UKFB_LDG(zm + c) : 0.0;
-        }
-        meas_boxminus(zin, zref, rot, innov);
-    }
-    /* K = Sxz S^-1, KS = K S */
-    for (int e = lane; e < 3 * F::N; e += 32) {
-        const int i = e / 3, c = e % 3;
-        double k3[3];
+    if (lane == 0) {
         UKFB_UNROLL
-        for (int cc = 0; cc < 3; ++cc) {
-            double s = 0.0;
-            UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) s += w.SXZ[i * 3 + k] * Si[k * 3 + cc];
-            k3[cc] = s;
-        }
-        double ks = 0.0;
-        UKFB_UNROLL
-        for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + c];
-        w.KM[e] = k3[c];
-        w.KS[e] = ks;
-    }
-    __syncwarp();
-    /* sigma <- sigma_prior - (K S) K^T, lower triangle; overwrites the factor, which is no longer needed.
-     * sigma_prior[e] was stored by this same lane (same e = lane + 32 q mapping). */
-    UKFB_UNROLL
-    for (int q = 0; q < (F::LP + 31) / 32; ++q) {
-        const int e = lane + 32 * q;
-        if (e < F::LP) {
-            /* row of packed index e: i (i + 1) / 2 <= e */
-            int i = int((sqrtf(8.0f * float(e) + 1.0f) - 1.0f) * 0.5f);
-            if ((i + 1) * (i + 2) / 2 <= e) ++i;
-            if (i * (i + 1) / 2 > e) --i;
-            const int j = e - i * (i + 1) / 2;
-            double s = 0.0;
-            UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) s += w.KS[i * 3 + k] * w.KM[j * 3 + k];
-            sig[e] = sigma_prior[e] - s;
-        }
-    }
-    if (lane < F::N) {
-        double s = 0.0;
-        UKFB_UNROLL
-        for (int k = 0; k < 3; ++k) s += w.KM[lane * 3 + k] * innov[k];
-        delta[lane] = s;
+        for (int i = 0; i < F::MU; ++i) mu[i] = ref[i];
     }
     __syncwarp();
     return st;
 }
 
 /* ---- the kernel ------------------------------------------------------------------- */
-/* Cholesky phase for every filter of the group whose flag has `bit`: T = 32/G lanes each. */
+/* Cholesky phase for every filter of the group whose flag has `bit`: T = 32/G lanes each.  Out of line: one
+ * copy of the unrolled factorisation serves the three call sites (few values are live across the calls). */
 template <class F, int G>
-UKFB_D void cholesky_phase(double* wsm, int* cflag, int* cstat, int lane, int cnt, int bit, int clear_bits, bool dirty_on_fail)
+UKFB_DNI void cholesky_phase(double* wsm, int* cflag, int* cstat, int lane, int cnt, int bit, int clear_bits, int dirty_on_fail)
 {
     typedef Smem<F, G> SM;
     constexpr int T = 32 / G;
@@ -775,7 +770,7 @@ UKFB_D void cholesky_phase(double* wsm, int* cflag, int* cstat, int lane, int cn
 }
 
 template <class F, int G, int WPB, int MINB>
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepParams p)
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef Smem<F, G> SM;
     UKFB_SMEM_DECL
@@ -786,7 +781,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepPa
     const int cnt = (p.B - first) < G ? int(p.B - first) : G;
 
     double* wsm = ukfb_smem + warp * SM::TOTAL;
-    Warp<F> w;
+    Warp w;
     w.D = wsm + SM::OFF_D;
     w.SXZ = wsm + SM::OFF_SXZ;
     w.KM = wsm + SM::OFF_KM;
@@ -883,16 +878,25 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepPa
                                         : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
                     if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
                     if (kind >= 0) {
+                        /* stage the measurement: z zero padded to 3, R identity padded to 3x3 */
+                        const int m = meas_dim(kind);
+                        const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+                        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
                         bool ok = true;
-                        if (F::KIND == 1) { /* checkMeasurment, OrientationUKF.cpp:67 */
-                            const int m = meas_dim(kind);
-                            const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-                            const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
-                            for (int a = 0; a < m; ++a) ok = ok && (fabs(zm[a]) <= 1.79769313486231570e308);
-                            for (int a = 0; a < m; ++a)
-                                for (int c = 0; c < m; ++c) ok = ok && (fabs(Rm[a * p.r_ld + c]) <= 1.79769313486231570e308);
+                        UKFB_UNROLL
+                        for (int a = 0; a < 3; ++a) {
+                            const double zv = a < m ? zm[a] : 0.0;
+                            ok = ok && (fabs(zv) <= 1.79769313486231570e308);
+                            fr[SM::OFF_Z + a] = zv;
+                            UKFB_UNROLL
+                            for (int c = 0; c < 3; ++c) {
+                                const double rv = (a < m && c < m) ? Rm[a * p.r_ld + c] : (a == c ? 1.0 : 0.0);
+                                ok = ok && (fabs(rv) <= 1.79769313486231570e308);
+                                fr[SM::OFF_R + a * 3 + c] = rv;
+                            }
                         }
-                        if (ok)
+                        /* checkMeasurment: OrientationUKF only (OrientationUKF.cpp:67); PoseUKF never checks */
+                        if (F::KIND == 0 || ok)
                             flags |= CF_UPD;
                         else {
                             st |= UKFB_STATUS_NONFINITE_MEAS;
@@ -909,11 +913,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepPa
 
         /* ---- predict ------------------------------------------------------------------ */
         if (p.do_predict) {
-            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_PRED, CF_PRED | CF_UPD, false);
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_PRED, CF_PRED | CF_UPD, 0);
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_PRED)) continue;
-                double* fr = wsm + g * SM::FS;
-                const uint32_t st = sigma_predict<F>(w, p, first + g, fr + SM::OFF_SIG, fr + SM::OFF_MU, fr + SM::OFF_IMU, fr[SM::OFF_DT]);
+                const uint32_t st = sigma_pass<F, G, MODE_PREDICT>(w, &p, first + g, -1, wsm + g * SM::FS, nullptr);
                 if (lane == 0) {
                     cstat[g] |= int(st);
                     cflag[g] |= CF_DIRTY;
@@ -924,30 +927,27 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const StepPa
 
         /* ---- update --------------------------------------------------------------------- */
         if (p.do_update) {
-            /* spill the prior covariance of the updating filters to their HBM records: the factor is about to
-             * overwrite it in shared memory and sigma - K S K^T needs it back (read by the lane that wrote it) */
+            /* spill the prior covariance of the updating filters to their HBM records (L2 resident): the factor
+             * is about to overwrite it in shared memory and sigma - K S K^T needs it back */
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
                 const double* sig = wsm + g * SM::FS + SM::OFF_SIG;
                 double* dst = rec + g * F::REC + F::MU;
                 for (int e = lane; e < F::LP; e += 32) dst[e] = sig[e];
             }
-            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, false);
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, 0);
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
-                double* fr = wsm + g * SM::FS;
-                const uint32_t st = sigma_update<F>(w, p, first + g, tick, ckind[g], fr + SM::OFF_SIG, rec + g * F::REC + F::MU,
-                                                    fr + SM::OFF_MU, fr + SM::OFF_DELTA);
+                const uint32_t st = sigma_pass<F, G, MODE_UPDATE>(w, &p, first + g, ckind[g], wsm + g * SM::FS, rec + g * F::REC + F::MU);
                 if (lane == 0) cstat[g] |= int(st);
             }
             __syncwarp();
             /* the reference has already replaced sigma by sigma - K S K^T when MTK's assert fires inside
              * apply_delta: on failure keep that matrix (dirty), leave mu alone */
-            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, true);
+            cholesky_phase<F, G>(wsm, cflag, cstat, lane, cnt, CF_UPD, CF_UPD, 1);
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
-                double* fr = wsm + g * SM::FS;
-                const uint32_t st = sigma_apply_delta<F>(w, fr + SM::OFF_SIG, fr + SM::OFF_MU, fr + SM::OFF_DELTA);
+                const uint32_t st = sigma_pass<F, G, MODE_APPLY>(w, &p, first + g, -1, wsm + g * SM::FS, nullptr);
                 if (lane == 0) {
                     cstat[g] |= int(st);
                     cflag[g] |= CF_DIRTY;
