@@ -105,20 +105,18 @@ UKFB_CONSTANT double SO3_ATAN_C[10] = {1.0, -0x1.5555555555500p-2, 0x1.999999998
                                        0x1.c71c6cf04ff82p-4, -0x1.745c4ca68d45dp-4, 0x1.3aff6b481f0f7p-4,
                                        -0x1.0fcd05c851591p-4, 0x1.c90783e417298p-5, -0x1.229f36308eeefp-5};
 
-UKFB_D double poly6(double v, double v2, const double* c)
-{
-    const double p01 = fma(c[1], v, c[0]), p23 = fma(c[3], v, c[2]), p45 = fma(c[5], v, c[4]);
-    const double q0 = fma(p23, v2, p01), q1 = fma(c[6], v2, p45);
-    return fma(q1, v2 * v2, q0);
-}
+/* the coefficient arrays are named directly (not passed as pointers) so that the compiler can address them
+ * as constant-bank operands */
+#define UKFB_POLY6(C, v, v2) \
+    fma(fma(C[6], v2, fma(C[5], v, C[4])), (v2) * (v2), fma(fma(C[3], v, C[2]), v2, fma(C[1], v, C[0])))
 
 /* atan(t)/t as a function of u = t*t, u <= 0.09 */
 UKFB_D double atan_over_t_poly(double u)
 {
-    const double* c = SO3_ATAN_C;
     const double u2 = u * u, u4 = u2 * u2;
-    const double p01 = fma(c[1], u, c[0]), p23 = fma(c[3], u, c[2]), p45 = fma(c[5], u, c[4]);
-    const double p67 = fma(c[7], u, c[6]), p89 = fma(c[9], u, c[8]);
+    const double p01 = fma(SO3_ATAN_C[1], u, SO3_ATAN_C[0]), p23 = fma(SO3_ATAN_C[3], u, SO3_ATAN_C[2]);
+    const double p45 = fma(SO3_ATAN_C[5], u, SO3_ATAN_C[4]), p67 = fma(SO3_ATAN_C[7], u, SO3_ATAN_C[6]);
+    const double p89 = fma(SO3_ATAN_C[9], u, SO3_ATAN_C[8]);
     const double q0 = fma(p23, u2, p01), q1 = fma(p67, u2, p45);
     return fma(fma(p89, u4, q1), u4, q0);
 }
@@ -172,8 +170,8 @@ UKFB_D void so3_exp(const double* v, double scale, double* q)
     double c, sinc;
     if (x2 <= SO3_EXP_FAST_X2) {
         const double x4 = x2 * x2;
-        c = poly6(x2, x4, SO3_COS_C);
-        sinc = poly6(x2, x4, SO3_SINC_C);
+        c = UKFB_POLY6(SO3_COS_C, x2, x4);
+        sinc = UKFB_POLY6(SO3_SINC_C, x2, x4);
     } else {
         cos_sinc_sqrt(x2, &c, &sinc);
     }

@@ -46,7 +46,7 @@ struct ukfb_handle {
     int kind = 0, device = 0;
     long long B = 0;
     int n = 0, MU = 0, LP = 0, REC = 0;
-    int G = 8, WPB = 4, MINB = 4; /* launch shape: filters per warp, warps per block, resident blocks per SM */
+    int G = 8, WPB = 4, MINB = 3; /* launch shape: filters per warp, warps per block, resident blocks per SM */
     cudaStream_t stream = nullptr;
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
@@ -316,8 +316,8 @@ static cudaError_t launch_step_f(const ukfb_handle* h, const StepParams& p)
         case 1642: return launch_step_t<F, 16, 4, 2>(h, p);
         case 1652: return launch_step_t<F, 16, 5, 2>(h, p);
         case 842: return launch_step_t<F, 8, 4, 2>(h, p);
-        case 843: return launch_step_t<F, 8, 4, 3>(h, p);
-        default: return launch_step_t<F, 8, 4, 4>(h, p);
+        case 844: return launch_step_t<F, 8, 4, 4>(h, p);
+        default: return launch_step_t<F, 8, 4, 3>(h, p);
     }
 }
 

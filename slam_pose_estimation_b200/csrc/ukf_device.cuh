@@ -86,8 +86,8 @@ struct Smem {
     static constexpr int OFF_SM = OFF_KS + 40;     /* S, 3x3 */
     static constexpr int OFF_MD = OFF_SM + 10;     /* mean delta broadcast */
     static constexpr int OFF_BC = OFF_MD + 16;     /* state broadcast */
-    static constexpr int OFF_QR = OFF_BC + 16;     /* two rotated 3x3 blocks of Q */
-    static constexpr int OFF_CTL = OFF_QR + 18;    /* ints: flags[G], kind[G], status[G], mean-pass histogram[8] */
+    static constexpr int OFF_NT = OFF_BC + 16;     /* this predict's process noise, packed lower */
+    static constexpr int OFF_CTL = OFF_NT + F::LP + (F::LP & 1); /* ints: flags[G], kind[G], status[G], mean-pass histogram[8] */
     static constexpr int TOTAL_RAW = OFF_CTL + (3 * G + 8 + 1) / 2;
     static constexpr int TOTAL = (TOTAL_RAW + 1) & ~1;
 };
@@ -336,7 +336,7 @@ struct Warp {
     double* SM;
     double* MD;
     double* BC;
-    double* QR;
+    double* NT;
     int* HP; /* mean-pass histogram of this warp, 8 ints */
     int lane;
 };
@@ -445,8 +445,18 @@ UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b
         if (F::KIND == 0)
             has_acc = (fabs(acc[0]) <= 1.79769313486231570e308) && (fabs(acc[1]) <= 1.79769313486231570e308) &&
                       (fabs(acc[2]) <= 1.79769313486231570e308);
-        /* rotated blocks of Q: rot * Q[blk] * rot^T with the PRIOR orientation (PoseUKF.cpp:182-185,
-         * OrientationUKF.cpp:81-85) */
+        /* this step's process noise, packed lower, into the warp's noise table:
+         *   no acceleration: scale * Q with the two rotated blocks rot * Q[blk] * rot^T, rot from the PRIOR
+         *     orientation; scale = dt (PoseUKF.cpp:182-186) or dt^2 (OrientationUKF.cpp:81-86);
+         *   acceleration (the shadowing local of PoseUKF.cpp:190-191): Q unrotated and unscaled, velocity
+         *     block = 2 acc.cov */
+        const double scale = has_acc ? 1.0 : (F::KIND == 0 ? dt : dt * dt);
+        UKFB_UNROLL
+        for (int q = 0; q < (F::LP + 31) / 32; ++q) {
+            const int e = lane + 32 * q;
+            if (e < F::LP) w.NT[e] = scale * UKFB_LDG(Qp + e);
+        }
+        __syncwarp();
         if (!has_acc && lane < 18) {
             double Rm[9];
             quat_matrix(mu + F::ROT, Rm);
@@ -461,7 +471,11 @@ UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b
                 for (int l = 0; l < 3; ++l) t += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
                 acc_rc += t * Rm[c * 3 + k];
             }
-            w.QR[lane] = acc_rc;
+            if (c <= r) w.NT[tri(off + r, off + c)] = scale * acc_rc;
+        }
+        if (F::KIND == 0 && has_acc && lane < 9) {
+            const int r = lane / 3, c = lane % 3;
+            if (c <= r) w.NT[tri(6 + r, 6 + c)] = 2.0 * UKFB_LDG(p.acc_cov + b * 9 + r * 3 + c);
         }
         if (F::KIND == 0) {
             process_model_pose(x, dt, has_acc, acc);
@@ -704,26 +718,11 @@ UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b
         const int r = lane >> 2, c = 2 * (lane & 3);
         double nz00[2] = {0.0, 0.0}, nz10[2] = {0.0, 0.0}, nz11[2] = {0.0, 0.0};
         if (mode == MODE_PREDICT) {
-            const double scale = F::KIND == 0 ? dt : dt * dt; /* PoseUKF.cpp:186 vs OrientationUKF.cpp:86 */
-            const double* QR = w.QR;
-            const double* acov = p.acc_cov ? p.acc_cov + b * 9 : nullptr;
-            auto noise = [&](int i, int j) -> double {
-                if (F::KIND == 0 && has_acc) {
-                    /* shadowing local of PoseUKF.cpp:190-191: unrotated, unscaled Q, velocity block = 2 acc.cov */
-                    if (i >= 6 && i < 9 && j >= 6 && j < 9) return 2.0 * UKFB_LDG(acov + (i - 6) * 3 + (j - 6));
-                    return q_sym(Qp, i, j);
-                }
-                if (i >= F::QB0 && i < F::QB0 + 3 && j >= F::QB0 && j < F::QB0 + 3)
-                    return scale * QR[(i - F::QB0) * 3 + (j - F::QB0)];
-                if (i >= F::QB1 && i < F::QB1 + 3 && j >= F::QB1 && j < F::QB1 + 3)
-                    return scale * QR[9 + (i - F::QB1) * 3 + (j - F::QB1)];
-                return scale * q_sym(Qp, i, j);
-            };
             UKFB_UNROLL
             for (int e = 0; e < 2; ++e) {
-                if (c + e <= r) nz00[e] = noise(r, c + e);
-                if (8 + r < F::N) nz10[e] = noise(8 + r, c + e);
-                if (8 + r < F::N && c + e <= r) nz11[e] = noise(8 + r, 8 + c + e);
+                if (c + e <= r) nz00[e] = w.NT[tri(r, c + e)];
+                if (8 + r < F::N) nz10[e] = w.NT[tri(8 + r, c + e)];
+                if (8 + r < F::N && c + e <= r) nz11[e] = w.NT[tri(8 + r, 8 + c + e)];
             }
         }
         double c00[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
@@ -789,7 +788,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
     w.SM = wsm + SM::OFF_SM;
     w.MD = wsm + SM::OFF_MD;
     w.BC = wsm + SM::OFF_BC;
-    w.QR = wsm + SM::OFF_QR;
+    w.NT = wsm + SM::OFF_NT;
     w.lane = lane;
     int* cflag = reinterpret_cast<int*>(wsm + SM::OFF_CTL);
     int* ckind = cflag + G;

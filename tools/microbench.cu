@@ -47,6 +47,38 @@ __global__ void k_dmma16816(double* out, double a, double b)
     if (s == 1.2345) out[0] = s;
 }
 
+template <int NCH>
+__global__ void k_dfma_chains(double* out, double a, double b)
+{
+    double x[NCH];
+    for (int i = 0; i < NCH; ++i) x[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) x[i] = fma(x[i], a, b);
+    double s = 0;
+    for (int i = 0; i < NCH; ++i) s += x[i];
+    if (s == 1.2345) out[0] = s;
+}
+
+/* 4 DFMA chains interleaved with 1 DMMA chain per iteration: do the two share one pipe? */
+__global__ void k_mix(double* out, double a, double b)
+{
+    double x[8];
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
+    double c[2][2] = {{1, 2}, {3, 4}};
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = c[0][0] + c[0][1] + c[1][0] + c[1][1];
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 1.2345) out[0] = s;
+}
+
 __global__ void k_rcp(double* out, double a)
 {
     double x[8];
@@ -139,6 +171,28 @@ int main()
         printf("dmma m8n8k4 dependent-chain latency: %.1f cycles\n", ms * 1e-3 * clk_khz * 1e3 / ITERS);
         ms = timeit([&] { k_dfma<<<sms, 32>>>(out, 0.999, 1e-9); });
         printf("dfma 8-chain per-iteration: %.1f cycles (8 independent)\n", ms * 1e-3 * clk_khz * 1e3 / ITERS);
+    }
+    {
+        float ms;
+        ms = timeit([&] { k_dfma_chains<1><<<sms, 32>>>(out, 0.999, 1e-9); });
+        printf("single warp, 1 dfma chain : %.2f cycles per dfma (latency)\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 1);
+        ms = timeit([&] { k_dfma_chains<2><<<sms, 32>>>(out, 0.999, 1e-9); });
+        printf("single warp, 2 dfma chains: %.2f cycles per dfma\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 2);
+        ms = timeit([&] { k_dfma_chains<4><<<sms, 32>>>(out, 0.999, 1e-9); });
+        printf("single warp, 4 dfma chains: %.2f cycles per dfma\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 4);
+        ms = timeit([&] { k_dfma_chains<16><<<sms, 32>>>(out, 0.999, 1e-9); });
+        printf("single warp, 16 dfma chains: %.2f cycles per dfma\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 16);
+        ms = timeit([&] { k_dfma_chains<4><<<sms, 128>>>(out, 0.999, 1e-9); });
+        printf("4 warps (1/SMSP), 4 chains: %.2f cycles per dfma per warp\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 4);
+        ms = timeit([&] { k_dfma_chains<2><<<sms, 512>>>(out, 0.999, 1e-9); });
+        printf("16 warps (4/SMSP), 2 chains: %.2f SM-cycles per warp-dfma\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 2 / 16);
+        ms = timeit([&] { k_dfma_chains<1><<<sms, 512>>>(out, 0.999, 1e-9); });
+        printf("16 warps (4/SMSP), 1 chain : %.2f SM-cycles per warp-dfma\n", ms * 1e-3 * clk_khz * 1e3 / ITERS / 1 / 16);
+    }
+    {
+        float ms = timeit([&] { k_mix<<<blocks, threads>>>(out, 0.999, 1e-9); });
+        double cyc = ms * 1e-3 * clk_khz * 1e3 * sms / (warps * ITERS);
+        printf("mix 8 dfma + 2 dmma per iteration: %.2f SM-cycles per iteration (separate pipes: ~8.6; shared: ~12.7)\n", cyc);
     }
     rep("dmma m16n8k16 x2", timeit([&] { k_dmma16816<2><<<blocks, threads>>>(out, 0.999, 1e-9); }), ITERS * 2.0, 4096);
     rep("dmma m16n8k16 x4", timeit([&] { k_dmma16816<4><<<blocks, threads>>>(out, 0.999, 1e-9); }), ITERS * 4.0, 4096);
