@@ -1,0 +1,138 @@
+// shim_demo.cpp -- drives the C++ host shim (include/pose_estimation_b200) the way a caller of the reference
+// classes would, and prints the resulting states for tests/test_cpp_shim.py to compare with the oracle.
+// Build: g++ -std=c++17 -I include tests/cpp/shim_demo.cpp -L slam_pose_estimation_b200/lib -lukfb -Wl,-rpath,...
+#include <cmath>
+#include <cstdio>
+#include <limits>
+
+#include <pose_estimation_b200/OrientationUKF.hpp>
+#include <pose_estimation_b200/PoseUKF.hpp>
+
+using namespace pose_estimation_b200;
+
+template <class S>
+static void print_state(const char* tag, const S& s, int n)
+{
+    printf("%s", tag);
+    for (int i = 0; i < n; ++i) printf(" %.17g", s.v[i]);
+    printf("\n");
+}
+
+int main()
+{
+    // ---- PoseUKF: predict from sample times, then one update of each kind ------------------------------
+    PoseUKF::State x0 = {};
+    x0.v[6] = 1.0;  // identity orientation
+    x0.v[7] = 1.0;  // body velocity x
+    x0.v[12] = 0.05;
+    PoseUKF::Covariance p0 = {};
+    const double d0[12] = {1, 1, 1, 0.01, 0.01, 0.01, 0.1, 0.1, 0.1, 0.01, 0.01, 0.01};
+    for (int i = 0; i < 12; ++i) p0.v[i * 12 + i] = d0[i];
+    PoseUKF pose(x0, p0);
+    printf("pose_state_size %u initialized %d\n", pose.getStateSize(), int(pose.isInitialized()));
+    pose.predictionStepFromSampleTime(int64_t(1000000));  // first call only latches
+    pose.predictionStepFromSampleTime(int64_t(1010000));
+    PoseUKF::PositionMeasurement pm;
+    pm.mu[0] = 0.02, pm.mu[1] = -0.01, pm.mu[2] = 0.005;
+    for (int i = 0; i < 3; ++i) pm.cov[i * 3 + i] = 0.25;
+    pose.integrateMeasurement(pm);
+    PoseUKF::XYMeasurement xy;
+    xy.mu[0] = 0.01, xy.mu[1] = 0.0;
+    pose.integrateMeasurement(xy);
+    PoseUKF::ZMeasurement zm;
+    zm.mu[0] = -0.02;
+    pose.integrateMeasurement(zm);
+    PoseUKF::OrientationMeasurement om;
+    om.mu[2] = 0.001;
+    for (int i = 0; i < 3; ++i) om.cov[i * 3 + i] = 1e-4;
+    pose.integrateMeasurement(om);
+    PoseUKF::VelocityMeasurement vm;
+    vm.mu[0] = 1.01;
+    for (int i = 0; i < 3; ++i) vm.cov[i * 3 + i] = 1e-4;
+    pose.integrateMeasurement(vm);
+    PoseUKF::XYVelocityMeasurement xyv;
+    xyv.mu[0] = 0.99;
+    pose.integrateMeasurement(xyv);
+    PoseUKF::ZVelocityMeasurement zv;
+    pose.integrateMeasurement(zv);
+    PoseUKF::XVelYawVelMeasurement xw;
+    xw.mu[0] = 1.0, xw.mu[1] = 0.05;
+    pose.integrateMeasurement(xw);
+    PoseUKF::AngularVelocityMeasurement wm;
+    wm.mu[2] = 0.049;
+    for (int i = 0; i < 3; ++i) wm.cov[i * 3 + i] = 1e-6;
+    pose.integrateMeasurement(wm);
+    PoseUKF::AccelerationMeasurement am;
+    am.mu[0] = 0.1;
+    for (int i = 0; i < 3; ++i) am.cov[i * 3 + i] = 1e-4;
+    pose.integrateMeasurement(am);
+    pose.predictionStep(0.01);
+    PoseUKF::State xs;
+    PoseUKF::Covariance ps;
+    if (!pose.getCurrentState(xs, ps)) return 2;
+    print_state("pose_mu", xs, 13);
+    print_state("pose_sigma", ps, 144);
+    printf("pose_last_time %lld\n", (long long)pose.getLastMeasurementTime());
+
+    // ---- the reference's exceptions ----------------------------------------------------------------------
+    int caught = 0;
+    try {
+        pose.predictionStep(-0.5);
+    } catch (const std::runtime_error& e) {
+        printf("caught: %s\n", e.what());
+        ++caught;
+    }
+    pose.setMaxTimeDelta(1.0);
+    try {
+        pose.predictionStep(2.0);
+    } catch (const std::runtime_error& e) {
+        printf("caught: %s\n", e.what());
+        ++caught;
+    }
+    pose.predictionStep(0.0);  // silently ignored (:114-118)
+
+    // ---- OrientationUKF ------------------------------------------------------------------------------------
+    OrientationUKF::State o0 = {};
+    o0.v[3] = 1.0;
+    o0.v[13] = 9.81;
+    OrientationUKF::Covariance op = {};
+    const double od[13] = {0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 1e-6, 1e-6, 1e-6, 1e-4, 1e-4, 1e-4, 1e-4};
+    for (int i = 0; i < 13; ++i) op.v[i * 13 + i] = od[i];
+    LocationConfiguration loc = {0.92698121, 0.154595663, 0.0};
+    OrientationUKF ori(o0, op, 3600.0, 3600.0, loc);
+    OrientationUKF::Covariance oq = {};
+    const double qd[13] = {1e-6, 1e-6, 1e-6, 1e-4, 1e-4, 1e-4, 1e-10, 1e-10, 1e-10, 1e-8, 1e-8, 1e-8, 1e-12};
+    for (int i = 0; i < 13; ++i) oq.v[i * 13 + i] = qd[i];
+    ori.setProcessNoiseCovariance(oq);
+    OrientationUKF::RotationRate rr;
+    rr.mu[2] = 0.05;
+    OrientationUKF::Acceleration ac;
+    ac.mu[2] = 9.81;
+    for (int k = 0; k < 5; ++k) {
+        ori.integrateMeasurement(rr);
+        ori.integrateMeasurement(ac);
+        ori.predictionStepFromSampleTime(int64_t(1000000 + 1000 * k));
+    }
+    OrientationUKF::VelocityMeasurement ov;
+    ov.mu[0] = 0.01;
+    for (int i = 0; i < 3; ++i) ov.cov[i * 3 + i] = 1e-4;
+    ori.integrateMeasurement(ov);
+    try {
+        OrientationUKF::VelocityMeasurement bad;
+        bad.mu[1] = std::numeric_limits<double>::quiet_NaN();
+        ori.integrateMeasurement(bad);
+    } catch (const std::runtime_error& e) {
+        printf("caught: %s\n", e.what());
+        ++caught;
+    }
+    OrientationUKF::State os;
+    OrientationUKF::Covariance oss;
+    if (!ori.getCurrentState(os, oss)) return 3;
+    print_state("ori_mu", os, 14);
+    print_state("ori_sigma", oss, 169);
+    double rate[3];
+    ori.getRotationRate(rate);
+    printf("ori_rate %.17g %.17g %.17g\n", rate[0], rate[1], rate[2]);
+    printf("caught_total %d\n", caught);
+    return caught == 3 ? 0 : 1;
+}
