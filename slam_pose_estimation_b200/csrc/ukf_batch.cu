@@ -18,6 +18,7 @@
 #include <new>
 
 #include "ukf_device.cuh"
+#include "ukf_thread.cuh"
 
 using namespace ukfb;
 
@@ -46,7 +47,8 @@ struct ukfb_handle {
     int kind = 0, device = 0;
     long long B = 0;
     int n = 0, MU = 0, LP = 0, REC = 0;
-    int G = 8, WPB = 4, MINB = 3; /* launch shape: filters per warp, warps per block, resident blocks per SM */
+    int G = 8, WPB = 4, MINB = 3; /* warp kernel launch shape: filters per warp, warps per block, resident blocks per SM */
+    int tiled = 1;                /* 1: lane-per-filter kernel, tile-interleaved records; 0: warp-per-group kernel, AoS records */
     cudaStream_t stream = nullptr;
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
@@ -106,9 +108,16 @@ struct Bind { /* sets the device for the duration of a call */
 
 /* ---- small kernels ------------------------------------------------------------------------- */
 
+/* element index of record entry e of filter b: AoS records (warp kernel) or 32-filter entry-major tiles (thread kernel) */
+__device__ __forceinline__ long long rec_index(int tiled, long long b, int e, int REC)
+{
+    return tiled ? tile_index(b, e, REC) : b * REC + e;
+}
+
+
 /* host layout (mu B x MU, sigma B x n x n) -> records */
 __global__ void pack_kernel(double* __restrict__ state, const double* __restrict__ mu, const double* __restrict__ sigma,
-                            long long B, int n, int MU, int LP, int REC)
+                            long long B, int n, int MU, int LP, int REC, int tiled)
 {
     const long long total = B * REC;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -124,21 +133,21 @@ __global__ void pack_kernel(double* __restrict__ state, const double* __restrict
             const int c = e - r * (r + 1) / 2;
             v = sigma[(b * n + r) * n + c];
         }
-        state[i] = v;
+        state[rec_index(tiled, b, k, REC)] = v;
     }
 }
 
-__global__ void unpack_mu_kernel(const double* __restrict__ state, double* __restrict__ mu, long long B, int MU, int REC)
+__global__ void unpack_mu_kernel(const double* __restrict__ state, double* __restrict__ mu, long long B, int MU, int REC, int tiled)
 {
     const long long total = B * MU;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / MU;
         const int k = int(i - b * MU);
-        mu[i] = state[b * REC + k];
+        mu[i] = state[rec_index(tiled, b, k, REC)];
     }
 }
 
-__global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __restrict__ sigma, long long B, int n, int MU, int REC)
+__global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __restrict__ sigma, long long B, int n, int MU, int REC, int tiled)
 {
     const long long total = B * n * n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -150,7 +159,7 @@ __global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __
             r = c;
             c = t;
         }
-        sigma[i] = state[b * REC + MU + tri(r, c)];
+        sigma[i] = state[rec_index(tiled, b, MU + tri(r, c), REC)];
     }
 }
 
@@ -225,24 +234,24 @@ __global__ void store_vec3_kernel(double* __restrict__ dst_mu, double* __restric
 
 /* OrientationUKF::getRotationRate (OrientationUKF.cpp:74-77) */
 __global__ void rotation_rate_kernel(const double* __restrict__ state, const double* __restrict__ gyro, double e0, double e1,
-                                     double e2, double* __restrict__ out, long long B)
+                                     double e2, double* __restrict__ out, long long B, int tiled)
 {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        const double* x = state + b * OriF::REC;
-        const double q[4] = {x[0], x[1], x[2], x[3]};
+        double q[4];
+        for (int i = 0; i < 4; ++i) q[i] = state[rec_index(tiled, b, i, OriF::REC)];
         const double e[3] = {e0, e1, e2};
         double r[3];
         quat_inv_rotate(q, e, r);
-        for (int i = 0; i < 3; ++i) out[b * 3 + i] = gyro[b * 3 + i] - x[7 + i] - r[i];
+        for (int i = 0; i < 3; ++i) out[b * 3 + i] = gyro[b * 3 + i] - state[rec_index(tiled, b, 7 + i, OriF::REC)] - r[i];
     }
 }
 
 /* initial stored acceleration of OrientationUKF: (0, 0, gravity) (OrientationUKF.cpp:50) */
 __global__ void ori_default_imu_kernel(const double* __restrict__ state, double* __restrict__ acc, double* __restrict__ gyro,
-                                       long long B)
+                                       long long B, int tiled)
 {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        acc[b * 3] = 0.0, acc[b * 3 + 1] = 0.0, acc[b * 3 + 2] = state[b * OriF::REC + 13];
+        acc[b * 3] = 0.0, acc[b * 3 + 1] = 0.0, acc[b * 3 + 2] = state[rec_index(tiled, b, 13, OriF::REC)];
         gyro[b * 3] = gyro[b * 3 + 1] = gyro[b * 3 + 2] = 0.0;
     }
 }
@@ -321,9 +330,28 @@ static cudaError_t launch_step_f(const ukfb_handle* h, const StepParams& p)
     }
 }
 
+template <class F>
+static cudaError_t launch_thread_f(const ukfb_handle* h, const StepParams& p)
+{
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(double) * TSmem<F>::TOTAL;
+    if (!attr_set[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(ukf_thread_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_set[h->device & 63] = true;
+    }
+    const long long grid = (p.B + TILE - 1) / TILE;
+    ukf_thread_kernel<F><<<unsigned(grid), TILE, smem, h->stream>>>(p);
+    return cudaGetLastError();
+}
+
 static int launch_step(ukfb_handle* h, const StepParams& p)
 {
-    const cudaError_t e = h->kind == UKFB_POSE ? launch_step_f<PoseF>(h, p) : launch_step_f<OriF>(h, p);
+    cudaError_t e;
+    if (h->tiled)
+        e = h->kind == UKFB_POSE ? launch_thread_f<PoseF>(h, p) : launch_thread_f<OriF>(h, p);
+    else
+        e = h->kind == UKFB_POSE ? launch_step_f<PoseF>(h, p) : launch_step_f<OriF>(h, p);
     if (e != cudaSuccess) return fail(UKFB_ERR_CUDA, "ukf_step_kernel launch: %s", cudaGetErrorString(e));
     h->launches++;
     return UKFB_OK;
@@ -391,6 +419,7 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         const int G = atoi(g);
         if (G == 4 || G == 8 || G == 16) h->G = G;
     }
+    if (const char* g = getenv("UKFB_KERNEL")) h->tiled = strcmp(g, "warp") != 0;
     if (const char* g = getenv("UKFB_WPB")) h->WPB = atoi(g);
     if (const char* g = getenv("UKFB_MINB")) h->MINB = atoi(g);
     Bind bind_(h);
@@ -409,7 +438,8 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
     } while (0)
     const long long B = batch;
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUH(cudaMalloc(&h->state, sizeof(double) * B * h->REC));
+    const long long Bpad = (B + TILE - 1) / TILE * TILE; /* whole tiles: lanes past the end address valid memory */
+    CUH(cudaMalloc(&h->state, sizeof(double) * Bpad * h->REC));
     CUH(cudaMalloc(&h->Q, sizeof(double) * h->LP));
     CUH(cudaMalloc(&h->status, sizeof(uint32_t) * B));
     CUH(cudaMalloc(&h->t_last, sizeof(long long) * B));
@@ -418,7 +448,7 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
     CUH(cudaMalloc(&h->acc_cov, sizeof(double) * B * 9));
     CUH(cudaMalloc(&h->gyro_mu, sizeof(double) * B * 3));
     CUH(cudaMalloc(&h->summary, sizeof(long long) * 2));
-    CUH(cudaMemsetAsync(h->state, 0, sizeof(double) * B * h->REC, h->stream));
+    CUH(cudaMemsetAsync(h->state, 0, sizeof(double) * Bpad * h->REC, h->stream));
     CUH(cudaMemsetAsync(h->status, 0, sizeof(uint32_t) * B, h->stream));
     CUH(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * B, h->stream));
     CUH(cudaMemsetAsync(h->hist, 0, sizeof(unsigned long long) * HIST_SLOTS * 8, h->stream));
@@ -467,11 +497,11 @@ extern "C" int ukfb_is_initialized(const ukfb_handle* h) { return h && h->initia
 
 static int initialize_dev(ukfb_handle* h, const double* d_mu, const double* d_sigma)
 {
-    pack_kernel<<<grid_for(h->B * h->REC), 256, 0, h->stream>>>(h->state, d_mu, d_sigma, h->B, h->n, h->MU, h->LP, h->REC);
+    pack_kernel<<<grid_for(h->B * h->REC), 256, 0, h->stream>>>(h->state, d_mu, d_sigma, h->B, h->n, h->MU, h->LP, h->REC, h->tiled);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * h->B, h->stream)); /* :43 */
     if (h->kind == UKFB_ORIENTATION && h->first_init) {
-        ori_default_imu_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->acc_mu, h->gyro_mu, h->B);
+        ori_default_imu_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->acc_mu, h->gyro_mu, h->B, h->tiled);
         CU(cudaGetLastError());
     }
     h->first_init = false;
@@ -500,8 +530,8 @@ extern "C" int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma)
 {
     CHECK_H(h);
     NEED_INIT(h);
-    if (d_mu) unpack_mu_kernel<<<grid_for(h->B * h->MU), 256, 0, h->stream>>>(h->state, d_mu, h->B, h->MU, h->REC);
-    if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->MU, h->REC);
+    if (d_mu) unpack_mu_kernel<<<grid_for(h->B * h->MU), 256, 0, h->stream>>>(h->state, d_mu, h->B, h->MU, h->REC, h->tiled);
+    if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->MU, h->REC, h->tiled);
     CU(cudaGetLastError());
     return UKFB_OK;
 }
@@ -857,7 +887,7 @@ extern "C" int ukfb_get_rotation_rate(ukfb_handle* h, double* out)
     int rc = stage_reserve(h, sizeof(double) * h->B * 3);
     if (rc) return rc;
     rotation_rate_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->gyro_mu, h->earth[0], h->earth[1], h->earth[2],
-                                                               reinterpret_cast<double*>(h->stage), h->B);
+                                                               reinterpret_cast<double*>(h->stage), h->B, h->tiled);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, h->stage, sizeof(double) * h->B * 3, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

@@ -41,7 +41,8 @@ def load(sanitize: bool = False):
     srcs = [os.path.join(_DIR, "emu_harness.cpp"), os.path.join(_DIR, "simt_emu_rt.hpp"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh"),
-            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/simt.cuh")]
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/simt.cuh"),
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", _DIR,
                "-o", out, srcs[0]]
@@ -58,13 +59,15 @@ def _ptr(a):
 class EmuBatch:
     """Host-side state + calls into the emulated kernel; mirrors OracleBatch method names."""
 
-    def __init__(self, kind: int, B: int, G: int = 4):
+    def __init__(self, kind: int, B: int, G: int = 4, kernel: str = "warp"):
+        """kernel: 'warp' (ukf_device.cuh, AoS records) or 'thread' (ukf_thread.cuh, 32-filter entry-major tiles)"""
         self.lib = load()
-        self.kind, self.B, self.G = kind, B, G
+        self.kind, self.B, self.G, self.tiled = kind, B, G, kernel == "thread"
         self.n, self.MU, self.REC = (12, 13, 91) if kind == 0 else (13, 14, 105)
         self.LP = self.n * (self.n + 1) // 2
         self.tril = np.tril_indices(self.n)
-        self.state = np.zeros((B, self.REC))
+        self.Bpad = (B + 31) // 32 * 32
+        self.state = np.zeros((self.Bpad, self.REC))  # logical [filter][entry] view; see _to_device / _from_device
         self.status = np.zeros(B, np.uint32)
         self.t_last = np.zeros(B, np.int64)
         self.hist = np.zeros(64 * 8, np.uint64)
@@ -85,8 +88,8 @@ class EmuBatch:
         mu = np.asarray(mu, float).reshape(self.B, self.MU)
         sigma = np.asarray(sigma, float).reshape(self.B, self.n, self.n)
         self.state[:] = 0
-        self.state[:, : self.MU] = mu
-        self.state[:, self.MU : self.MU + self.LP] = sigma[:, self.tril[0], self.tril[1]]
+        self.state[: self.B, : self.MU] = mu
+        self.state[: self.B, self.MU : self.MU + self.LP] = sigma[:, self.tril[0], self.tril[1]]
         self.t_last[:] = 0
         if self.kind == 1 and self._first_init:
             self.acc_mu[:] = 0
@@ -94,9 +97,9 @@ class EmuBatch:
         self._first_init = False
 
     def get_state(self):
-        mu = self.state[:, : self.MU].copy()
+        mu = self.state[: self.B, : self.MU].copy()
         sg = np.zeros((self.B, self.n, self.n))
-        sg[:, self.tril[0], self.tril[1]] = self.state[:, self.MU : self.MU + self.LP]
+        sg[:, self.tril[0], self.tril[1]] = self.state[: self.B, self.MU : self.MU + self.LP]
         sg = sg + np.transpose(np.tril(sg, -1), (0, 2, 1))
         return mu, sg
 
@@ -151,7 +154,13 @@ class EmuBatch:
                 setattr(p, k, _ptr(v))
             else:
                 setattr(p, k, v)
-        rc = self.lib.emu_step(C.c_int(self.kind), C.c_int(self.G), C.byref(p))
+        if self.tiled:  # [tile][entry][lane] in memory
+            dev = np.ascontiguousarray(self.state.reshape(-1, 32, self.REC).transpose(0, 2, 1))
+            p.state = _ptr(dev)
+            rc = self.lib.emu_thread_step(C.c_int(self.kind), C.byref(p))
+            self.state[:] = dev.transpose(0, 2, 1).reshape(self.Bpad, self.REC)
+        else:
+            rc = self.lib.emu_step(C.c_int(self.kind), C.c_int(self.G), C.byref(p))
         assert rc == 0
 
     def predict_dt(self, dt):

@@ -6,6 +6,7 @@
  */
 #define UKFB_SIMT_EMU 1
 #include "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"
+#include "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"
 
 using namespace ukfb;
 
@@ -35,6 +36,17 @@ extern "C" int emu_step(int filter_kind, int G, const StepParams* p)
         }
     }
     return -1;
+}
+
+/* the lane-per-filter kernel (ukf_thread.cuh): one 32-thread block per tile of 32 filters */
+extern "C" int emu_thread_step(int filter_kind, const StepParams* p)
+{
+    const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
+    if (filter_kind == 0)
+        simt_emu::launch(ukf_thread_kernel<PoseF>, grid, TILE, sizeof(double) * TSmem<PoseF>::TOTAL, *p);
+    else
+        simt_emu::launch(ukf_thread_kernel<OriF>, grid, TILE, sizeof(double) * TSmem<OriF>::TOTAL, *p);
+    return 0;
 }
 
 extern "C" int emu_sizeof_params(void) { return int(sizeof(StepParams)); }
