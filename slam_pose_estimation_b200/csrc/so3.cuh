@@ -201,6 +201,74 @@ UKFB_D void so3_log(const double* q, double* out)
     out[2] = s * q[2];
 }
 
+/* ---- optimistic variants for straight-line code -------------------------------------------------------
+ * FAST = true evaluates only the polynomial path, with no branch, and ORs `slow` when the argument was outside
+ * the polynomial's range (the result is then meaningless); the caller discards the whole pass and redoes it with
+ * FAST = false, which is the branching code above.  This keeps calls and branches out of the sigma-point loops,
+ * so the scheduler can overlap independent sigma points. */
+template <bool FAST>
+UKFB_D void so3_exp_t(const double* v, double scale, double* q, bool& slow)
+{
+    if (!FAST) {
+        so3_exp(v, scale, q);
+        return;
+    }
+    const double half = scale / 2.0;
+    const double norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double x2 = half * half * norm2;
+    slow = slow || !(x2 <= SO3_EXP_FAST_X2);
+    const double x4 = x2 * x2;
+    const double c = UKFB_POLY6(SO3_COS_C, x2, x4);
+    const double mult = UKFB_POLY6(SO3_SINC_C, x2, x4) * half;
+    q[0] = mult * v[0];
+    q[1] = mult * v[1];
+    q[2] = mult * v[2];
+    q[3] = c;
+}
+
+template <bool FAST>
+UKFB_D void so3_log_t(const double* q, double* out, bool& slow)
+{
+    if (!FAST) {
+        so3_log(q, out);
+        return;
+    }
+    const double nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const double w = q[3];
+    slow = slow || !(nv2 <= SO3_LOG_FAST_U * (w * w));
+    const double rw = fast_rcp(w);
+    const double t = nv2 * rw;
+    const double s = (2.0 * rw) * atan_over_t_poly(t * rw);
+    out[0] = s * q[0];
+    out[1] = s * q[1];
+    out[2] = s * q[2];
+}
+
+template <bool FAST>
+UKFB_D void so3_boxplus_t(double* q, const double* v, double scale, bool& slow)
+{
+    double e[4], r[4];
+    so3_exp_t<FAST>(v, scale, e, slow);
+#if UKFB_SO3_BOXPLUS_LEFT
+    quat_mul(e, q, r);
+#else
+    quat_mul(q, e, r);
+#endif
+    q[0] = r[0], q[1] = r[1], q[2] = r[2], q[3] = r[3];
+}
+
+template <bool FAST>
+UKFB_D void so3_boxminus_t(const double* q, const double* o, double* res, bool& slow)
+{
+    double r[4];
+#if UKFB_SO3_BOXPLUS_LEFT
+    quat_mul_conj(q, o, r);
+#else
+    quat_conj_mul(o, q, r);
+#endif
+    so3_log_t<FAST>(r, res, slow);
+}
+
 /* q <- q [+] v*scale */
 UKFB_D void so3_boxplus(double* q, const double* v, double scale)
 {

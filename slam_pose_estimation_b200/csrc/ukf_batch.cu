@@ -19,6 +19,7 @@
 
 #include "ukf_device.cuh"
 #include "ukf_thread.cuh"
+#include "ukf_pose_fast.cuh"
 
 using namespace ukfb;
 
@@ -49,6 +50,7 @@ struct ukfb_handle {
     int n = 0, MU = 0, LP = 0, REC = 0;
     int G = 8, WPB = 4, MINB = 3; /* warp kernel launch shape: filters per warp, warps per block, resident blocks per SM */
     int tiled = 1;                /* 1: lane-per-filter kernel, tile-interleaved records; 0: warp-per-group kernel, AoS records */
+    int fast = UKFB_SO3_BOXPLUS_LEFT; /* tiled PoseUKF: 1 = structure-exploiting kernel (ukf_pose_fast.cuh), 0 = literal kernel (ukf_thread.cuh) */
     cudaStream_t stream = nullptr;
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
@@ -345,10 +347,26 @@ static cudaError_t launch_thread_f(const ukfb_handle* h, const StepParams& p)
     return cudaGetLastError();
 }
 
+static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p)
+{
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(double) * PF_PER_LANE * TILE;
+    if (!attr_set[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(ukf_pose_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_set[h->device & 63] = true;
+    }
+    const long long grid = (p.B + TILE - 1) / TILE;
+    ukf_pose_fast_kernel<<<unsigned(grid), TILE, smem, h->stream>>>(p);
+    return cudaGetLastError();
+}
+
 static int launch_step(ukfb_handle* h, const StepParams& p)
 {
     cudaError_t e;
-    if (h->tiled)
+    if (h->tiled && h->fast && h->kind == UKFB_POSE)
+        e = launch_pose_fast(h, p);
+    else if (h->tiled)
         e = h->kind == UKFB_POSE ? launch_thread_f<PoseF>(h, p) : launch_thread_f<OriF>(h, p);
     else
         e = h->kind == UKFB_POSE ? launch_step_f<PoseF>(h, p) : launch_step_f<OriF>(h, p);
@@ -419,7 +437,10 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         const int G = atoi(g);
         if (G == 4 || G == 8 || G == 16) h->G = G;
     }
-    if (const char* g = getenv("UKFB_KERNEL")) h->tiled = strcmp(g, "warp") != 0;
+    if (const char* g = getenv("UKFB_KERNEL")) { /* fast (default) | thread (literal lane-per-filter) | warp (literal warp-per-group) */
+        h->tiled = strcmp(g, "warp") != 0;
+        if (strcmp(g, "thread") == 0) h->fast = 0;
+    }
     if (const char* g = getenv("UKFB_WPB")) h->WPB = atoi(g);
     if (const char* g = getenv("UKFB_MINB")) h->MINB = atoi(g);
     Bind bind_(h);

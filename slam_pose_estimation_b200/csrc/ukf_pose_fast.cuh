@@ -1,0 +1,916 @@
+/*
+ * ukf_pose_fast.cuh -- the structure-exploiting lane-per-filter step kernel for PoseUKF (sm_100a).
+ *
+ * Same StepParams, same HBM tile layout and same results (to rounding) as ukf_thread.cuh, which stays the general
+ * ("literal") kernel: every lane owns one filter.  This kernel evaluates the SAME estimator -- ukfom predict /
+ * update / apply_delta over the 2n+1 sigma points mu [+] +-L[:,j] with the PoseUKF models
+ * (PoseUKF.cpp:7-97,180-196) -- but uses what is known at compile time about those models, so that sums the
+ * reference evaluates term by term are taken in closed form wherever they are EXACT identities:
+ *
+ *   predict (PoseUKF.cpp:75-97): velocity and angular velocity pass through the process model unchanged, hence
+ *     their deviations from the mean are exactly +-L[6:12,j]:
+ *       - the velocity/angular-velocity block of the new covariance is  Sigma[6:12,6:12] + Q[6:12,6:12];
+ *       - its cross block with position/orientation is  1/2 sum_j L[6:12,j] (d+_j - d-_j)^T;
+ *       - only the 21 position/orientation entries are accumulated point by point.
+ *     L is lower triangular, so columns j >= 6 perturb neither position nor orientation: those 12 sigma points
+ *     share the rotation of the prior orientation (one 3x3 matrix) and need no sigma-point boxplus.
+ *     The +/- points of a column share exp(L_ori), conj for the minus point.
+ *   update with a component-selector measurement (all PoseUKF models but the orientation one, PoseUKF.cpp:7-69):
+ *     Z_p = mu[sel] +- L[sel,j], so zbar = mu[sel], S = Sigma[sel,sel] + R and Sigma_xz = Sigma[:,sel] exactly
+ *     (valid while every |L_ori[:,j]| < pi, guaranteed by trace(Sigma_ori) < pi^2, else the literal path runs);
+ *     gain, Sigma - K S K^T and delta = K innov follow the reference's expression order.
+ *   apply_delta: the Euclidean components of mu [+] (delta +- L[:,j]) have mean mu + delta and deviations +-L, so
+ *     the Euclidean block of the new covariance is that of Sigma - K S K^T; only the orientation rows/columns are
+ *     recomputed, from the 12 points of columns 0..5 (the others carry the orientation of X_0), and only the first
+ *     six columns of the second Cholesky factor are needed.
+ *
+ * All SO(3) exp/log calls here are the branch-free polynomial kernels of so3.cuh; a lane whose argument leaves the
+ * polynomial range, an orientation measurement (kind 3) or a failed guard falls back to the literal code of
+ * ukf_thread.cuh (out of line, cold), which is also what UKFB_KERNEL=thread runs for every filter.
+ * Covariance accumulators (57 / 33 doubles) and the state stay in registers, both Cholesky factorisations run in
+ * registers on statically indexed arrays; shared memory ([entry][lane], conflict free) only holds the factor
+ * columns, which the sigma-point loops index dynamically.
+ */
+#ifndef UKFB_POSE_FAST_CUH
+#define UKFB_POSE_FAST_CUH
+
+#include "ukf_thread.cuh"
+
+namespace ukfb {
+
+#define UKFB_PS(e) sm[(e) * TILE + lane]
+
+/* shared-memory slots (doubles per lane).  The factor is stored as two square blocks with explicit zeros above the
+ * diagonal so that the column loops need no triangular index tests:
+ *   LA(j, i) = j * 12 + i        columns 0..5,  rows 0..11
+ *   LB(j, i) = 72 + (j-6)*6 + (i-6)   columns 6..11, rows 6..11
+ * Between predict and update the first 78 slots hold the predicted covariance, packed lower (dynamic selector
+ * indexing).  The literal fallback uses the TSmem<PoseF> layout in the same buffer. */
+constexpr int PF_LA = 0;
+constexpr int PF_LB = 72;
+constexpr int PF_PER_LANE = TSmem<PoseF>::PER_LANE;
+constexpr double PF_PI2_GUARD = 9.0; /* trace(Sigma_ori) below this (< pi^2) makes (mu [+] L_j) [-] mu = L_j exact */
+
+/* ---- branch-free SO(3) kernels: polynomial path only, `slow` collects range violations ------------------------ */
+UKFB_D void pf_exp(const double* v, double scale, double* q, bool& slow)
+{
+    const double half = scale * 0.5;
+    const double norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double x2 = half * half * norm2;
+    slow = slow || !(x2 <= SO3_EXP_FAST_X2);
+    const double x4 = x2 * x2;
+    const double c = UKFB_POLY6(SO3_COS_C, x2, x4);
+    const double mult = UKFB_POLY6(SO3_SINC_C, x2, x4) * half;
+    q[0] = mult * v[0];
+    q[1] = mult * v[1];
+    q[2] = mult * v[2];
+    q[3] = c;
+}
+
+UKFB_D void pf_log(const double* q, double* out, bool& slow)
+{
+    const double nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const double w = q[3];
+    slow = slow || !(nv2 <= SO3_LOG_FAST_U * (w * w)) || !(w > 0.0);
+    const double rw = fast_rcp(w);
+    const double t = nv2 * rw;
+    const double s = (2.0 * rw) * atan_over_t_poly(t * rw);
+    out[0] = s * q[0];
+    out[1] = s * q[1];
+    out[2] = s * q[2];
+}
+
+UKFB_D void pf_matvec(const double* Rm, const double* v, double* out)
+{
+    out[0] = Rm[0] * v[0] + Rm[1] * v[1] + Rm[2] * v[2];
+    out[1] = Rm[3] * v[0] + Rm[4] * v[1] + Rm[5] * v[2];
+    out[2] = Rm[6] * v[0] + Rm[7] * v[1] + Rm[8] * v[2];
+}
+
+/* ---- Cholesky of a packed lower 12x12 in registers, first NCOL columns (LAPACK dpotf2('L') order) ------------- */
+template <int NCOL>
+UKFB_D bool pf_cholesky(double* a)
+{
+    bool ok = true;
+    UKFB_UNROLL
+    for (int j = 0; j < NCOL; ++j) {
+        double ajj = a[tri(j, j)];
+        UKFB_UNROLL
+        for (int k = 0; k < j; ++k) ajj -= a[tri(j, k)] * a[tri(j, k)];
+        if (!(ajj > 0.0) || !(ajj < 1.0e300)) {
+            ok = false;
+            ajj = 1.0;
+        }
+        double d, rinv;
+        fast_sqrt_rsqrt(ajj, d, rinv);
+        a[tri(j, j)] = d;
+        UKFB_UNROLL
+        for (int i = j + 1; i < 12; ++i) {
+            double s = a[tri(i, j)];
+            UKFB_UNROLL
+            for (int k = 0; k < j; ++k) s -= a[tri(i, k)] * a[tri(j, k)];
+            a[tri(i, j)] = s * rinv;
+        }
+    }
+    return ok;
+}
+
+struct PoseMu {
+    double p[3], q[4], v[3], w[3];
+};
+
+/* one propagated sigma point: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
+UKFB_D void pf_point(const double* qs, const double* ps, const double* vs, const double* ws, double dt, const double* ref_p,
+                     const double* ref_q, double* d, bool& slow)
+{
+    double rv[3], rw[3], e[4], qn[4], r[4];
+    quat_rotate(qs, vs, rv);
+    quat_rotate(qs, ws, rw);
+    pf_exp(rw, dt, e, slow);
+    quat_mul(e, qs, qn);
+    d[0] = fma(dt, rv[0], ps[0]) - ref_p[0];
+    d[1] = fma(dt, rv[1], ps[1]) - ref_p[1];
+    d[2] = fma(dt, rv[2], ps[2]) - ref_p[2];
+    quat_mul_conj(qn, ref_q, r);
+    pf_log(r, d + 3, slow);
+}
+
+/* the +/- sigma points of a column j < 6 through the process model; L receives the column (12 entries) */
+UKFB_D void pf_pair_a(const double* sm, int lane, int j, const PoseMu& m, const double* vm, double dt, const double* ref_p,
+                      const double* ref_q, double* L, double* dpl, double* dmi, bool& slow)
+{
+    UKFB_UNROLL
+    for (int i = 0; i < 12; ++i) L[i] = UKFB_PS(PF_LA + j * 12 + i);
+    double e[4];
+    pf_exp(L + 3, 1.0, e, slow);
+    /* exp(+-Lo) * q = e.w q +- t,  t = (e.vec, 0) * q */
+    const double* q = m.q;
+    const double t0 = e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
+    const double t1 = e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
+    const double t2 = e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
+    const double t3 = -(e[0] * q[0] + e[1] * q[1] + e[2] * q[2]);
+    {
+        const double qs[4] = {fma(e[3], q[0], t0), fma(e[3], q[1], t1), fma(e[3], q[2], t2), fma(e[3], q[3], t3)};
+        const double ps[3] = {m.p[0] + L[0], m.p[1] + L[1], m.p[2] + L[2]};
+        const double vs[3] = {vm[0] + L[6], vm[1] + L[7], vm[2] + L[8]};
+        const double ws[3] = {m.w[0] + L[9], m.w[1] + L[10], m.w[2] + L[11]};
+        pf_point(qs, ps, vs, ws, dt, ref_p, ref_q, dpl, slow);
+    }
+    {
+        const double qs[4] = {fma(e[3], q[0], -t0), fma(e[3], q[1], -t1), fma(e[3], q[2], -t2), fma(e[3], q[3], -t3)};
+        const double ps[3] = {m.p[0] - L[0], m.p[1] - L[1], m.p[2] - L[2]};
+        const double vs[3] = {vm[0] - L[6], vm[1] - L[7], vm[2] - L[8]};
+        const double ws[3] = {m.w[0] - L[9], m.w[1] - L[10], m.w[2] - L[11]};
+        pf_point(qs, ps, vs, ws, dt, ref_p, ref_q, dmi, slow);
+    }
+}
+
+/* the +/- sigma points of a column j >= 6: position and orientation unperturbed.
+ * rw0 = R w, c = q * conj(ref_q).  Outputs the orientation deviations and wv = (R Lv) dt, the +- offset of the
+ * propagated position; L receives rows 6..11 of the column. */
+UKFB_D void pf_pair_b(const double* sm, int lane, int j, const double* Rm, const double* rw0, const double* c, double dt,
+                      double* L, double* dopl, double* domi, double* wv, bool& slow)
+{
+    UKFB_UNROLL
+    for (int i = 0; i < 6; ++i) L[i] = UKFB_PS(PF_LB + (j - 6) * 6 + i);
+    double u[3], rv[3];
+    pf_matvec(Rm, L + 3, u);
+    pf_matvec(Rm, L, rv);
+    wv[0] = dt * rv[0], wv[1] = dt * rv[1], wv[2] = dt * rv[2];
+    {
+        const double rw[3] = {rw0[0] + u[0], rw0[1] + u[1], rw0[2] + u[2]};
+        double e[4], r[4];
+        pf_exp(rw, dt, e, slow);
+        quat_mul(e, c, r);
+        pf_log(r, dopl, slow);
+    }
+    {
+        const double rw[3] = {rw0[0] - u[0], rw0[1] - u[1], rw0[2] - u[2]};
+        double e[4], r[4];
+        pf_exp(rw, dt, e, slow);
+        quat_mul(e, c, r);
+        pf_log(r, domi, slow);
+    }
+}
+
+/* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
+#ifdef UKFB_SIMT_EMU
+/* host emulation only: how often each fallback ran (predict, update, apply), so the tests can tell that they did */
+inline unsigned long long pf_fallbacks[3] = {0, 0, 0};
+#define UKFB_PF_COUNT(i) __atomic_fetch_add(&pf_fallbacks[i], 1ull, __ATOMIC_RELAXED)
+#else
+#define UKFB_PF_COUNT(i)
+#endif
+UKFB_DNI uint32_t pf_literal_predict(double* sm, int lane, double* sig, const double* Qp, const double* acov, ModelArgs ma, int* passes)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_PF_COUNT(0);
+    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
+    store_noise<PoseF>(sm, lane, sig, Qp, acov, ma);
+    const uint32_t st = mean_and_cov<PoseF, true>(sm, lane, sig, ma, passes);
+    UKFB_UNROLL
+    for (int i = 0; i < PoseF::MU; ++i) UKFB_PS(TS::OFF_MU + i) = UKFB_PS(TS::OFF_REF + i);
+    return st;
+}
+
+/* apply_delta from the record's covariance and the TS delta / mu slots; mu slots receive the new mean */
+UKFB_DNI uint32_t pf_literal_apply(double* sm, int lane, double* sig, ModelArgs ma, int* passes)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_PF_COUNT(2);
+    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
+    const uint32_t st = mean_and_cov<PoseF, false>(sm, lane, sig, ma, passes);
+    UKFB_UNROLL
+    for (int i = 0; i < PoseF::MU; ++i) UKFB_PS(TS::OFF_MU + i) = UKFB_PS(TS::OFF_REF + i);
+    return st;
+}
+
+UKFB_DNI uint32_t pf_literal_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld,
+                                    ModelArgs ma, int* passes)
+{
+    UKFB_PF_COUNT(1);
+    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
+    uint32_t st = update_first_half<PoseF>(sm, lane, sig, kind, zm, Rm, r_ld);
+    st |= pf_literal_apply(sm, lane, sig, ma, passes);
+    return st;
+}
+
+UKFB_D void pf_mu_to_smem(double* sm, int lane, const PoseMu& m)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        UKFB_PS(TS::OFF_MU + i) = m.p[i];
+        UKFB_PS(TS::OFF_MU + 7 + i) = m.v[i];
+        UKFB_PS(TS::OFF_MU + 10 + i) = m.w[i];
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 4; ++i) UKFB_PS(TS::OFF_MU + 3 + i) = m.q[i];
+}
+
+UKFB_D void pf_mu_from_smem(const double* sm, int lane, PoseMu& m)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        m.p[i] = UKFB_PS(TS::OFF_MU + i);
+        m.v[i] = UKFB_PS(TS::OFF_MU + 7 + i);
+        m.w[i] = UKFB_PS(TS::OFF_MU + 10 + i);
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 4; ++i) m.q[i] = UKFB_PS(TS::OFF_MU + 3 + i);
+}
+
+/* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
+/* On success: m holds the new mean, the record and (when to_smem) slots 0..77 hold the new covariance. */
+UKFB_D bool pf_predict(double* sm, int lane, double* sig, const double* Qp, const double* acov, const ModelArgs& ma, PoseMu& m,
+                       bool to_smem, uint32_t& status, int& passes_out, bool& spd)
+{
+    const double dt = ma.dt;
+    /* Cholesky of the record's covariance, in registers; the factor goes to the LA / LB blocks */
+    {
+        double a[PoseF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < PoseF::LP; ++e) a[e] = sig[e * TILE];
+        spd = pf_cholesky<12>(a);
+        if (!spd) return true;
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) {
+            UKFB_UNROLL
+            for (int i = 0; i < 12; ++i) UKFB_PS(PF_LA + j * 12 + i) = i >= j ? a[tri(i, j)] : 0.0;
+        }
+        UKFB_UNROLL
+        for (int j = 6; j < 12; ++j) {
+            UKFB_UNROLL
+            for (int i = 6; i < 12; ++i) UKFB_PS(PF_LB + (j - 6) * 6 + (i - 6)) = i >= j ? a[tri(i, j)] : 0.0;
+        }
+    }
+    bool slow = false;
+    double Rm[9];
+    quat_matrix(m.q, Rm);
+    double vm[3] = {m.v[0], m.v[1], m.v[2]};
+    if (ma.has_acc) {
+        vm[0] = fma(dt, ma.acc[0], vm[0]);
+        vm[1] = fma(dt, ma.acc[1], vm[1]);
+        vm[2] = fma(dt, ma.acc[2], vm[2]);
+    }
+    /* X0' = g(mu) */
+    double rw0[3], p0n[3], q0n[4];
+    {
+        double rv0[3], e0[4];
+        pf_matvec(Rm, vm, rv0);
+        pf_matvec(Rm, m.w, rw0);
+        p0n[0] = fma(dt, rv0[0], m.p[0]);
+        p0n[1] = fma(dt, rv0[1], m.p[1]);
+        p0n[2] = fma(dt, rv0[2], m.p[2]);
+        pf_exp(rw0, dt, e0, slow);
+        quat_mul(e0, m.q, q0n);
+    }
+    double ref_p[3] = {p0n[0], p0n[1], p0n[2]};
+    double ref_q[4] = {q0n[0], q0n[1], q0n[2], q0n[3]};
+
+    /* ---- manifold mean (ukfom sigma_points_mean): only position and orientation can move */
+    int it = 0, passes = 0;
+    while (true) {
+        double md[6];
+        double d0[6];
+        {
+            double r[4];
+            d0[0] = p0n[0] - ref_p[0], d0[1] = p0n[1] - ref_p[1], d0[2] = p0n[2] - ref_p[2];
+            quat_mul_conj(q0n, ref_q, r);
+            pf_log(r, d0 + 3, slow);
+        }
+        /* X0 and the 12 points of columns 6..11 deviate by d0 in position (the +- offsets cancel) */
+        md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
+        md[3] = d0[3], md[4] = d0[4], md[5] = d0[5];
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double L[12], dpl[6], dmi[6];
+            pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 6; ++i) md[i] += dpl[i] + dmi[i];
+        }
+        double c[4];
+        quat_mul_conj(m.q, ref_q, c);
+        UKFB_NOUNROLL
+        for (int j = 6; j < 12; ++j) {
+            double L[6], dopl[3], domi[3], wv[3];
+            pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) md[3 + i] += dopl[i] + domi[i];
+        }
+        double n2 = 0.0;
+        UKFB_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            md[i] = div_ns<PoseF::NS>(md[i]);
+            n2 += md[i] * md[i];
+        }
+        ref_p[0] += md[0], ref_p[1] += md[1], ref_p[2] += md[2];
+        {
+            double e[4], r[4];
+            pf_exp(md + 3, 1.0, e, slow);
+            quat_mul(e, ref_q, r);
+            ref_q[0] = r[0], ref_q[1] = r[1], ref_q[2] = r[2], ref_q[3] = r[3];
+        }
+        ++passes;
+        if (slow || !(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
+        if (++it >= UKFB_MEAN_MAX_IT) {
+            status |= UKFB_STATUS_MEAN_NO_CONVERGE;
+            break;
+        }
+    }
+    if (slow) return false;
+
+    /* ---- covariance: C = position/orientation block, X = cross block (rows 6..11 x columns 0..5) */
+    double C[21], X[36];
+    {
+        double d0[6], r[4];
+        d0[0] = p0n[0] - ref_p[0], d0[1] = p0n[1] - ref_p[1], d0[2] = p0n[2] - ref_p[2];
+        quat_mul_conj(q0n, ref_q, r);
+        pf_log(r, d0 + 3, slow);
+        UKFB_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k <= i; ++k) C[tri(i, k)] = d0[i] * d0[k];
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 36; ++i) X[i] = 0.0;
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double L[12], dpl[6], dmi[6];
+            pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 6; ++i) {
+                UKFB_UNROLL
+                for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
+            }
+            UKFB_UNROLL
+            for (int k = 0; k < 6; ++k) {
+                const double dd = dpl[k] - dmi[k];
+                UKFB_UNROLL
+                for (int i = 0; i < 6; ++i) X[i * 6 + k] = fma(L[6 + i], dd, X[i * 6 + k]);
+            }
+        }
+        double c[4];
+        quat_mul_conj(m.q, ref_q, c);
+        UKFB_NOUNROLL
+        for (int j = 6; j < 12; ++j) {
+            double L[6], dpl[6], dmi[6], wv[3];
+            pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dpl + 3, dmi + 3, wv, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) dpl[i] = d0[i] + wv[i], dmi[i] = d0[i] - wv[i];
+            UKFB_UNROLL
+            for (int i = 0; i < 6; ++i) {
+                UKFB_UNROLL
+                for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
+            }
+            UKFB_UNROLL
+            for (int k = 0; k < 6; ++k) {
+                const double dd = k < 3 ? 2.0 * wv[k] : dpl[k] - dmi[k];
+                UKFB_UNROLL
+                for (int i = 0; i < 6; ++i) X[i * 6 + k] = fma(L[i], dd, X[i * 6 + k]);
+            }
+        }
+    }
+    if (slow) return false;
+
+    /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record */
+    {
+        const double scale = ma.has_acc ? 1.0 : dt;
+        double nz[PoseF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < PoseF::LP; ++e) nz[e] = scale * UKFB_LDG(Qp + e);
+        if (!ma.has_acc) {
+            UKFB_UNROLL
+            for (int blk = 0; blk < 2; ++blk) {
+                const int off = blk * 3;
+                double t[9];
+                UKFB_UNROLL
+                for (int r = 0; r < 3; ++r) {
+                    UKFB_UNROLL
+                    for (int k = 0; k < 3; ++k) {
+                        double s = 0.0;
+                        UKFB_UNROLL
+                        for (int l = 0; l < 3; ++l) s += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
+                        t[r * 3 + k] = s;
+                    }
+                }
+                UKFB_UNROLL
+                for (int r = 0; r < 3; ++r) {
+                    UKFB_UNROLL
+                    for (int cc = 0; cc <= r; ++cc) {
+                        double s = 0.0;
+                        UKFB_UNROLL
+                        for (int k = 0; k < 3; ++k) s += t[r * 3 + k] * Rm[cc * 3 + k];
+                        nz[tri(off + r, off + cc)] = scale * s;
+                    }
+                }
+            }
+        } else {
+            UKFB_UNROLL
+            for (int r = 0; r < 3; ++r) {
+                UKFB_UNROLL
+                for (int cc = 0; cc <= r; ++cc) nz[tri(6 + r, 6 + cc)] = 2.0 * UKFB_LDG(acov + r * 3 + cc);
+            }
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k <= i; ++k) {
+                const int e = tri(i, k);
+                double s;
+                if (i < 6)
+                    s = fma(0.5, C[e], nz[e]);
+                else if (k < 6)
+                    s = fma(0.5, X[(i - 6) * 6 + k], nz[e]);
+                else
+                    s = sig[e * TILE] + nz[e];
+                sig[e * TILE] = s;
+                if (to_smem) UKFB_PS(e) = s;
+            }
+        }
+    }
+    m.p[0] = ref_p[0], m.p[1] = ref_p[1], m.p[2] = ref_p[2];
+    m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
+    m.v[0] = vm[0], m.v[1] = vm[1], m.v[2] = vm[2];
+    passes_out = passes;
+    return true;
+}
+
+/* tangent index of measurement component c of a selector kind (PoseUKF.cpp:7-69), -1 = unused component */
+UKFB_D int pf_sel(int kind, int c)
+{
+    switch (kind) {
+        case 0: return c;
+        case 1: return c < 2 ? c : -1;
+        case 2: return c == 0 ? 2 : -1;
+        case 4: return 6 + c;
+        case 5: return c < 2 ? 6 + c : -1;
+        case 6: return c == 0 ? 8 : -1;
+        case 7: return c == 0 ? 6 : (c == 1 ? 11 : -1);
+        default: return 9 + c; /* 8 */
+    }
+}
+
+UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
+{
+    /* Euclidean tangent component t (0..2 position, 6..8 velocity, 9..11 angular velocity) of the mean */
+    double r = m.p[0];
+    r = t == 1 ? m.p[1] : r;
+    r = t == 2 ? m.p[2] : r;
+    r = t == 6 ? m.v[0] : r;
+    r = t == 7 ? m.v[1] : r;
+    r = t == 8 ? m.v[2] : r;
+    r = t == 9 ? m.w[0] : r;
+    r = t == 10 ? m.w[1] : r;
+    r = t == 11 ? m.w[2] : r;
+    return r;
+}
+
+/* ---- structured update with a selector measurement.  Slots 0..77 hold the prior covariance (packed lower), which
+ * is also in the record.  Returns false when apply_delta left the polynomial range: the record then holds
+ * Sigma - K S K^T and the TS mu / delta slots are set up for pf_literal_apply. */
+UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rmeas, int r_ld, PoseMu& m,
+                      uint32_t& status, int& passes_out, bool& spd)
+{
+    typedef TSmem<PoseF> TS;
+    const int m_dim = meas_dim(kind);
+    int sel[3];
+    UKFB_UNROLL
+    for (int c = 0; c < 3; ++c) sel[c] = pf_sel(kind, c);
+
+    /* S = Sigma[sel,sel] + R, Sxz = Sigma[:,sel] (identity / zero padded to 3 like the reference's 3-vectors) */
+    double Sxz[36], S[9], innov[3];
+    UKFB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        const int s = sel[c] < 0 ? 0 : sel[c];
+        const bool used = c < m_dim;
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) {
+            const int e = i >= s ? tri(i, 0) + s : tri(s, 0) + i;
+            const double x = UKFB_PS(e);
+            Sxz[i * 3 + c] = used ? x : 0.0;
+        }
+        innov[c] = used ? zm[c] - pf_mu_tangent(m, s) : 0.0;
+    }
+    UKFB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        UKFB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            const int sa = sel[a] < 0 ? 0 : sel[a], sc = sel[c] < 0 ? 0 : sel[c];
+            const int e = sa >= sc ? tri(sa, 0) + sc : tri(sc, 0) + sa;
+            const bool used = a < m_dim && c < m_dim;
+            const double x = UKFB_PS(e);
+            S[a * 3 + c] = used ? x + Rmeas[a * r_ld + c] : (a == c ? 1.0 : 0.0);
+        }
+    }
+    /* S^-1 by cofactors (Eigen fixed-size inverse) */
+    double Si[9];
+    {
+        const double c00 = S[4] * S[8] - S[5] * S[7];
+        const double c10 = S[7] * S[2] - S[8] * S[1];
+        const double c20 = S[1] * S[5] - S[2] * S[4];
+        const double det = c00 * S[0] + c10 * S[3] + c20 * S[6];
+        const double invdet = 1.0 / det;
+        Si[0] = c00 * invdet;
+        Si[1] = c10 * invdet;
+        Si[2] = c20 * invdet;
+        Si[3] = (S[5] * S[6] - S[3] * S[8]) * invdet;
+        Si[4] = (S[8] * S[0] - S[6] * S[2]) * invdet;
+        Si[5] = (S[2] * S[3] - S[0] * S[5]) * invdet;
+        Si[6] = (S[3] * S[7] - S[4] * S[6]) * invdet;
+        Si[7] = (S[6] * S[1] - S[7] * S[0]) * invdet;
+        Si[8] = (S[0] * S[4] - S[1] * S[3]) * invdet;
+    }
+    /* K = Sxz S^-1 (in place), KS = K S, delta = K innov */
+    double KS[36], delta[12];
+    UKFB_UNROLL
+    for (int i = 0; i < 12; ++i) {
+        double k3[3];
+        UKFB_UNROLL
+        for (int cc = 0; cc < 3; ++cc) {
+            double s = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) s += Sxz[i * 3 + k] * Si[k * 3 + cc];
+            k3[cc] = s;
+        }
+        double dl = 0.0;
+        UKFB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            double ks = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + c];
+            KS[i * 3 + c] = ks;
+            Sxz[i * 3 + c] = k3[c];
+            dl += k3[c] * innov[c];
+        }
+        delta[i] = dl;
+    }
+    /* Sigma <- Sigma - (K S) K^T: to the record, and kept in registers for the factorisation */
+    double a[PoseF::LP];
+    UKFB_UNROLL
+    for (int i = 0; i < 12; ++i) {
+        UKFB_UNROLL
+        for (int j = 0; j <= i; ++j) {
+            double s = 0.0;
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) s += KS[i * 3 + k] * Sxz[j * 3 + k];
+            const double x = UKFB_PS(tri(i, j)) - s;
+            a[tri(i, j)] = x;
+            sig[tri(i, j) * TILE] = x;
+        }
+    }
+    /* first six columns of the factor of the updated covariance (the reference factorises all of it: a failure in the
+     * later columns shows at the next factorisation of this filter instead) */
+    spd = pf_cholesky<6>(a);
+    if (!spd) return true;
+    UKFB_UNROLL
+    for (int j = 0; j < 6; ++j) {
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) UKFB_PS(PF_LA + j * 12 + i) = i >= j ? a[tri(i, j)] : 0.0;
+    }
+
+    /* ---- apply_delta: orientation rows only */
+    bool slow = false;
+    double e0[4], q0n[4];
+    pf_exp(delta + 3, 1.0, e0, slow);
+    quat_mul(e0, m.q, q0n);
+    double ref_q[4] = {q0n[0], q0n[1], q0n[2], q0n[3]};
+    int it = 0, passes = 0;
+    while (true) {
+        double c[4], r[4], d0[3], md[3];
+        quat_mul_conj(m.q, ref_q, c);
+        quat_mul(e0, c, r);
+        pf_log(r, d0, slow);
+        md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double vp[3], vn[3], ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
+                vp[i] = delta[3 + i] + l;
+                vn[i] = delta[3 + i] - l;
+            }
+            pf_exp(vp, 1.0, ep, slow);
+            pf_exp(vn, 1.0, en, slow);
+            quat_mul(ep, c, rp);
+            quat_mul(en, c, rn);
+            pf_log(rp, dp, slow);
+            pf_log(rn, dn, slow);
+            md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
+        }
+        double n2 = 0.0;
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            md[i] = div_ns<PoseF::NS>(md[i]);
+            n2 += md[i] * md[i];
+        }
+        {
+            double e[4], rr[4];
+            pf_exp(md, 1.0, e, slow);
+            quat_mul(e, ref_q, rr);
+            ref_q[0] = rr[0], ref_q[1] = rr[1], ref_q[2] = rr[2], ref_q[3] = rr[3];
+        }
+        ++passes;
+        if (slow || !(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
+        if (++it >= UKFB_MEAN_MAX_IT) {
+            status |= UKFB_STATUS_MEAN_NO_CONVERGE;
+            break;
+        }
+    }
+    /* covariance of the orientation rows: Coo (6) and the cross block with the 9 Euclidean components */
+    double Coo[6], Xc[27];
+    if (!slow) {
+        double c[4], r[4], d0[3];
+        quat_mul_conj(m.q, ref_q, c);
+        quat_mul(e0, c, r);
+        pf_log(r, d0, slow);
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = 13.0 * d0[i] * d0[k];
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 27; ++i) Xc[i] = 0.0;
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double L[12], vp[3], vn[3], ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
+            UKFB_UNROLL
+            for (int i = 0; i < 12; ++i) L[i] = UKFB_PS(PF_LA + j * 12 + i);
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                vp[i] = delta[3 + i] + L[3 + i];
+                vn[i] = delta[3 + i] - L[3 + i];
+            }
+            pf_exp(vp, 1.0, ep, slow);
+            pf_exp(vn, 1.0, en, slow);
+            quat_mul(ep, c, rp);
+            quat_mul(en, c, rn);
+            pf_log(rp, dp, slow);
+            pf_log(rn, dn, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                UKFB_UNROLL
+                for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = fma(dp[i], dp[k], fma(dn[i], dn[k], Coo[tri(i, k)]));
+            }
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                const double dd = dp[k] - dn[k];
+                UKFB_UNROLL
+                for (int t = 0; t < 9; ++t) Xc[t * 3 + k] = fma(L[t < 3 ? t : t + 3], dd, Xc[t * 3 + k]);
+            }
+        }
+    }
+    if (slow) { /* hand over to the literal apply_delta: mu and delta in the TS slots, Sigma - K S K^T in the record */
+        pf_mu_to_smem(sm, lane, m);
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) UKFB_PS(TS::OFF_DELTA + i) = delta[i];
+        return false;
+    }
+    /* commit */
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        UKFB_UNROLL
+        for (int k = 0; k <= i; ++k) sig[tri(3 + i, 3 + k) * TILE] = 0.5 * Coo[tri(i, k)];
+        UKFB_UNROLL
+        for (int t = 0; t < 3; ++t) sig[tri(3 + i, t) * TILE] = 0.5 * Xc[t * 3 + i];         /* orientation x position */
+        UKFB_UNROLL
+        for (int t = 3; t < 9; ++t) sig[tri(t + 3, 3 + i) * TILE] = 0.5 * Xc[t * 3 + i];     /* (vel, angvel) x orientation */
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        m.p[i] += delta[i];
+        m.v[i] += delta[6 + i];
+        m.w[i] += delta[9 + i];
+    }
+    m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
+    passes_out = passes;
+    return true;
+}
+
+/* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
+{
+    typedef PoseF F;
+    typedef TSmem<F> TS;
+    UKFB_SMEM_DECL
+    double* sm = ukfb_smem;
+    const int lane = threadIdx.x;
+    const long long b = (long long)blockIdx.x * TILE + lane;
+    const bool valid = b < p.B;
+    const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
+    double* rec = p.state + (long long)blockIdx.x * (TILE * F::REC) + lane; /* entry e at rec[e * TILE] */
+    double* sig = rec + F::MU * TILE;
+
+    PoseMu m;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) m.p[i] = rec[i * TILE], m.v[i] = rec[(7 + i) * TILE], m.w[i] = rec[(10 + i) * TILE];
+    UKFB_UNROLL
+    for (int i = 0; i < 4; ++i) m.q[i] = rec[(3 + i) * TILE];
+
+    ModelArgs ma;
+    ma.dt = 0.0;
+    ma.has_acc = false;
+    ma.neg_inv_tau_g = 0.0;
+    ma.neg_inv_tau_a = 0.0;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        ma.earth[i] = 0.0;
+        ma.acc[i] = p.acc_mu[bb * 3 + i];
+        ma.omega[i] = 0.0;
+    }
+    const double big = 1.79769313486231570e308;
+    uint32_t status = 0;
+    bool dirty_mu = false;
+    int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    UKFB_NOUNROLL
+    for (int tick = 0; tick < p.K; ++tick) {
+        /* ---- control: time guards (UnscentedKalmanFilter.hpp:83-125), masks */
+        bool do_pred = false, do_upd = false;
+        int kind = -1;
+        if (valid) {
+            if (p.do_predict) {
+                double dt;
+                bool have_dt = true;
+                if (p.time_mode) {
+                    const long long ts = p.ts[tick * p.ts_kstride + b * p.ts_stride];
+                    const long long tl = p.t_last[b];
+                    if (tl == 0) { /* first call: latch only (:86-90) */
+                        p.t_last[b] = ts;
+                        have_dt = false;
+                        dt = 0.0;
+                    } else {
+                        dt = double(ts - tl) / UKFB_US_PER_S;
+                        if (dt > p.min_dt) p.t_last[b] = ts; /* :96-97 */
+                    }
+                } else {
+                    dt = p.dt[tick * p.dt_kstride + b * p.dt_stride];
+                }
+                if (have_dt) {
+                    if (dt < 0.0)
+                        status |= UKFB_STATUS_NEG_DT;
+                    else if (dt <= p.min_dt) {
+                        /* delta time is zero or close to zero: no-op */
+                    } else if (dt > p.max_dt)
+                        status |= UKFB_STATUS_DT_TOO_LARGE;
+                    else {
+                        do_pred = true;
+                        ma.dt = dt;
+                    }
+                }
+            }
+            if (p.do_update) {
+                kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+                do_upd = kind >= 0; /* PoseUKF never finite-checks a measurement (PoseUKF.cpp:112-173) */
+            }
+        }
+
+        int passes_a = 0, passes_b = 0;
+        bool sigma_in_smem = false; /* slots 0..77 hold this lane's current covariance */
+        const double* Qp = p.Q + b * p.q_stride;
+        const double* acov = p.acc_cov ? p.acc_cov + b * 9 : nullptr;
+
+        /* ---- predict (ukfom predict, App. A.3) ------------------------------------------------------------- */
+        if (do_pred) {
+            ma.has_acc = (fabs(ma.acc[0]) <= big) && (fabs(ma.acc[1]) <= big) && (fabs(ma.acc[2]) <= big);
+            bool spd = true;
+            const bool want_smem = do_upd && kind != UKFB_MEAS_POSE_ORIENTATION;
+            if (pf_predict(sm, lane, sig, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
+                if (!spd) {
+                    status |= UKFB_STATUS_NOT_SPD;
+                    do_upd = false; /* every later factorisation of this covariance fails too */
+                } else {
+                    sigma_in_smem = want_smem;
+                    dirty_mu = true;
+                }
+            } else { /* a polynomial range was left: nothing was modified, run the literal code */
+                pf_mu_to_smem(sm, lane, m);
+                const uint32_t st = pf_literal_predict(sm, lane, sig, Qp, acov, ma, &passes_a);
+                status |= st;
+                if (st & UKFB_STATUS_NOT_SPD)
+                    do_upd = false;
+                else {
+                    pf_mu_from_smem(sm, lane, m);
+                    dirty_mu = true;
+                }
+            }
+        }
+
+        /* ---- update (ukfom update + apply_delta, App. A.4) --------------------------------------------------- */
+        if (do_upd) {
+            const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+            const double* Rmeas = p.R + tick * p.r_kstride + b * p.r_stride;
+            bool literal = kind == UKFB_MEAS_POSE_ORIENTATION;
+            if (!literal) {
+                if (!sigma_in_smem) {
+                    /* no predict ran on this covariance in this tick: it has not been shown to be SPD yet, and the
+                     * reference's update factorises it first */
+                    double a[F::LP];
+                    UKFB_UNROLL
+                    for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
+                    UKFB_UNROLL
+                    for (int e = 0; e < F::LP; ++e) UKFB_PS(e) = a[e];
+                    if (!pf_cholesky<12>(a)) {
+                        status |= UKFB_STATUS_NOT_SPD;
+                        do_upd = false;
+                    }
+                }
+                const double tr = UKFB_PS(tri(3, 3)) + UKFB_PS(tri(4, 4)) + UKFB_PS(tri(5, 5));
+                literal = !(tr < PF_PI2_GUARD);
+            }
+            if (do_upd && !literal) {
+                bool spd = true;
+                if (pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, status, passes_b, spd)) {
+                    if (!spd)
+                        status |= UKFB_STATUS_NOT_SPD;
+                    else
+                        dirty_mu = true;
+                } else {
+                    const uint32_t st = pf_literal_apply(sm, lane, sig, ma, &passes_b);
+                    status |= st;
+                    if (!(st & UKFB_STATUS_NOT_SPD)) {
+                        pf_mu_from_smem(sm, lane, m);
+                        dirty_mu = true;
+                    }
+                }
+            } else if (do_upd) {
+                pf_mu_to_smem(sm, lane, m);
+                const uint32_t st = pf_literal_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, &passes_b);
+                status |= st;
+                if (!(st & UKFB_STATUS_NOT_SPD)) {
+                    pf_mu_from_smem(sm, lane, m);
+                    dirty_mu = true;
+                }
+            }
+        }
+        {
+            const int pa = passes_a < 7 ? passes_a : 7, pb = passes_b < 7 ? passes_b : 7;
+            UKFB_UNROLL
+            for (int k = 1; k < 8; ++k) hist[k] += (pa == k) + (pb == k);
+        }
+    }
+
+    /* ---- write back the mean: the covariance is already in the record ---------------------------------------------- */
+    if (valid && dirty_mu) {
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) rec[i * TILE] = m.p[i], rec[(7 + i) * TILE] = m.v[i], rec[(10 + i) * TILE] = m.w[i];
+        UKFB_UNROLL
+        for (int i = 0; i < 4; ++i) rec[(3 + i) * TILE] = m.q[i];
+    }
+    if (valid && status) p.status[b] |= status;
+    if (p.hist && valid) {
+        unsigned long long* hs = p.hist + (blockIdx.x % HIST_SLOTS) * 8;
+        UKFB_UNROLL
+        for (int k = 1; k < 8; ++k)
+            if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);
+    }
+}
+
+#undef UKFB_PS
+
+} /* namespace ukfb */
+
+#endif /* UKFB_POSE_FAST_CUH */

@@ -42,7 +42,8 @@ def load(sanitize: bool = False):
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/simt.cuh"),
-            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh")]
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"),
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", _DIR,
                "-o", out, srcs[0]]
@@ -60,9 +61,11 @@ class EmuBatch:
     """Host-side state + calls into the emulated kernel; mirrors OracleBatch method names."""
 
     def __init__(self, kind: int, B: int, G: int = 4, kernel: str = "warp"):
-        """kernel: 'warp' (ukf_device.cuh, AoS records) or 'thread' (ukf_thread.cuh, 32-filter entry-major tiles)"""
+        """kernel: 'warp' (ukf_device.cuh, AoS records), 'thread' (ukf_thread.cuh, 32-filter entry-major tiles) or
+        'fast' (ukf_pose_fast.cuh, PoseUKF only, same tiles)"""
         self.lib = load()
-        self.kind, self.B, self.G, self.tiled = kind, B, G, kernel == "thread"
+        self.kind, self.B, self.G, self.tiled = kind, B, G, kernel in ("thread", "fast")
+        self.fast = kernel == "fast" and kind == 0
         self.n, self.MU, self.REC = (12, 13, 91) if kind == 0 else (13, 14, 105)
         self.LP = self.n * (self.n + 1) // 2
         self.tril = np.tril_indices(self.n)
@@ -157,7 +160,10 @@ class EmuBatch:
         if self.tiled:  # [tile][entry][lane] in memory
             dev = np.ascontiguousarray(self.state.reshape(-1, 32, self.REC).transpose(0, 2, 1))
             p.state = _ptr(dev)
-            rc = self.lib.emu_thread_step(C.c_int(self.kind), C.byref(p))
+            if self.fast:
+                rc = self.lib.emu_pose_fast_step(C.byref(p))
+            else:
+                rc = self.lib.emu_thread_step(C.c_int(self.kind), C.byref(p))
             self.state[:] = dev.transpose(0, 2, 1).reshape(self.Bpad, self.REC)
         else:
             rc = self.lib.emu_step(C.c_int(self.kind), C.c_int(self.G), C.byref(p))
@@ -192,6 +198,12 @@ class EmuBatch:
         dt = np.ascontiguousarray(np.atleast_1d(np.asarray(dt, float)))
         a = self._upd_args(kind, mu, cov, mask)
         self._launch(do_predict=1, time_mode=0, dt=dt, dt_stride=1 if dt.size == self.B else 0, **a)
+
+    def fallbacks(self):
+        """(literal predict, literal update, literal apply_delta) calls made so far by the fast kernel's lanes"""
+        out = (C.c_ulonglong * 3)()
+        self.lib.emu_pose_fast_fallbacks(out)
+        return np.array(list(out), np.int64)
 
     def get_status(self):
         return self.status.copy()

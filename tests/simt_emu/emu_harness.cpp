@@ -7,6 +7,7 @@
 #define UKFB_SIMT_EMU 1
 #include "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"
 #include "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"
+#include "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh"
 
 using namespace ukfb;
 
@@ -47,6 +48,19 @@ extern "C" int emu_thread_step(int filter_kind, const StepParams* p)
     else
         simt_emu::launch(ukf_thread_kernel<OriF>, grid, TILE, sizeof(double) * TSmem<OriF>::TOTAL, *p);
     return 0;
+}
+
+/* the structure-exploiting PoseUKF kernel (ukf_pose_fast.cuh), same tiles */
+extern "C" int emu_pose_fast_step(const StepParams* p)
+{
+    const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
+    simt_emu::launch(ukf_pose_fast_kernel, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
+    return 0;
+}
+
+extern "C" void emu_pose_fast_fallbacks(unsigned long long* out3)
+{
+    for (int i = 0; i < 3; ++i) out3[i] = pf_fallbacks[i];
 }
 
 extern "C" int emu_sizeof_params(void) { return int(sizeof(StepParams)); }

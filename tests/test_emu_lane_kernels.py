@@ -1,0 +1,142 @@
+"""The two lane-per-filter kernels -- ukf_thread.cuh (literal sigma-point sequence) and ukf_pose_fast.cuh (the
+structure-exploiting PoseUKF kernel, with its literal fallbacks) -- compiled for the host by tests/simt_emu and
+compared with the CPU oracle in the GPU-less container.  The GPU gate is tests/test_gpu_parity.py."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import parity as P
+from emu_lib import EmuBatch
+from oracle.oracle_lib import OracleBatch
+from slam_pose_estimation_b200 import synthetic as syn
+
+TOL = 1e-12
+KERNELS = ["thread", "fast"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pose_stream(kernel):
+    B = 37  # one full tile and a ragged one
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel=kernel)
+    P.run_pose_c3(o, B, 12)
+    P.run_pose_c3(e, B, 12)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} pose stream")
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert not e.get_status().any()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("fused", [False, True])
+def test_pose_every_measurement_kind(kernel, fused):
+    B = 5
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel=kernel)
+    for rnd in range(2):
+        for kind in range(9):
+            z, R = syn.pose_measurement(kind, B, kind + 1 + 9 * rnd)
+            for x in (o, e):
+                if fused:
+                    x.step(0.02, kind, z, R)
+                else:
+                    x.predict_dt(0.02)
+                    x.update(kind, z, R)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} update kinds")
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pose_acceleration_mask_and_guards(kernel):
+    B = 6
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel=kernel)
+    acc = 0.01 * syn.noise(np.arange(B), 1, 13, 3)
+    mask = (np.arange(B) % 2).astype(np.uint8)
+    dt = np.array([-1.0, 0.0, 0.01, 0.02, 5.0, 0.03])
+    z, R = syn.pose_measurement(4, B, 2)
+    for x in (o, e):
+        x.set_time_bounds(1e-9, 1.0)
+        x.set_acceleration(acc, np.eye(3) * 1e-4, mask)
+        x.predict_dt(dt)
+        x.update(4, z, R, mask)
+        x.step(dt, 0, *syn.pose_measurement(0, B, 3), mask)
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} acceleration / mask / guards")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_not_spd_leaves_the_filter_untouched(kernel):
+    mu, sg = syn.pose_initial(3)
+    sg[1, 7, 7] = -1.0
+    z, R = syn.pose_measurement(8, 3, 1)
+    for fused in (True, False):
+        o, e = OracleBatch(0, 3), EmuBatch(0, 3, kernel=kernel)
+        for x in (o, e):
+            x.initialize(mu, sg)
+            if fused:
+                x.step(0.01, 8, z, R)
+            else:
+                x.update(8, z, R)
+        assert e.get_status().tolist() == o.get_status().tolist() == [0, 8, 0]
+        assert np.array_equal(e.get_state()[0][1], mu[1]) and np.array_equal(np.tril(e.get_state()[1][1]), np.tril(sg[1]))
+        P.assert_parity(0, (e.get_state()[0][[0, 2]], e.get_state()[1][[0, 2]]),
+                        (o.get_state()[0][[0, 2]], o.get_state()[1][[0, 2]]), tol=TOL, what="neighbours of a non-SPD filter")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pose_large_angles_take_the_literal_expressions(kernel):
+    """Orientation spread and rates far outside the polynomial ranges of so3.cuh (half angle 0.5 rad in exp, 33
+    degrees in log) and an orientation variance beyond the selector-update guard: the fast kernel must hand these
+    lanes to the literal code and still agree with the oracle."""
+    B = 4
+    mu, sg = syn.pose_initial(B)
+    sg[0, 3:6, 3:6] *= 150.0  # sqrt(1.5) rad orientation sigma: exp and log leave the polynomial range
+    sg[1, 3:6, 3:6] *= 400.0  # trace 12 > 9: selector-update guard
+    mu[2, 10:13] = [3.0, -40.0, 25.0]  # 47 rad/s: |w| dt = 0.94 rad with dt = 0.02 stays fast; with 0.05 it does not
+    o, e = OracleBatch(0, B), EmuBatch(0, B, kernel=kernel)
+    before = e.fallbacks()
+    for x in (o, e):
+        x.initialize(mu, sg)
+        for k, kind in enumerate([8, 4, 0, 7]):
+            z, R = syn.pose_measurement(kind, B, k + 1)
+            x.step(0.05, kind, z, R)
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=1e-10, what=f"{kernel} large angles")
+    if kernel == "fast":
+        fb = e.fallbacks() - before
+        assert (fb > 0).all(), f"the fallbacks were not exercised: {fb}"
+        assert fb.sum() < 3 * 4 * B, "every lane fell back: the fast path was not exercised"
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pose_mixed_kinds_per_filter_noise_and_time_mode(kernel):
+    B = 9
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel=kernel)
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(B, 12, 12)) * 0.01
+    Q = A @ np.transpose(A, (0, 2, 1)) + 1e-5 * np.eye(12)
+    kinds = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8], np.int8)
+    for x in (o, e):
+        x.set_process_noise(Q)
+        x.predict_time(np.full(B, 1_000_000, np.int64))
+        for k in range(1, 4):
+            x.predict_time(1_000_000 + 20_000 * k + np.arange(B, dtype=np.int64) * (k == 2))
+            z = np.zeros((B, 3))
+            R = np.tile(np.eye(3), (B, 1, 1))
+            for b in range(B):
+                zz, RR = syn.pose_measurement(int(kinds[b]), B, k)
+                m = zz.shape[1]
+                z[b, :m] = zz[b]
+                R[b, :m, :m] = RR if RR.ndim == 2 else RR[b]
+            x.update_mixed(np.roll(kinds, k), np.roll(z, k, axis=0), np.roll(R, k, axis=0))
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} mixed kinds")
+    assert np.array_equal(e.t_last, o.get_last_time())
+
+
+def test_orientation_stream_thread_kernel():
+    B = 3
+    o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel="thread")
+    P.run_ori_c1(o, B, 12, every=4)
+    P.run_ori_c1(e, B, 12, every=4)
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=TOL, what="thread orientation stream")
+    assert np.array_equal(e.t_last, o.get_last_time())
