@@ -45,10 +45,10 @@ namespace ukfb {
  *   LA(j, i) = j * 12 + i        columns 0..5,  rows 0..11
  *   LB(j, i) = 72 + (j-6)*6 + (i-6)   columns 6..11, rows 6..11
  * Between predict and update the first 78 slots hold the predicted covariance, packed lower (dynamic selector
- * indexing).  The literal fallback uses the TSmem<PoseF> layout in the same buffer. */
+ * indexing).  The literal fallback runs on a per-thread local array instead (cold path). */
 constexpr int PF_LA = 0;
 constexpr int PF_LB = 72;
-constexpr int PF_PER_LANE = TSmem<PoseF>::PER_LANE;
+constexpr int PF_PER_LANE = 108;
 constexpr double PF_PI2_GUARD = 9.0; /* trace(Sigma_ori) below this (< pi^2) makes (mu [+] L_j) [-] mu = L_j exact */
 
 /* ---- branch-free SO(3) kernels: polynomial path only, `slow` collects range violations ------------------------ */
@@ -201,77 +201,105 @@ inline unsigned long long pf_fallbacks[3] = {0, 0, 0};
 #else
 #define UKFB_PF_COUNT(i)
 #endif
-UKFB_DNI uint32_t pf_literal_predict(double* sm, int lane, double* sig, const double* Qp, const double* acov, ModelArgs ma, int* passes)
+struct PfLit { /* result of a literal fallback, returned by value so that the caller's state stays in registers */
+    PoseMu m;
+    uint32_t status;
+    int passes;
+};
+
+UKFB_D void pf_mu_to_slots(double* loc, const PoseMu& m)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        loc[TS::OFF_MU + i] = m.p[i];
+        loc[TS::OFF_MU + 7 + i] = m.v[i];
+        loc[TS::OFF_MU + 10 + i] = m.w[i];
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 4; ++i) loc[TS::OFF_MU + 3 + i] = m.q[i];
+}
+
+UKFB_D void pf_mu_from_slots(const double* loc, PoseMu& m)
+{
+    typedef TSmem<PoseF> TS;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        m.p[i] = loc[TS::OFF_MU + i];
+        m.v[i] = loc[TS::OFF_MU + 7 + i];
+        m.w[i] = loc[TS::OFF_MU + 10 + i];
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 4; ++i) m.q[i] = loc[TS::OFF_MU + 3 + i];
+}
+
+/* The literal functions of ukf_thread.cuh index their scratch as [entry * ST + lane]; here they run on a per-thread
+ * local array (ST = 1, lane = 0), so the fast kernel's shared memory only has to hold the factor blocks. */
+UKFB_DNI PfLit pf_literal_predict(double* sig, const double* Qp, const double* acov, ModelArgs ma, PoseMu m)
 {
     typedef TSmem<PoseF> TS;
     UKFB_PF_COUNT(0);
-    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
-    store_noise<PoseF>(sm, lane, sig, Qp, acov, ma);
-    const uint32_t st = mean_and_cov<PoseF, true>(sm, lane, sig, ma, passes);
-    UKFB_UNROLL
-    for (int i = 0; i < PoseF::MU; ++i) UKFB_PS(TS::OFF_MU + i) = UKFB_PS(TS::OFF_REF + i);
-    return st;
-}
-
-/* apply_delta from the record's covariance and the TS delta / mu slots; mu slots receive the new mean */
-UKFB_DNI uint32_t pf_literal_apply(double* sm, int lane, double* sig, ModelArgs ma, int* passes)
-{
-    typedef TSmem<PoseF> TS;
-    UKFB_PF_COUNT(2);
-    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
-    const uint32_t st = mean_and_cov<PoseF, false>(sm, lane, sig, ma, passes);
-    UKFB_UNROLL
-    for (int i = 0; i < PoseF::MU; ++i) UKFB_PS(TS::OFF_MU + i) = UKFB_PS(TS::OFF_REF + i);
-    return st;
-}
-
-UKFB_DNI uint32_t pf_literal_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld,
-                                    ModelArgs ma, int* passes)
-{
-    UKFB_PF_COUNT(1);
-    if (!cholesky_thread<PoseF>(sig, sm, lane)) return UKFB_STATUS_NOT_SPD;
-    uint32_t st = update_first_half<PoseF>(sm, lane, sig, kind, zm, Rm, r_ld);
-    st |= pf_literal_apply(sm, lane, sig, ma, passes);
-    return st;
-}
-
-UKFB_D void pf_mu_to_smem(double* sm, int lane, const PoseMu& m)
-{
-    typedef TSmem<PoseF> TS;
-    UKFB_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        UKFB_PS(TS::OFF_MU + i) = m.p[i];
-        UKFB_PS(TS::OFF_MU + 7 + i) = m.v[i];
-        UKFB_PS(TS::OFF_MU + 10 + i) = m.w[i];
+    double loc[TS::PER_LANE];
+    PfLit r;
+    r.m = m, r.passes = 0;
+    pf_mu_to_slots(loc, m);
+    if (!cholesky_thread<PoseF, 1>(sig, loc, 0)) {
+        r.status = UKFB_STATUS_NOT_SPD;
+        return r;
     }
+    store_noise<PoseF, 1>(loc, 0, sig, Qp, acov, ma);
+    r.status = mean_and_cov<PoseF, true, 1>(loc, 0, sig, ma, &r.passes);
     UKFB_UNROLL
-    for (int i = 0; i < 4; ++i) UKFB_PS(TS::OFF_MU + 3 + i) = m.q[i];
+    for (int i = 0; i < PoseF::MU; ++i) loc[TS::OFF_MU + i] = loc[TS::OFF_REF + i];
+    pf_mu_from_slots(loc, r.m);
+    return r;
 }
 
-UKFB_D void pf_mu_from_smem(const double* sm, int lane, PoseMu& m)
+/* apply_delta (second half of ukfom update) from the record's covariance: first = true runs the first half too */
+struct PfDelta {
+    double d[12];
+};
+
+UKFB_DNI PfLit pf_literal_update(double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma, PoseMu m,
+                                 PfDelta delta, bool first)
 {
     typedef TSmem<PoseF> TS;
-    UKFB_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        m.p[i] = UKFB_PS(TS::OFF_MU + i);
-        m.v[i] = UKFB_PS(TS::OFF_MU + 7 + i);
-        m.w[i] = UKFB_PS(TS::OFF_MU + 10 + i);
+    UKFB_PF_COUNT(first ? 1 : 2);
+    double loc[TS::PER_LANE];
+    PfLit r;
+    r.m = m, r.passes = 0, r.status = 0;
+    pf_mu_to_slots(loc, m);
+    if (first) {
+        if (!cholesky_thread<PoseF, 1>(sig, loc, 0)) {
+            r.status = UKFB_STATUS_NOT_SPD;
+            return r;
+        }
+        r.status = update_first_half<PoseF, 1>(loc, 0, sig, kind, zm, Rm, r_ld);
+    } else {
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) loc[TS::OFF_DELTA + i] = delta.d[i];
     }
+    if (!cholesky_thread<PoseF, 1>(sig, loc, 0)) {
+        r.status |= UKFB_STATUS_NOT_SPD;
+        return r;
+    }
+    r.status |= mean_and_cov<PoseF, false, 1>(loc, 0, sig, ma, &r.passes);
     UKFB_UNROLL
-    for (int i = 0; i < 4; ++i) m.q[i] = UKFB_PS(TS::OFF_MU + 3 + i);
+    for (int i = 0; i < PoseF::MU; ++i) loc[TS::OFF_MU + i] = loc[TS::OFF_REF + i];
+    pf_mu_from_slots(loc, r.m);
+    return r;
 }
 
 /* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
-/* On success: m holds the new mean, the record and (when to_smem) slots 0..77 hold the new covariance. */
-UKFB_D bool pf_predict(double* sm, int lane, double* sig, const double* Qp, const double* acov, const ModelArgs& ma, PoseMu& m,
-                       bool to_smem, uint32_t& status, int& passes_out, bool& spd)
+/* On success: m holds the new mean, the record and (when to_smem) slots 0..77 hold the new covariance.
+ * `a` (the prior covariance, packed lower) is destroyed. */
+UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const double* Qp, const double* acov, const ModelArgs& ma,
+                       PoseMu& m, bool to_smem, uint32_t& status, int& passes_out, bool& spd)
 {
     const double dt = ma.dt;
-    /* Cholesky of the record's covariance, in registers; the factor goes to the LA / LB blocks */
+    /* Cholesky of the covariance (a: loaded from the record by the caller), in registers; the factor goes to the
+     * LA / LB blocks */
     {
-        double a[PoseF::LP];
-        UKFB_UNROLL
-        for (int e = 0; e < PoseF::LP; ++e) a[e] = sig[e * TILE];
         spd = pf_cholesky<12>(a);
         if (!spd) return true;
         UKFB_UNROLL
@@ -509,11 +537,10 @@ UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
 
 /* ---- structured update with a selector measurement.  Slots 0..77 hold the prior covariance (packed lower), which
  * is also in the record.  Returns false when apply_delta left the polynomial range: the record then holds
- * Sigma - K S K^T and the TS mu / delta slots are set up for pf_literal_apply. */
+ * Sigma - K S K^T, `delta` = K innov, m is untouched. */
 UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rmeas, int r_ld, PoseMu& m,
-                      uint32_t& status, int& passes_out, bool& spd)
+                      double* delta, uint32_t& status, int& passes_out, bool& spd)
 {
-    typedef TSmem<PoseF> TS;
     const int m_dim = meas_dim(kind);
     int sel[3];
     UKFB_UNROLL
@@ -563,7 +590,7 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
         Si[8] = (S[0] * S[4] - S[1] * S[3]) * invdet;
     }
     /* K = Sxz S^-1 (in place), KS = K S, delta = K innov */
-    double KS[36], delta[12];
+    double KS[36];
     UKFB_UNROLL
     for (int i = 0; i < 12; ++i) {
         double k3[3];
@@ -702,12 +729,7 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             }
         }
     }
-    if (slow) { /* hand over to the literal apply_delta: mu and delta in the TS slots, Sigma - K S K^T in the record */
-        pf_mu_to_smem(sm, lane, m);
-        UKFB_UNROLL
-        for (int i = 0; i < 12; ++i) UKFB_PS(TS::OFF_DELTA + i) = delta[i];
-        return false;
-    }
+    if (slow) return false; /* the caller hands mu and delta to the literal apply_delta; Sigma - K S K^T is in the record */
     /* commit */
     UKFB_UNROLL
     for (int i = 0; i < 3; ++i) {
@@ -733,7 +755,6 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef PoseF F;
-    typedef TSmem<F> TS;
     UKFB_SMEM_DECL
     double* sm = ukfb_smem;
     const int lane = threadIdx.x;
@@ -767,6 +788,12 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
 
     UKFB_NOUNROLL
     for (int tick = 0; tick < p.K; ++tick) {
+        /* the covariance is needed first by whichever phase runs: issue its loads before the control code so that
+         * their latency overlaps it (and the loads of mu above) */
+        double a[F::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
+
         /* ---- control: time guards (UnscentedKalmanFilter.hpp:83-125), masks */
         bool do_pred = false, do_upd = false;
         int kind = -1;
@@ -818,7 +845,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
             ma.has_acc = (fabs(ma.acc[0]) <= big) && (fabs(ma.acc[1]) <= big) && (fabs(ma.acc[2]) <= big);
             bool spd = true;
             const bool want_smem = do_upd && kind != UKFB_MEAS_POSE_ORIENTATION;
-            if (pf_predict(sm, lane, sig, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
+            if (pf_predict(sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
                     do_upd = false; /* every later factorisation of this covariance fails too */
@@ -827,13 +854,13 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                     dirty_mu = true;
                 }
             } else { /* a polynomial range was left: nothing was modified, run the literal code */
-                pf_mu_to_smem(sm, lane, m);
-                const uint32_t st = pf_literal_predict(sm, lane, sig, Qp, acov, ma, &passes_a);
-                status |= st;
-                if (st & UKFB_STATUS_NOT_SPD)
+                const PfLit r = pf_literal_predict(sig, Qp, acov, ma, m);
+                status |= r.status;
+                passes_a = r.passes;
+                if (r.status & UKFB_STATUS_NOT_SPD)
                     do_upd = false;
                 else {
-                    pf_mu_from_smem(sm, lane, m);
+                    m = r.m;
                     dirty_mu = true;
                 }
             }
@@ -846,11 +873,12 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
             bool literal = kind == UKFB_MEAS_POSE_ORIENTATION;
             if (!literal) {
                 if (!sigma_in_smem) {
-                    /* no predict ran on this covariance in this tick: it has not been shown to be SPD yet, and the
+                    /* no fast predict ran on this covariance in this tick: it has not been shown to be SPD yet, and the
                      * reference's update factorises it first */
-                    double a[F::LP];
-                    UKFB_UNROLL
-                    for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
+                    if (do_pred) { /* the literal predict rewrote the record */
+                        UKFB_UNROLL
+                        for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
+                    }
                     UKFB_UNROLL
                     for (int e = 0; e < F::LP; ++e) UKFB_PS(e) = a[e];
                     if (!pf_cholesky<12>(a)) {
@@ -861,28 +889,31 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                 const double tr = UKFB_PS(tri(3, 3)) + UKFB_PS(tri(4, 4)) + UKFB_PS(tri(5, 5));
                 literal = !(tr < PF_PI2_GUARD);
             }
-            if (do_upd && !literal) {
-                bool spd = true;
-                if (pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, status, passes_b, spd)) {
-                    if (!spd)
-                        status |= UKFB_STATUS_NOT_SPD;
-                    else
-                        dirty_mu = true;
-                } else {
-                    const uint32_t st = pf_literal_apply(sm, lane, sig, ma, &passes_b);
-                    status |= st;
-                    if (!(st & UKFB_STATUS_NOT_SPD)) {
-                        pf_mu_from_smem(sm, lane, m);
-                        dirty_mu = true;
+            if (do_upd) {
+                bool spd = true, fast_done = false;
+                double delta[12];
+                UKFB_UNROLL
+                for (int i = 0; i < 12; ++i) delta[i] = 0.0;
+                if (!literal) {
+                    fast_done = pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd);
+                    if (fast_done) {
+                        if (!spd)
+                            status |= UKFB_STATUS_NOT_SPD;
+                        else
+                            dirty_mu = true;
                     }
                 }
-            } else if (do_upd) {
-                pf_mu_to_smem(sm, lane, m);
-                const uint32_t st = pf_literal_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, &passes_b);
-                status |= st;
-                if (!(st & UKFB_STATUS_NOT_SPD)) {
-                    pf_mu_from_smem(sm, lane, m);
-                    dirty_mu = true;
+                if (!fast_done) { /* orientation measurement, failed guard, or apply_delta left the polynomial range */
+                    PfDelta dl;
+                    UKFB_UNROLL
+                    for (int i = 0; i < 12; ++i) dl.d[i] = delta[i];
+                    const PfLit r = pf_literal_update(sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal);
+                    status |= r.status;
+                    passes_b = r.passes;
+                    if (!(r.status & UKFB_STATUS_NOT_SPD)) {
+                        m = r.m;
+                        dirty_mu = true;
+                    }
                 }
             }
         }

@@ -44,12 +44,14 @@ struct TSmem { /* per-lane doubles, stored entry-major: entry e of lane l at e *
     static constexpr int TOTAL = PER_LANE * TILE;
 };
 
-#define UKFB_TS(e) sm[(e) * TILE + lane]
+/* ST: element stride between consecutive entries of one lane: TILE in shared memory ([entry][lane]); the fast PoseUKF
+ * kernel runs these functions as its cold fallback on a per-thread local array with ST = 1, lane = 0 */
+#define UKFB_TS(e) sm[(e) * ST + lane]
 
 /* ---- Cholesky of the covariance in the HBM record into shared memory ------------------------------------ */
 /* LAPACK dpotf2('L') order.  sig: this lane's covariance in its record (entry stride TILE).  Out of line: one
  * copy of the unrolled factorisation serves the three call sites. */
-template <class F>
+template <class F, int ST = TILE>
 UKFB_DNI bool cholesky_thread(const double* sig, double* sm, int lane)
 {
     typedef TSmem<F> TS;
@@ -83,7 +85,7 @@ UKFB_DNI bool cholesky_thread(const double* sig, double* sm, int lane)
 
 /* ---- sigma point p of this lane's filter: X0 = mu [+] delta, X(2j+1) = mu [+] (delta + L[:,j]),
  * X(2j+2) = mu [+] (delta - L[:,j]).  p is uniform over the warp. */
-template <class F, bool WITH_DELTA>
+template <class F, bool WITH_DELTA, int ST = TILE>
 UKFB_D void sigma_point(const double* sm, int lane, int p, double* x)
 {
     typedef TSmem<F> TS;
@@ -123,7 +125,7 @@ UKFB_D void apply_model(double* x, const ModelArgs& a)
  * PREDICT = false: X_p = mu [+] (delta +- L[:,j])  (apply_delta, App. A.4);   out = 0.5 C
  * Leaves the new mean in the REF slots and writes the new covariance to `sig` (HBM record).  Returns the number of
  * mean passes through *passes. */
-template <class F, bool PREDICT>
+template <class F, bool PREDICT, int ST = TILE>
 UKFB_D uint32_t mean_and_cov(double* sm, int lane, double* sig, const ModelArgs& ma, int* passes_out)
 {
     typedef TSmem<F> TS;
@@ -137,7 +139,7 @@ UKFB_D uint32_t mean_and_cov(double* sm, int lane, double* sig, const ModelArgs&
         UKFB_NOUNROLL
         for (int p = 0; p < F::NS; ++p) {
             double x[F::MU];
-            sigma_point<F, !PREDICT>(sm, lane, p, x);
+            sigma_point<F, !PREDICT, ST>(sm, lane, p, x);
             if (PREDICT) apply_model<F>(x, ma);
             if (p == 0 && passes == 0) {
                 UKFB_UNROLL
@@ -180,7 +182,7 @@ UKFB_D uint32_t mean_and_cov(double* sm, int lane, double* sig, const ModelArgs&
         double d[F::N];
         {
             double x[F::MU];
-            sigma_point<F, !PREDICT>(sm, lane, p, x);
+            sigma_point<F, !PREDICT, ST>(sm, lane, p, x);
             if (PREDICT) apply_model<F>(x, ma);
             double ref[F::MU];
             UKFB_UNROLL
@@ -207,7 +209,7 @@ UKFB_D uint32_t mean_and_cov(double* sm, int lane, double* sig, const ModelArgs&
  *   no acceleration: scale * Q with the two rotated blocks rot * Q[blk] * rot^T, rot from the PRIOR orientation;
  *     scale = dt (PoseUKF.cpp:182-186) or dt^2 (OrientationUKF.cpp:81-86);
  *   acceleration (the shadowing local of PoseUKF.cpp:190-191): Q unrotated and unscaled, velocity block = 2 acc.cov */
-template <class F>
+template <class F, int ST = TILE>
 UKFB_D void store_noise(const double* sm, int lane, double* sig, const double* Qp, const double* acov, const ModelArgs& ma)
 {
     typedef TSmem<F> TS;
@@ -254,7 +256,7 @@ UKFB_D void store_noise(const double* sm, int lane, double* sig, const double* Q
 }
 
 /* ---- first half of ukfom update (App. A.4): innovation statistics, gain, sigma <- sigma - K S K^T, delta = K innov */
-template <class F>
+template <class F, int ST = TILE>
 UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld)
 {
     typedef TSmem<F> TS;
@@ -266,7 +268,7 @@ UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, c
     double zref[4];
     {
         double x[F::MU];
-        sigma_point<F, false>(sm, lane, 0, x);
+        sigma_point<F, false, ST>(sm, lane, 0, x);
         measure<F>(x, kind, zref);
     }
     {
@@ -276,7 +278,7 @@ UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, c
             UKFB_NOUNROLL
             for (int p = 0; p < F::NS; ++p) {
                 double x[F::MU], z[4], dz[3];
-                sigma_point<F, false>(sm, lane, p, x);
+                sigma_point<F, false, ST>(sm, lane, p, x);
                 measure<F>(x, kind, z);
 #if UKFB_EUCLID_MEAS_DIRECT_MEAN
                 if (!rot)
@@ -319,7 +321,7 @@ UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, c
     UKFB_NOUNROLL
     for (int p = 0; p < F::NS; ++p) {
         double x[F::MU], z[4], dz[3], dx[F::N], mu[F::MU];
-        sigma_point<F, false>(sm, lane, p, x);
+        sigma_point<F, false, ST>(sm, lane, p, x);
         measure<F>(x, kind, z);
         meas_boxminus(z, zref, rot, dz);
         UKFB_UNROLL
@@ -420,6 +422,7 @@ template <class F>
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef TSmem<F> TS;
+    constexpr int ST = TILE;
     UKFB_SMEM_DECL
     double* sm = ukfb_smem;
     const int lane = threadIdx.x;
