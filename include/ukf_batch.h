@@ -179,6 +179,16 @@ int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, int meas_kind
 int ukfb_step_dev(ukfb_handle* h, const double* d_dt, int dt_per_filter, int meas_kind, const double* d_mu,
                   const double* d_cov, int cov_per_filter, const uint8_t* d_mask);
 
+/* Pipelined host-pointer variants for streaming callers (the aggregator callbacks of the reference's oroGen tasks
+ * deliver one sample set per tick): same arguments and results as ukfb_step / ukfb_get_state, but the calls only
+ * enqueue.  Inputs travel on a copy-in stream into one of two staging slots while the previous step's kernel runs;
+ * estimates are unpacked after the steps issued so far and travel on a copy-out stream while later steps run.
+ * Host arrays (pinned memory for true overlap) must stay valid and unchanged until ukfb_synchronize(), which is also
+ * when mu / sigma hold the estimates. */
+int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filter, int meas_kind, const double* mu,
+                    const double* cov, int cov_per_filter, const uint8_t* mask);
+int ukfb_get_state_async(ukfb_handle* h, double* mu, double* sigma);
+
 /* K consecutive fused steps with the state resident on chip between them.
  * dt: K x B (or K when dt_per_filter = 0); kinds: K measurement kinds (one per tick,
  * UKFB_MEAS_NONE = predict only); mu3: K x B x 3; cov33: K x B x 3 x 3, or K x 3 x 3

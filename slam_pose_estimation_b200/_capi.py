@@ -49,6 +49,8 @@ SIGNATURES = {
     "ukfb_get_rotation_rate": (I, [P, P]),
     "ukfb_step": (I, [P, P, I, I, P, P, I, P]),
     "ukfb_step_dev": (I, [P, P, I, I, P, P, I, P]),
+    "ukfb_step_async": (I, [P, P, I, I, P, P, I, P]),
+    "ukfb_get_state_async": (I, [P, P, P]),
     "ukfb_run_dev": (I, [P, I, P, I, P, P, P, I, P]),
     "ukfb_get_status": (I, [P, P]),
     "ukfb_clear_status": (I, [P]),

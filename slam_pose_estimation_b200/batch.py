@@ -60,6 +60,7 @@ class UkfBatch:
         self.h = h
         self.n = self.lib.ukfb_dof(h)
         self.MU = self.lib.ukfb_mu_size(h)
+        self._inflight = []  # host arrays referenced by enqueued *_async calls
 
     def close(self):
         if getattr(self, "h", None):
@@ -210,6 +211,25 @@ class UkfBatch:
         mask, pk = _host(mask, np.uint8)
         self._chk(self.lib.ukfb_step(self.h, pd, per, kind, pm, pc, cper, pk))
 
+    def step_async(self, dt, kind: int, mu=None, cov=None, mask=None):
+        """ukfb_step_async: enqueue only.  The arrays passed here are kept alive by this object until synchronize();
+        pass pinned, C-contiguous float64 arrays (no conversion copy is made for those) for real overlap."""
+        dt = np.atleast_1d(np.asarray(dt, np.float64))
+        per = int(dt.size == self.B)
+        dt, pd = _host(dt, np.float64)
+        mu, pm = _host(mu, np.float64)
+        cov, pc = _host(cov, np.float64)
+        cper = 1 if (cov is not None and cov.ndim == 3) else 0
+        mask, pk = _host(mask, np.uint8)
+        self._inflight.append((dt, mu, cov, mask))
+        self._chk(self.lib.ukfb_step_async(self.h, pd, per, kind, pm, pc, cper, pk))
+
+    def get_state_async(self, mu: np.ndarray, sigma: np.ndarray | None = None):
+        """ukfb_get_state_async into caller-owned (pinned) host arrays; valid after synchronize()."""
+        self._inflight.append((mu, sigma))
+        self._chk(self.lib.ukfb_get_state_async(self.h, mu.ctypes.data_as(C.c_void_p),
+                                                sigma.ctypes.data_as(C.c_void_p) if sigma is not None else None))
+
     def step_dev(self, d_dt, dt_per_filter: bool, kind: int, d_mu=None, d_cov=None, cov_per_filter: bool = False, d_mask=None):
         self._chk(self.lib.ukfb_step_dev(self.h, _dev(d_dt), int(dt_per_filter), kind, _dev(d_mu), _dev(d_cov),
                                          int(cov_per_filter), _dev(d_mask)))
@@ -247,6 +267,7 @@ class UkfBatch:
     # ---- stream plumbing ------------------------------------------------------------------------------
     def synchronize(self):
         self._chk(self.lib.ukfb_synchronize(self.h))
+        self._inflight.clear()
 
     def stream(self) -> int:
         return int(self.lib.ukfb_stream(self.h) or 0)

@@ -71,6 +71,17 @@ struct ukfb_handle {
     long long* summary = nullptr; /* 2 words */
     cudaEvent_t ev[16] = {};
     long long launches = 0;
+    /* pipelined host-pointer calls (ukfb_step_async / ukfb_get_state_async): copy-in and copy-out streams beside the
+     * compute stream, two staging slots each, events ordering slot reuse */
+    struct Pipe {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        char* in[2] = {nullptr, nullptr};
+        char* out[2] = {nullptr, nullptr};
+        size_t in_bytes[2] = {0, 0}, out_bytes[2] = {0, 0};
+        cudaEvent_t in_ready[2] = {}, in_consumed[2] = {}, out_ready[2] = {}, out_drained[2] = {};
+        unsigned long long n_in = 0, n_out = 0;
+        bool made = false;
+    } pipe;
 };
 
 static int stage_reserve(ukfb_handle* h, size_t bytes)
@@ -505,6 +516,15 @@ extern "C" int ukfb_destroy(ukfb_handle* h)
     cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary);
     for (int i = 0; i < 16; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->pipe.made) {
+        cudaStreamSynchronize(h->pipe.s_in), cudaStreamSynchronize(h->pipe.s_out);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->pipe.in[i]), cudaFree(h->pipe.out[i]);
+            cudaEventDestroy(h->pipe.in_ready[i]), cudaEventDestroy(h->pipe.in_consumed[i]);
+            cudaEventDestroy(h->pipe.out_ready[i]), cudaEventDestroy(h->pipe.out_drained[i]);
+        }
+        cudaStreamDestroy(h->pipe.s_in), cudaStreamDestroy(h->pipe.s_out);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return UKFB_OK;
@@ -960,6 +980,113 @@ extern "C" int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, in
     return UKFB_OK;
 }
 
+/* ---- pipelined host-pointer calls -------------------------------------------------------------------------------- */
+static int pipe_make(ukfb_handle* h)
+{
+    if (h->pipe.made) return UKFB_OK;
+    CU(cudaStreamCreateWithFlags(&h->pipe.s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->pipe.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&h->pipe.in_ready[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->pipe.in_consumed[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->pipe.out_ready[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->pipe.out_drained[i], cudaEventDisableTiming));
+    }
+    h->pipe.made = true;
+    return UKFB_OK;
+}
+
+static int pipe_reserve(ukfb_handle* h, char** buf, size_t* have, size_t bytes)
+{
+    if (bytes <= *have) return UKFB_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->pipe.s_in));
+    CU(cudaStreamSynchronize(h->pipe.s_out));
+    if (*buf) CU(cudaFree(*buf));
+    *buf = nullptr, *have = 0;
+    const size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(buf, want);
+    if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "pipeline staging buffer of %zu bytes: %s", want, cudaGetErrorString(e));
+    *have = want;
+    return UKFB_OK;
+}
+
+/* ukfb_step without the final synchronisation: the inputs are copied on a copy-in stream into one of two staging
+ * slots while the previous step's kernel runs; the host arrays must stay valid and unchanged until
+ * ukfb_synchronize() (or until two further ukfb_step_async calls have been issued and the first has been waited
+ * for); pinned host memory makes the copies truly asynchronous. */
+extern "C" int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filter, int meas_kind, const double* mu, const double* cov,
+                               int cov_per_filter, const uint8_t* mask)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!dt) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null dt");
+    const bool upd = meas_kind != UKFB_MEAS_NONE;
+    if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: measurement kind %d does not belong to this filter kind", meas_kind);
+    if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null measurement");
+    int rc = pipe_make(h);
+    if (rc) return rc;
+    const int slot = int(h->pipe.n_in & 1);
+    const int m = upd ? meas_dim(meas_kind) : 0;
+    const size_t bd = align256(sizeof(double) * (dt_per_filter ? h->B : 1));
+    const size_t bm = upd ? align256(sizeof(double) * h->B * m) : 0;
+    const size_t bc = upd ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0;
+    const size_t bk = (upd && mask) ? align256(size_t(h->B)) : 0;
+    rc = pipe_reserve(h, &h->pipe.in[slot], &h->pipe.in_bytes[slot], bd + bm + bc + bk);
+    if (rc) return rc;
+    char* base = h->pipe.in[slot];
+    cudaStream_t si = h->pipe.s_in;
+    if (h->pipe.n_in >= 2) CU(cudaStreamWaitEvent(si, h->pipe.in_consumed[slot], 0)); /* the kernel that read this slot is done */
+    CU(cudaMemcpyAsync(base, dt, sizeof(double) * (dt_per_filter ? h->B : 1), cudaMemcpyHostToDevice, si));
+    const double *d_mu = nullptr, *d_cov = nullptr;
+    const uint8_t* d_mask = nullptr;
+    if (upd) {
+        CU(cudaMemcpyAsync(base + bd, mu, sizeof(double) * h->B * m, cudaMemcpyHostToDevice, si));
+        CU(cudaMemcpyAsync(base + bd + bm, cov, sizeof(double) * (cov_per_filter ? h->B : 1) * m * m, cudaMemcpyHostToDevice, si));
+        d_mu = reinterpret_cast<const double*>(base + bd);
+        d_cov = reinterpret_cast<const double*>(base + bd + bm);
+        if (mask) {
+            CU(cudaMemcpyAsync(base + bd + bm + bc, mask, size_t(h->B), cudaMemcpyHostToDevice, si));
+            d_mask = reinterpret_cast<const uint8_t*>(base + bd + bm + bc);
+        }
+    }
+    CU(cudaEventRecord(h->pipe.in_ready[slot], si));
+    CU(cudaStreamWaitEvent(h->stream, h->pipe.in_ready[slot], 0));
+    rc = ukfb_step_dev(h, reinterpret_cast<const double*>(base), dt_per_filter, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->pipe.in_consumed[slot], h->stream));
+    h->pipe.n_in++;
+    return UKFB_OK;
+}
+
+/* ukfb_get_state without the final synchronisation: the estimates of the steps issued so far are unpacked on the
+ * compute stream into one of two staging slots and copied to the host on a copy-out stream, overlapping later
+ * steps; mu / sigma are valid after ukfb_synchronize(). */
+extern "C" int ukfb_get_state_async(ukfb_handle* h, double* mu, double* sigma)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    int rc = pipe_make(h);
+    if (rc) return rc;
+    const int slot = int(h->pipe.n_out & 1);
+    const size_t bm = align256(sizeof(double) * h->B * h->MU), bs = sizeof(double) * h->B * h->n * h->n;
+    rc = pipe_reserve(h, &h->pipe.out[slot], &h->pipe.out_bytes[slot], bm + (sigma ? bs : 0));
+    if (rc) return rc;
+    double* d_mu = reinterpret_cast<double*>(h->pipe.out[slot]);
+    double* d_sigma = reinterpret_cast<double*>(h->pipe.out[slot] + bm);
+    if (h->pipe.n_out >= 2) CU(cudaStreamWaitEvent(h->stream, h->pipe.out_drained[slot], 0)); /* the copy that read this slot is done */
+    rc = ukfb_get_state_dev(h, mu ? d_mu : nullptr, sigma ? d_sigma : nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->pipe.out_ready[slot], h->stream));
+    cudaStream_t so = h->pipe.s_out;
+    CU(cudaStreamWaitEvent(so, h->pipe.out_ready[slot], 0));
+    if (mu) CU(cudaMemcpyAsync(mu, d_mu, sizeof(double) * h->B * h->MU, cudaMemcpyDeviceToHost, so));
+    if (sigma) CU(cudaMemcpyAsync(sigma, d_sigma, bs, cudaMemcpyDeviceToHost, so));
+    CU(cudaEventRecord(h->pipe.out_drained[slot], so));
+    h->pipe.n_out++;
+    return UKFB_OK;
+}
+
 extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, const int8_t* kinds_host, const double* d_mu3,
                             const double* d_cov33, int cov_per_filter, const double* d_imu)
 {
@@ -1058,6 +1185,10 @@ extern "C" int ukfb_synchronize(ukfb_handle* h)
 {
     CHECK_H(h);
     CU(cudaStreamSynchronize(h->stream));
+    if (h->pipe.made) {
+        CU(cudaStreamSynchronize(h->pipe.s_in));
+        CU(cudaStreamSynchronize(h->pipe.s_out));
+    }
     return UKFB_OK;
 }
 

@@ -293,3 +293,67 @@ def test_large_batch_invariants(Ukf):
         o = P.make_pose(OracleBatch, 1, first=int(i))
         P.run_pose_c3(o, 1, 10, first=int(i))
         P.assert_parity(0, (mu[i:i + 1], sg[i:i + 1]), o.get_state(), what=f"filter {i} of 65536")
+
+
+# ---- kernel variants and the streaming calls ------------------------------------------------------
+
+@pytest.mark.parametrize("kernel", ["fast", "thread", "warp"])
+def test_pose_kernels_agree_with_the_oracle(Ukf, kernel, monkeypatch):
+    """UKFB_KERNEL selects the step kernel at ukfb_create: 'fast' (default, ukf_pose_fast.cuh), 'thread' (literal
+    lane-per-filter, ukf_thread.cuh), 'warp' (literal warp-per-group, ukf_device.cuh).  All three against the oracle
+    on the C3 schedule plus one update of every kind."""
+    monkeypatch.setenv("UKFB_KERNEL", kernel)
+    B = 77
+    g, o = both(Ukf, 0, B)
+    for x in (g, o):
+        P.run_pose_c3(x, B, 30)
+        for kind in range(9):
+            z, R = syn.pose_measurement(kind, B, 40 + kind)
+            x.step(0.02, kind, z, R)
+    P.assert_parity(0, g.get_state(), o.get_state(), what=f"kernel={kernel}")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert not g.get_status().any()
+
+
+def test_pose_fast_kernel_fallback_lanes(Ukf):
+    """lanes that leave the polynomial ranges / the selector-update guard run the literal code inside the fast kernel"""
+    B = 64
+    mu, sg = syn.pose_initial(B)
+    sg[0::4, 3:6, 3:6] *= 150.0
+    sg[1::4, 3:6, 3:6] *= 400.0
+    mu[2::4, 10:13] = [3.0, -40.0, 25.0]
+    g, o = Ukf(0, B), OracleBatch(0, B)
+    for x in (g, o):
+        x.initialize(mu, sg)
+        for k, kind in enumerate([8, 4, 0, 7, 3]):
+            z, R = syn.pose_measurement(kind, B, k + 1)
+            x.step(0.05, kind, z, R)
+    assert np.array_equal(g.get_status(), o.get_status())
+    P.assert_parity(0, g.get_state(), o.get_state(), tol=1e-9, what="fast kernel fallback lanes")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+def test_streaming_calls_match_the_blocking_ones(Ukf):
+    import torch
+
+    B, steps = 5000, 7
+    a, b = P.make_pose(Ukf, B), P.make_pose(Ukf, B)
+    zs = [torch.from_numpy(syn.pose_measurement(8, B, k + 1)[0]).pin_memory() for k in range(steps)]
+    R = np.eye(3) * syn.SIGMA_GYRO**2
+    outs = [torch.empty((B, 13), dtype=torch.float64).pin_memory() for _ in range(steps)]
+    sig = torch.empty((B, 12, 12), dtype=torch.float64).pin_memory()
+    want = []
+    for k in range(steps):
+        a.step(syn.DT, 8, zs[k].numpy(), R)
+        want.append(a.get_state()[0])
+    for k in range(steps):
+        b.step_async(syn.DT, 8, zs[k].numpy(), R)
+        b.get_state_async(outs[k].numpy(), sig.numpy() if k == steps - 1 else None)
+    b.synchronize()
+    for k in range(steps):
+        assert np.array_equal(outs[k].numpy(), want[k]), f"streamed estimates of step {k} differ"
+    assert np.array_equal(sig.numpy(), a.get_state()[1])
+    # mixing blocking calls after streamed ones keeps the order
+    b.step(syn.DT, 8, zs[0].numpy(), R)
+    a.step(syn.DT, 8, zs[0].numpy(), R)
+    assert np.array_equal(a.get_state()[0], b.get_state()[0])
