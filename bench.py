@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct measurement sets cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-literal", action="store_true", help="skip the secondary measurement of the literal kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -272,10 +273,36 @@ def main():
     sampler.stop()
     clocks = sampler.summary()
 
+    # ---- the literal kernel on the same workload (secondary figure) -----------------------------------
+    # UKFB_KERNEL=thread selects ukf_thread.cuh at ukfb_create: every sigma point of every pass is pushed through
+    # boxplus / model / boxminus exactly in the reference's sequence.  The default kernel (ukf_pose_fast.cuh) computes
+    # the same estimator with the closed forms its header lists.
+    literal = None
+    if not args.no_literal:
+        f.close()
+        os.environ["UKFB_KERNEL"] = "thread"
+        g = UkfBatch(0, B, device=local)
+        os.environ.pop("UKFB_KERNEL")
+        g.initialize(mu0, sg0)
+        for k in range(args.warmup):
+            g.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
+        g.synchronize()
+        g.event_record(0)
+        for k in range(args.steps):
+            g.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
+        g.event_record(1)
+        g.synchronize()
+        lit_ms = max_over_ranks(g.event_elapsed_ms(0, 1))
+        literal = {"kernel": "ukf_thread_kernel<PoseF>", "value": world * B * args.steps / (lit_ms * 1e-3), "unit": UNIT,
+                   "ms_per_step": lit_ms / args.steps}
+        fp64_peak = g.measure_fp64_peak() if rank == 0 else 0.0
+        g.close()
+    else:
+        fp64_peak = f.measure_fp64_peak() if rank == 0 else 0.0
+
     # ---- roofline -------------------------------------------------------------------------------
     passes = float((hist * np.arange(8)).sum() / max(1, hist.sum()))
     flops_step = FLOPS_PER_STEP_K3 + (passes - 3.0) * MEANS_PER_STEP * FLOPS_PER_MEAN_PASS
-    fp64_peak = f.measure_fp64_peak() if rank == 0 else 0.0
     launch_s = ms * 1e-3 / args.steps
     achieved_flops = flops_step * B / launch_s
     achieved_gbs = HBM_BYTES_PER_STEP * B / launch_s / 1e9
@@ -285,11 +312,19 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    prof = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    traffic = prof.get("dram_bytes_per_launch") if B == (1 << 20) else None
+    executed = None
+    if prof.get("executed_fp64_flops_per_step") and fp64_peak:
+        ex = float(prof["executed_fp64_flops_per_step"]) * B / launch_s
+        executed = {"flops_per_step": prof["executed_fp64_flops_per_step"], "achieved": ex / 1e12, "frac": ex / fp64_peak,
+                    "source": "ncu op counts of this kernel on this workload (profiles/traffic.json) / this run's launch time"}
+    if literal and fp64_peak:
+        literal["roofline_frac"] = flops_step * B / (literal["ms_per_step"] * 1e-3) / fp64_peak
 
     value = world * B * args.steps / (ms * 1e-3)
     line = {
@@ -307,7 +342,10 @@ def main():
                      "frac": (achieved_flops / fp64_peak) if fp64_peak else None, "traffic": traffic,
                      "peak_source": "measured in this run: independent-DFMA microkernel (MEASURED_PEAKS.json holds no FP64 figure)",
                      "flops_per_step": flops_step, "flops_per_step_contract_k3": FLOPS_PER_STEP_K3,
-                     "kernel": "ukf_step_kernel<PoseF>", "launch_ms": launch_s * 1e3,
+                     "flops_basis": "SURVEY.md 8(d): algorithmic flops of the reference's sigma-point sequence per step; the "
+                                    "kernel reaches the same result with fewer executed operations, see `executed`",
+                     "executed": executed, "literal_kernel": literal,
+                     "kernel": "ukf_pose_fast_kernel", "launch_ms": launch_s * 1e3,
                      "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                              "bytes_per_step": HBM_BYTES_PER_STEP,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}},
@@ -316,7 +354,7 @@ def main():
         line["e2e"] = e2e
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         v, threads, dt = time_oracle(args.ref_filters, 2, 1)  # calibrate, then ~10 s of CPU work
-        nsteps = int(min(200, max(4, 10.0 / (dt / 2))))
+        nsteps = int(min(20000, max(4, 12.0 / (dt / 2))))  # about 12 s of CPU work
         v, threads, dt = time_oracle(args.ref_filters, nsteps, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{args.ref_filters} filters x {nsteps} steps of the same workload, oracle port, "

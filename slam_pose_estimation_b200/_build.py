@@ -11,7 +11,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
-LIB = os.path.join(_PKG, "lib", "libukfb.so")
+# UKFB_LIB: load another build of the same library (kernel tuning experiments)
+LIB = os.environ.get("UKFB_LIB") or os.path.join(_PKG, "lib", "libukfb.so")
 SOURCES = ["ukf_batch.cu"]
 DEPS = ["ukf_batch.cu", "ukf_device.cuh", "ukf_thread.cuh", "ukf_pose_fast.cuh", "so3.cuh", "simt.cuh", "../../include/ukf_batch.h", "../../include/ukfb_constants.h"]
 

@@ -15,6 +15,19 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct", "per_issue_active.ratio", "sm__inst_executed_pipe_tensor", "pipe_fp64_op_dmma", "sm__inst_executed_pipe_uniform"]
 print("kernel:", r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
+def val(name):
+    return float(r[hdr.index(name)].replace(",", ""))
+try:
+    cyc = val("sm__cycles_elapsed.max")
+    ops = {k: val(f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") * cyc for k in ("dadd", "dmul", "dfma")}
+    flops = ops["dadd"] + ops["dmul"] + 2 * ops["dfma"]
+    inst = ops["dadd"] + ops["dmul"] + ops["dfma"]
+    ms = val("gpu__time_duration.sum")
+    print(f"  executed FP64 thread-instructions per filter: dadd {ops['dadd']/nf:.0f} dmul {ops['dmul']/nf:.0f} dfma {ops['dfma']/nf:.0f}"
+          f"  = {inst/nf:.0f} instr, {flops/nf:.0f} flops (FMA = 2)")
+    print(f"  executed FP64 rate: {flops/(ms*1e-3)/1e12:.2f} TFLOP/s; FP64 issue slots used: {100*inst/(cyc*148*64):.1f}% of 64 lanes/clk/SM")
+except (ValueError, KeyError) as e:
+    print("  (no op counts:", e, ")")
 for h, u, v in zip(hdr, units, r):
     if any(k in h for k in keys) and "min" not in h and "max" not in h:
         try:
