@@ -62,12 +62,21 @@ typedef struct ukfb_handle ukfb_handle;
 #define UKFB_MEAS_ORI_VELOCITY 9          /* OrientationUKF::VelocityMeasurement m=3  OrientationUKF.cpp:65-72 */
 #define UKFB_MEAS_KIND_COUNT 10
 
+/* event kinds of an event stream (ukfb_run_events): every measurement kind above, plus the integrateMeasurement
+ * overloads that only store their sample for the next predict, plus "no sample in this slot" */
+#define UKFB_EVENT_IDLE (-2)
+#define UKFB_EVENT_POSE_ACCELERATION 10 /* PoseUKF::integrateMeasurement(AccelerationMeasurement)   PoseUKF.cpp:175-178 */
+#define UKFB_EVENT_ORI_ROTATION_RATE 11 /* OrientationUKF::integrateMeasurement(RotationRate)       OrientationUKF.cpp:53-57 */
+#define UKFB_EVENT_ORI_ACCELERATION 12  /* OrientationUKF::integrateMeasurement(Acceleration)       OrientationUKF.cpp:59-63 */
+#define UKFB_EVENT_KIND_COUNT 13
+
 /* sticky per-filter status bits */
 #define UKFB_STATUS_NEG_DT 1u            /* "Delta time is negative!"                          :110-113 */
 #define UKFB_STATUS_DT_TOO_LARGE 2u      /* "Delta time is greater then the allowed maximum!"  :119-122 */
 #define UKFB_STATUS_NONFINITE_MEAS 4u    /* "Measurement or covariance contains non-finite values!" :142-147 */
 #define UKFB_STATUS_NOT_SPD 8u           /* ukfom: Cholesky of sigma failed (MTK asserts)               */
 #define UKFB_STATUS_MEAN_NO_CONVERGE 16u /* ukfom: sigma_points_mean hit max_it (MTK asserts)           */
+#define UKFB_STATUS_BAD_EVENT 32u        /* an event stream held a kind this filter class has no overload for (ignored) */
 
 /* error codes */
 #define UKFB_OK 0
@@ -196,6 +205,23 @@ int ukfb_get_state_async(ukfb_handle* h, double* mu, double* sigma);
  * is stored before each predict (may be NULL). */
 int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, const int8_t* kinds_host,
                  const double* d_mu3, const double* d_cov33, int cov_per_filter, const double* d_imu);
+
+/* Event streams: the device-side form of the reference's caller loop.  The oroGen tasks around the reference run one
+ * aggregator callback per sensor sample, in timestamp order, each doing
+ *     filter.predictionStepFromSampleTime(ts);  filter.integrateMeasurement(sample);
+ * (UnscentedKalmanFilter.hpp:83-100, PoseUKF.cpp:112-178, OrientationUKF.cpp:53-72).  Here every filter has its own
+ * queue of such samples, K slots deep, slot-major:  ts[k * B + b] (int64 microseconds), kinds[k * B + b] (a
+ * UKFB_MEAS_* kind of this filter class, a storing UKFB_EVENT_* kind, UKFB_MEAS_NONE = advance the time only, or
+ * UKFB_EVENT_IDLE = filter b has no sample in slot k: nothing happens, not even the time latch), mu3[(k * B + b) * 3]
+ * (the leading m values are used).  Covariances: cov_mode 0 = one table cov[UKFB_EVENT_KIND_COUNT][3][3] indexed by
+ * kind (a sensor's covariance, leading m x m block), 1 = one per event, cov[(k * B + b) * 9].
+ * All K slots of all filters run in ONE kernel launch with the filter state resident on chip; time guards, the
+ * first-call latch, finite checks and status bits behave per event as in the single calls.  A kind the filter class
+ * has no overload for is ignored and flagged UKFB_STATUS_BAD_EVENT. */
+int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us, const int8_t* d_kinds, const double* d_mu3,
+                        const double* d_cov, int cov_mode);
+int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3,
+                    const double* cov, int cov_mode);
 
 /* ---- status ------------------------------------------------------------------ */
 

@@ -333,6 +333,61 @@ int orc_set_rotation_rate(void* h, const double* mu, const double* cov, int cov_
     return 0;
 }
 
+/* The reference's caller loop (one aggregator callback per sensor sample, in timestamp order):
+ *     filter.predictionStepFromSampleTime(ts);  filter.integrateMeasurement(sample);
+ * (UnscentedKalmanFilter.hpp:83-100, PoseUKF.cpp:112-178, OrientationUKF.cpp:53-72) run over the K queued samples of
+ * every filter; same array shapes as ukfb_run_events.  Each of the two calls is guarded on its own. */
+int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const double* mu3, const double* cov, int cov_mode)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->initialized) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < b->B; ++i) {
+        for (int k = 0; k < K; ++k) {
+            const int64_t e = int64_t(k) * b->B + i;
+            const int kind = kinds[e];
+            if (kind == -2) continue; /* idle slot */
+            const bool pose = b->kind == 0;
+            const bool known = kind >= -1 && kind <= 12 && (pose ? (kind != MEAS_ORI_VELOCITY && kind <= 10) : (kind == -1 || kind == MEAS_ORI_VELOCITY || kind >= 11));
+            if (!known) {
+                b->status[i] |= 32u;
+                continue;
+            }
+            guarded(b, i, [&] {
+                if (pose)
+                    b->pose[i]->predictionStepFromSampleTime(ts[e]);
+                else
+                    b->ori[i]->predictionStepFromSampleTime(ts[e]);
+            });
+            if (kind < 0) continue;
+            const double* c33 = cov + (cov_mode ? e * 9 : int64_t(kind) * 9);
+            const double* z = mu3 + e * 3;
+            if (kind >= 10) {
+                guarded(b, i, [&] {
+                    if (pose)
+                        b->pose[i]->setAcceleration(z, c33);
+                    else if (kind == 11)
+                        b->ori[i]->setRotationRate(z, c33);
+                    else
+                        b->ori[i]->setAcceleration(z, c33);
+                });
+                continue;
+            }
+            const int m = meas_dim(kind);
+            double zc[9];
+            for (int a = 0; a < m; ++a)
+                for (int c = 0; c < m; ++c) zc[a * m + c] = c33[a * 3 + c];
+            guarded(b, i, [&] {
+                if (pose)
+                    b->pose[i]->integrateMeasurement(kind, z, zc);
+                else
+                    b->ori[i]->integrateVelocity(z, zc);
+            });
+        }
+    }
+    return 0;
+}
+
 int orc_get_rotation_rate(void* h, double* out)
 {
     Batch* b = static_cast<Batch*>(h);

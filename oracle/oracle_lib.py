@@ -134,6 +134,16 @@ class OracleBatch:
         cov33, pc = _p(cov33, np.float64)
         self._chk(self.lib.orc_update_mixed(self.h, pk, pm, pc), "orc_update_mixed")
 
+    def run_events(self, ts, kinds, mu3, cov):
+        ts, pt = _p(ts, np.int64)
+        kinds, pk = _p(kinds, np.int8)
+        mu3, pm = _p(mu3, np.float64)
+        cov, pc = _p(cov, np.float64)
+        K = ts.size // self.B
+        per_event = cov.size == K * self.B * 9 and cov.ndim != 3
+        self._chk(self.lib.orc_run_events(self.h, C.c_int(K), pt, pk, pm, pc, C.c_int(1 if per_event else 0)),
+                  "orc_run_events")
+
     def set_acceleration(self, mu, cov=None, mask=None):
         mu, pm = _p(mu, np.float64)
         cov, pc = _p(cov, np.float64)

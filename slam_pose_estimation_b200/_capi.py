@@ -52,6 +52,8 @@ SIGNATURES = {
     "ukfb_step_async": (I, [P, P, I, I, P, P, I, P]),
     "ukfb_get_state_async": (I, [P, P, P]),
     "ukfb_run_dev": (I, [P, I, P, I, P, P, P, I, P]),
+    "ukfb_run_events_dev": (I, [P, I, P, P, P, P, I]),
+    "ukfb_run_events": (I, [P, I, P, P, P, P, I]),
     "ukfb_get_status": (I, [P, P]),
     "ukfb_clear_status": (I, [P]),
     "ukfb_status_summary": (I, [P, C.POINTER(L), C.POINTER(C.c_uint32)]),

@@ -22,7 +22,10 @@ MEAS_POSE_POSITION, MEAS_POSE_XY, MEAS_POSE_Z, MEAS_POSE_ORIENTATION = 0, 1, 2, 
 MEAS_POSE_VELOCITY, MEAS_POSE_XY_VELOCITY, MEAS_POSE_Z_VELOCITY = 4, 5, 6
 MEAS_POSE_XVEL_YAWVEL, MEAS_POSE_ANGULAR_VELOCITY, MEAS_ORI_VELOCITY = 7, 8, 9
 
+EVENT_IDLE, EVENT_POSE_ACCELERATION, EVENT_ORI_ROTATION_RATE, EVENT_ORI_ACCELERATION, EVENT_KIND_COUNT = -2, 10, 11, 12, 13
+
 STATUS_NEG_DT, STATUS_DT_TOO_LARGE, STATUS_NONFINITE_MEAS, STATUS_NOT_SPD, STATUS_MEAN_NO_CONVERGE = 1, 2, 4, 8, 16
+STATUS_BAD_EVENT = 32
 
 ERR_INVALID, ERR_NOT_INITIALIZED, ERR_CUDA, ERR_NOMEM = -1, -2, -3, -4
 
@@ -243,6 +246,24 @@ class UkfBatch:
                                         int(cov_per_filter), _dev(d_imu)))
 
     # ---- status --------------------------------------------------------------------------------------
+    def run_events(self, ts, kinds, mu3, cov):
+        """K slots of per-filter queued samples (include/ukf_batch.h, "Event streams"): ts, kinds: K x B; mu3: K x B x 3;
+        cov: EVENT_KIND_COUNT x 3 x 3 (per-sensor table) or K x B x 3 x 3 (per event)."""
+        ts, pt = _host(ts, np.int64)
+        kinds, pk = _host(kinds, np.int8)
+        mu3, pm = _host(mu3, np.float64)
+        cov, pc = _host(cov, np.float64)
+        K = ts.shape[0] if ts.ndim == 2 else ts.size // self.B
+        assert ts.size == K * self.B and kinds.size == K * self.B and mu3.size == K * self.B * 3
+        per_event = cov.size == K * self.B * 9 and cov.ndim != 3
+        if not per_event:
+            assert cov.size == EVENT_KIND_COUNT * 9
+        self._chk(self.lib.ukfb_run_events(self.h, K, pt, pk, pm, pc, 1 if per_event else 0))
+
+    def run_events_dev(self, K: int, d_ts, d_kinds, d_mu3, d_cov, per_event: bool):
+        self._chk(self.lib.ukfb_run_events_dev(self.h, int(K), _dev(d_ts), _dev(d_kinds), _dev(d_mu3), _dev(d_cov),
+                                               1 if per_event else 0))
+
     def get_status(self):
         out = np.empty(self.B, np.uint32)
         self._chk(self.lib.ukfb_get_status(self.h, out.ctypes.data_as(C.c_void_p)))

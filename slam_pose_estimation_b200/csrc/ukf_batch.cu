@@ -1129,6 +1129,64 @@ extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_pe
     return launch_step(h, p);
 }
 
+/* ---- event streams --------------------------------------------------------------------------------------- */
+extern "C" int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us, const int8_t* d_kinds, const double* d_mu3,
+                                   const double* d_cov, int cov_mode)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: K must be >= 1");
+    if (!d_ts_us || !d_kinds || !d_mu3 || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events: null argument");
+    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: cov_mode must be 0 (per-kind table) or 1 (per event)");
+    if (!h->tiled) return fail(UKFB_ERR_INVALID, "ukfb_run_events: event streams need a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
+    StepParams p = base_params(h);
+    p.K = K;
+    p.events = 1;
+    p.do_predict = 1;
+    p.time_mode = 1;
+    p.ts = reinterpret_cast<const long long*>(d_ts_us);
+    p.ts_stride = 1;
+    p.ts_kstride = h->B;
+    p.do_update = 1;
+    p.kind = -2;
+    p.kinds = d_kinds;
+    p.kinds_kstride = h->B;
+    p.z = d_mu3;
+    p.z_stride = 3;
+    p.z_kstride = h->B * 3;
+    p.R = d_cov;
+    p.r_ld = 3;
+    p.r_stride = cov_mode ? 9 : 0;
+    p.r_kstride = cov_mode ? h->B * 9 : 0;
+    p.r_kind_stride = cov_mode ? 0 : 9;
+    return launch_step(h, p);
+}
+
+extern "C" int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3, const double* cov,
+                               int cov_mode)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: K must be >= 1");
+    if (!ts_us || !kinds || !mu3 || !cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events: null argument");
+    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: cov_mode must be 0 (per-kind table) or 1 (per event)");
+    const size_t n = size_t(K) * size_t(h->B);
+    const size_t bt = align256(sizeof(int64_t) * n), bk = align256(n), bm = align256(sizeof(double) * n * 3);
+    const size_t bc = sizeof(double) * (cov_mode ? n * 9 : size_t(UKFB_EVENT_KIND_COUNT) * 9);
+    int rc = stage_reserve(h, bt + bk + bm + bc);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, ts_us, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bt, kinds, n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bt + bk, mu3, sizeof(double) * n * 3, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bt + bk + bm, cov, bc, cudaMemcpyHostToDevice, h->stream));
+    rc = ukfb_run_events_dev(h, K, reinterpret_cast<const int64_t*>(h->stage), reinterpret_cast<const int8_t*>(h->stage + bt),
+                             reinterpret_cast<const double*>(h->stage + bt + bk), reinterpret_cast<const double*>(h->stage + bt + bk + bm),
+                             cov_mode);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
 /* ---- status ------------------------------------------------------------------------------------------------ */
 extern "C" int ukfb_get_status(ukfb_handle* h, uint32_t* flags)
 {

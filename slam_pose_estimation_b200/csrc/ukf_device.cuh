@@ -114,7 +114,7 @@ struct StepParams {
     long long ts_stride;
     double min_dt, max_dt;
     double* acc_mu;         /* B x 3: POSE stored acceleration (NaN = none); ORIENTATION acceleration */
-    const double* acc_cov;  /* B x 9: POSE only */
+    double* acc_cov;        /* B x 9: POSE only (written by UKFB_EVENT_POSE_ACCELERATION events) */
     double* gyro_mu;        /* B x 3: ORIENTATION only (both written back after an imu stream run) */
     double neg_inv_tau_g, neg_inv_tau_a; /* -1.0 / tau */
     double earth[3];
@@ -135,6 +135,11 @@ struct StepParams {
     const int8_t* tick_kinds; /* K uniform kinds, one per tick (overrides `kind`), or null */
     const double* imu;        /* ORIENTATION: K x B x 6 (gyro xyz, acc xyz) stored before each predict, or null */
     long long imu_kstride;
+    /* event streams (ukfb_run_events): kinds[tick][b] is one UKFB_EVENT_* / UKFB_MEAS_* code per filter and slot, ts its
+     * sample time; an idle slot touches nothing; kinds >= 10 only store their sample after the predict.  The covariance
+     * of an event is at R + tick * r_kstride + b * r_stride + kind * r_kind_stride (per-sensor table or per event). */
+    int events;
+    long long r_kind_stride;
 };
 
 UKFB_HD int meas_dim(int kind)

@@ -478,7 +478,7 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
             UKFB_UNROLL
             for (int r = 0; r < 3; ++r) {
                 UKFB_UNROLL
-                for (int cc = 0; cc <= r; ++cc) nz[tri(6 + r, 6 + cc)] = 2.0 * UKFB_LDG(acov + r * 3 + cc);
+                for (int cc = 0; cc <= r; ++cc) nz[tri(6 + r, 6 + cc)] = 2.0 * acov[r * 3 + cc];
             }
         }
         UKFB_UNROLL
@@ -796,9 +796,22 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
 
         /* ---- control: time guards (UnscentedKalmanFilter.hpp:83-125), masks */
         bool do_pred = false, do_upd = false;
-        int kind = -1;
+        int kind = -1, store = -1;
+        const double* Rmeas = p.R + tick * p.r_kstride + b * p.r_stride;
         if (valid) {
-            if (p.do_predict) {
+            bool idle = false;
+            if (p.events) { /* one queued sample per filter and slot; UKFB_EVENT_IDLE: nothing happens */
+                kind = int(p.kinds[tick * p.kinds_kstride + b]);
+                idle = kind == UKFB_EVENT_IDLE;
+                if (kind < UKFB_EVENT_IDLE || kind == UKFB_MEAS_ORI_VELOCITY || kind > UKFB_EVENT_POSE_ACCELERATION) {
+                    status |= UKFB_STATUS_BAD_EVENT;
+                    idle = true;
+                }
+                if (idle) kind = -1;
+                if (kind >= 0) Rmeas += kind * p.r_kind_stride;
+                if (kind == UKFB_EVENT_POSE_ACCELERATION) store = kind, kind = -1;
+            }
+            if (p.do_predict && !idle) {
                 double dt;
                 bool have_dt = true;
                 if (p.time_mode) {
@@ -828,9 +841,11 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                     }
                 }
             }
-            if (p.do_update) {
-                kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
-                if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+            if (p.do_update && !idle) {
+                if (!p.events) {
+                    kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                    if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+                }
                 do_upd = kind >= 0; /* PoseUKF never finite-checks a measurement (PoseUKF.cpp:112-173) */
             }
         }
@@ -866,10 +881,20 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
             }
         }
 
+        /* ---- AccelerationMeasurement event: kept for the next predict, unchecked (PoseUKF.cpp:175-178) ---------------- */
+        if (store >= 0) {
+            const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+            UKFB_UNROLL
+            for (int r = 0; r < 3; ++r) {
+                ma.acc[r] = zm[r];
+                UKFB_UNROLL
+                for (int cc = 0; cc < 3; ++cc) p.acc_cov[b * 9 + r * 3 + cc] = Rmeas[r * p.r_ld + cc];
+            }
+        }
+
         /* ---- update (ukfom update + apply_delta, App. A.4) --------------------------------------------------- */
         if (do_upd) {
             const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-            const double* Rmeas = p.R + tick * p.r_kstride + b * p.r_stride;
             bool literal = kind == UKFB_MEAS_POSE_ORIENTATION;
             if (!literal) {
                 if (!sigma_in_smem) {
@@ -930,6 +955,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
         for (int i = 0; i < 3; ++i) rec[i * TILE] = m.p[i], rec[(7 + i) * TILE] = m.v[i], rec[(10 + i) * TILE] = m.w[i];
         UKFB_UNROLL
         for (int i = 0; i < 4; ++i) rec[(3 + i) * TILE] = m.q[i];
+    }
+    if (valid && p.events) {
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) p.acc_mu[b * 3 + i] = ma.acc[i];
     }
     if (valid && status) p.status[b] |= status;
     if (p.hist && valid) {

@@ -250,7 +250,7 @@ UKFB_D void store_noise(const double* sm, int lane, double* sig, const double* Q
         UKFB_UNROLL
         for (int r = 0; r < 3; ++r) {
             UKFB_UNROLL
-            for (int c = 0; c <= r; ++c) sig[tri(6 + r, 6 + c) * TILE] = 2.0 * UKFB_LDG(acov + r * 3 + c);
+            for (int c = 0; c <= r; ++c) sig[tri(6 + r, 6 + c) * TILE] = 2.0 * acov[r * 3 + c];
         }
     }
 }
@@ -455,8 +455,23 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
     for (int tick = 0; tick < p.K; ++tick) {
         /* ---- control: time guards (UnscentedKalmanFilter.hpp:83-125), masks, finite checks */
         bool do_pred = false, do_upd = false;
-        int kind = -1;
+        int kind = -1, store = -1;
+        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
         if (valid) {
+            bool idle = false;
+            if (p.events) { /* one queued sample per filter and slot; UKFB_EVENT_IDLE: nothing happens */
+                kind = int(p.kinds[tick * p.kinds_kstride + b]);
+                idle = kind == UKFB_EVENT_IDLE;
+                if (kind >= UKFB_EVENT_KIND_COUNT || kind < UKFB_EVENT_IDLE
+                    || (kind >= 0 && (F::KIND == 0 ? (kind == UKFB_MEAS_ORI_VELOCITY || kind > UKFB_EVENT_POSE_ACCELERATION)
+                                                   : (kind < UKFB_MEAS_ORI_VELOCITY || kind == UKFB_EVENT_POSE_ACCELERATION)))) {
+                    status |= UKFB_STATUS_BAD_EVENT;
+                    idle = true;
+                }
+                if (idle) kind = -1;
+                if (kind >= 0) Rm += kind * p.r_kind_stride;
+                if (kind >= UKFB_EVENT_POSE_ACCELERATION) store = kind, kind = -1;
+            }
             if (F::KIND == 1 && p.imu) { /* integrateMeasurement(RotationRate / Acceleration): check, store */
                 const double* s6 = p.imu + tick * p.imu_kstride + b * 6;
                 const double g0 = s6[0], g1 = s6[1], g2 = s6[2], a0 = s6[3], a1 = s6[4], a2 = s6[5];
@@ -469,7 +484,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
                 else
                     status |= UKFB_STATUS_NONFINITE_MEAS;
             }
-            if (p.do_predict) {
+            if (p.do_predict && !idle) {
                 double dt;
                 bool have_dt = true;
                 if (p.time_mode) {
@@ -499,15 +514,16 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
                     }
                 }
             }
-            if (p.do_update) {
-                kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
-                if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+            if (p.do_update && !idle) {
+                if (!p.events) {
+                    kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                    if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+                }
                 if (kind >= 0) {
                     bool ok = true;
                     if (F::KIND == 1) { /* checkMeasurment: OrientationUKF only (OrientationUKF.cpp:67) */
                         const int m = meas_dim(kind);
                         const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-                        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
                         for (int a = 0; a < m; ++a) ok = ok && (fabs(zm[a]) <= big);
                         for (int a = 0; a < m; ++a)
                             for (int c = 0; c < m; ++c) ok = ok && (fabs(Rm[a * p.r_ld + c]) <= big);
@@ -539,13 +555,36 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
             }
         }
 
+        /* ---- storing events: the sample is kept for the next predict (after this slot's own predict) ----------------- */
+        if (store >= 0) {
+            const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
+            if (F::KIND == 0) { /* PoseUKF.cpp:175-178: no finite check (NaN mu = "no acceleration") */
+                UKFB_UNROLL
+                for (int r = 0; r < 3; ++r) {
+                    ma.acc[r] = zm[r];
+                    UKFB_UNROLL
+                    for (int c = 0; c < 3; ++c) p.acc_cov[b * 9 + r * 3 + c] = Rm[r * p.r_ld + c];
+                }
+            } else { /* OrientationUKF.cpp:53-63: checkMeasurment(mu, cov), then store */
+                bool ok = true;
+                for (int a = 0; a < 3; ++a) ok = ok && (fabs(zm[a]) <= big);
+                for (int a = 0; a < 3; ++a)
+                    for (int c = 0; c < 3; ++c) ok = ok && (fabs(Rm[a * p.r_ld + c]) <= big);
+                if (!ok)
+                    status |= UKFB_STATUS_NONFINITE_MEAS;
+                else if (store == UKFB_EVENT_ORI_ROTATION_RATE)
+                    ma.omega[0] = zm[0], ma.omega[1] = zm[1], ma.omega[2] = zm[2];
+                else
+                    ma.acc[0] = zm[0], ma.acc[1] = zm[1], ma.acc[2] = zm[2];
+            }
+        }
+
         /* ---- update (ukfom update + apply_delta, App. A.4) --------------------------------------------------- */
         if (do_upd) {
             if (!cholesky_thread<F>(sig, sm, lane)) {
                 status |= UKFB_STATUS_NOT_SPD;
             } else {
-                status |= update_first_half<F>(sm, lane, sig, kind, p.z + tick * p.z_kstride + b * p.z_stride,
-                                               p.R + tick * p.r_kstride + b * p.r_stride, p.r_ld);
+                status |= update_first_half<F>(sm, lane, sig, kind, p.z + tick * p.z_kstride + b * p.z_stride, Rm, p.r_ld);
                 /* the reference has already replaced sigma by sigma - K S K^T when MTK's assert fires inside
                  * apply_delta: on failure that matrix stays in the record, mu is left alone */
                 if (!cholesky_thread<F>(sig, sm, lane)) {
@@ -570,11 +609,11 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
         UKFB_UNROLL
         for (int i = 0; i < F::MU; ++i) rec[i * TILE] = UKFB_TS(TS::OFF_MU + i);
     }
-    if (valid && F::KIND == 1 && p.imu) {
+    if (valid && ((F::KIND == 1 && p.imu) || p.events)) {
         UKFB_UNROLL
         for (int i = 0; i < 3; ++i) {
             p.acc_mu[b * 3 + i] = ma.acc[i];
-            p.gyro_mu[b * 3 + i] = ma.omega[i];
+            if (F::KIND == 1) p.gyro_mu[b * 3 + i] = ma.omega[i];
         }
     }
     if (valid && status) p.status[b] |= status;

@@ -149,3 +149,63 @@ def orientation_velocity(B: int, step: int, first: int = 0):
     idx = np.arange(first, first + B)
     z = SIGMA_DVL * noise(idx, step, 12, 3)
     return z, np.eye(3) * SIGMA_DVL**2
+
+
+# ---- asynchronous sensor queues (C5) ---------------------------------------------------
+EVENT_IDLE = -2
+EVENT_KIND_COUNT = 13
+
+
+def sensor_cov_table():
+    """cov[kind] (13,3,3): one covariance per sensor kind, leading m x m block used (identity elsewhere)."""
+    tab = np.tile(np.eye(3), (EVENT_KIND_COUNT, 1, 1))
+    for kind, sig in ((8, SIGMA_GYRO), (4, SIGMA_DVL), (5, SIGMA_DVL), (6, SIGMA_DVL), (7, SIGMA_DVL), (0, SIGMA_GPS),
+                      (1, SIGMA_GPS), (2, SIGMA_GPS), (3, 1e-2), (9, SIGMA_DVL), (10, SIGMA_ACC), (11, SIGMA_GYRO),
+                      (12, SIGMA_ACC)):
+        tab[kind] = np.eye(3) * sig * sig
+    return tab
+
+
+def pack_events(ts_c, kinds_c, mu_c, valid):
+    """Per-filter queues from candidate samples: ts_c, kinds_c, valid: (C, B) in per-filter time order; mu_c: (C, B, 3).
+    Returns slot-major (K, B) arrays, K = the longest queue, shorter queues padded with EVENT_IDLE."""
+    C_, B = valid.shape
+    pos = np.cumsum(valid, axis=0) - 1
+    K = int(pos[-1].max()) + 1 if C_ else 0
+    ts = np.zeros((K, B), np.int64)
+    kinds = np.full((K, B), EVENT_IDLE, np.int8)
+    mu3 = np.zeros((K, B, 3))
+    c, b = np.nonzero(valid)
+    k = pos[c, b]
+    ts[k, b] = ts_c[c, b]
+    kinds[k, b] = kinds_c[c, b]
+    mu3[k, b] = mu_c[c, b]
+    return ts, kinds, mu3
+
+
+def pose_c5_events(B: int, tick0: int, n_ticks: int, first: int = 0, dvl_period: int = 100, gps_period: int = 1000):
+    """C5 (BASELINE.json config 5): per-filter queues of asynchronous samples over ticks tick0 .. tick0+n_ticks-1.
+    IMU 1 kHz -> AngularVelocityMeasurement (kind 8) at t_k; DVL 10 Hz with a per-filter phase -> VelocityMeasurement
+    (kind 4) at t_k + 300 us; GPS 1 Hz with a per-filter phase -> XYMeasurement (kind 1, nav-plane coordinates as
+    GeographicProjection::worldToNav produces them) at t_k + 600 us.  Returns ts, kinds (K,B), mu3 (K,B,3)."""
+    idx = np.arange(first, first + B)
+    ph_dvl = (_splitmix64(idx.astype(np.uint64) * np.uint64(3) + np.uint64(SEED)) % np.uint64(dvl_period)).astype(np.int64)
+    ph_gps = (_splitmix64(idx.astype(np.uint64) * np.uint64(5) + np.uint64(SEED)) % np.uint64(gps_period)).astype(np.int64)
+    ts_c = np.zeros((n_ticks * 3, B), np.int64)
+    kinds_c = np.zeros((n_ticks * 3, B), np.int8)
+    valid = np.zeros((n_ticks * 3, B), bool)
+    mu_c = np.zeros((n_ticks * 3, B, 3))
+    for j in range(n_ticks):
+        k = tick0 + j
+        t = T0_US + 1000 * k
+        ts_c[3 * j], kinds_c[3 * j], valid[3 * j] = t, 8, True
+        mu_c[3 * j] = pose_measurement(8, B, k, first=first)[0]
+        has_dvl = (k + ph_dvl) % dvl_period == 0
+        ts_c[3 * j + 1], kinds_c[3 * j + 1], valid[3 * j + 1] = t + 300, 4, has_dvl
+        if has_dvl.any():
+            mu_c[3 * j + 1] = pose_measurement(4, B, k, first=first)[0]
+        has_gps = (k + ph_gps) % gps_period == 0
+        ts_c[3 * j + 2], kinds_c[3 * j + 2], valid[3 * j + 2] = t + 600, 1, has_gps
+        if has_gps.any():
+            mu_c[3 * j + 2, :, :2] = pose_measurement(1, B, k, first=first)[0]
+    return pack_events(ts_c, kinds_c, mu_c, valid)

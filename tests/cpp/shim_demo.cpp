@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <limits>
 
+#include <pose_estimation_b200/EventQueue.hpp>
 #include <pose_estimation_b200/OrientationUKF.hpp>
 #include <pose_estimation_b200/PoseUKF.hpp>
 
@@ -133,6 +134,43 @@ int main()
     double rate[3];
     ori.getRotationRate(rate);
     printf("ori_rate %.17g %.17g %.17g\n", rate[0], rate[1], rate[2]);
+    // ---- EventQueue: three PoseUKF filters with queues of different depth, one launch -------------------
+    {
+        const int B = 3;
+        PoseUKF::State xs[B] = {x0, x0, x0};
+        PoseUKF::Covariance ps[B] = {p0, p0, p0};
+        PoseUKF batch(B, xs, ps);
+        EventQueue q(batch.handle());
+        for (int b = 0; b < B; ++b) {
+            for (int k = 0; k < 5; ++k) {
+                PoseUKF::AngularVelocityMeasurement w;
+                w.mu[2] = 0.05 + 0.001 * b;
+                for (int i = 0; i < 3; ++i) w.cov[i * 3 + i] = 1e-6;
+                q.push(b, 1000000 + 1000 * k + 100 * b, UKFB_MEAS_POSE_ANGULAR_VELOCITY, w);
+                if (k == 2 && b >= 1) {
+                    PoseUKF::VelocityMeasurement v;
+                    v.mu[0] = 1.0 + 0.01 * b;
+                    for (int i = 0; i < 3; ++i) v.cov[i * 3 + i] = 1e-4;
+                    q.push(b, 1002500, UKFB_MEAS_POSE_VELOCITY, v);
+                }
+                if (k == 3 && b == 2) {
+                    PoseUKF::AccelerationMeasurement a;
+                    a.mu[0] = 0.2;
+                    for (int i = 0; i < 3; ++i) a.cov[i * 3 + i] = 1e-4;
+                    q.push(b, 1003500, UKFB_EVENT_POSE_ACCELERATION, a);
+                }
+            }
+        }
+        printf("evq_depth %zu\n", q.depth());
+        q.flush();
+        PoseUKF::State es[B];
+        PoseUKF::Covariance ec[B];
+        if (!batch.getCurrentState(es, ec)) return 4;
+        for (int b = 0; b < B; ++b) {
+            print_state("evq_mu", es[b], 13);
+            print_state("evq_sigma", ec[b], 144);
+        }
+    }
     printf("caught_total %d\n", caught);
     return caught == 3 ? 0 : 1;
 }

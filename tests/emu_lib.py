@@ -30,6 +30,7 @@ class StepParams(C.Structure):
         ("K", C.c_int), ("dt_kstride", C.c_longlong), ("ts_kstride", C.c_longlong), ("z_kstride", C.c_longlong),
         ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
+        ("events", C.c_int), ("r_kind_stride", C.c_longlong),
     ]
 
 
@@ -198,6 +199,19 @@ class EmuBatch:
         dt = np.ascontiguousarray(np.atleast_1d(np.asarray(dt, float)))
         a = self._upd_args(kind, mu, cov, mask)
         self._launch(do_predict=1, time_mode=0, dt=dt, dt_stride=1 if dt.size == self.B else 0, **a)
+
+    def run_events(self, ts, kinds, mu3, cov):
+        """same arguments as UkfBatch.run_events (lane-per-filter kernels only)"""
+        assert self.tiled
+        ts = np.ascontiguousarray(np.asarray(ts, np.int64))
+        K, B = ts.size // self.B, self.B
+        cov = np.ascontiguousarray(np.asarray(cov, float))
+        per_event = cov.size == K * B * 9 and cov.ndim != 3
+        self._launch(K=K, events=1, do_predict=1, time_mode=1, ts=ts, ts_stride=1, ts_kstride=B, do_update=1, kind=-2,
+                     kinds=np.ascontiguousarray(np.asarray(kinds, np.int8)), kinds_kstride=B,
+                     z=np.ascontiguousarray(np.asarray(mu3, float)), z_stride=3, z_kstride=3 * B, R=cov, r_ld=3,
+                     r_stride=9 if per_event else 0, r_kstride=9 * B if per_event else 0,
+                     r_kind_stride=0 if per_event else 9)
 
     def fallbacks(self):
         """(literal predict, literal update, literal apply_delta) calls made so far by the fast kernel's lanes"""

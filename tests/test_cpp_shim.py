@@ -72,14 +72,46 @@ def _oracle_replay():
     return pose, q.get_state(), q.get_rotation_rate()
 
 
+def _oracle_event_queue():
+    """the samples shim_demo.cpp pushes into its EventQueue, as slot-major arrays"""
+    B = 3
+    queues = [[] for _ in range(B)]
+    for b in range(B):
+        for k in range(5):
+            queues[b].append((1000000 + 1000 * k + 100 * b, 8, [0, 0, 0.05 + 0.001 * b], np.eye(3) * 1e-6))
+            if k == 2 and b >= 1:
+                queues[b].append((1002500, 4, [1.0 + 0.01 * b, 0, 0], np.eye(3) * 1e-4))
+            if k == 3 and b == 2:
+                queues[b].append((1003500, 10, [0.2, 0, 0], np.eye(3) * 1e-4))
+    K = max(len(q) for q in queues)
+    ts, kinds = np.zeros((K, B), np.int64), np.full((K, B), -2, np.int8)
+    mu3, cov = np.zeros((K, B, 3)), np.zeros((K, B, 9))
+    for b, q in enumerate(queues):
+        for k, (t, kind, mu, c) in enumerate(q):
+            ts[k, b], kinds[k, b], mu3[k, b], cov[k, b] = t, kind, mu, c.ravel()
+    mu0 = np.zeros((B, 13))
+    mu0[:, 6], mu0[:, 7], mu0[:, 12] = 1.0, 1.0, 0.05
+    sg0 = np.tile(np.diag([1, 1, 1, 0.01, 0.01, 0.01, 0.1, 0.1, 0.1, 0.01, 0.01, 0.01]), (B, 1, 1))
+    o = OracleBatch(0, B)
+    o.initialize(mu0, sg0)
+    o.run_events(ts, kinds, mu3, cov)
+    return K, o.get_state()
+
+
 @pytest.mark.gpu
 def test_shim_matches_oracle_and_throws_like_the_reference(demo):
     r = subprocess.run([demo], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    vals, caught = {}, []
+    vals, caught, evq_mu, evq_sigma = {}, [], [], []
     for line in r.stdout.splitlines():
         tag, *rest = line.split()
-        if tag == "caught:":
+        if tag == "evq_mu":
+            evq_mu.append([float(x) for x in rest])
+        elif tag == "evq_sigma":
+            evq_sigma.append([float(x) for x in rest])
+        elif tag == "evq_depth":
+            evq_depth = int(rest[0])
+        elif tag == "caught:":
             caught.append(" ".join(rest))
         elif tag in ("pose_mu", "pose_sigma", "ori_mu", "ori_sigma", "ori_rate"):
             vals[tag] = np.array([float(x) for x in rest])
@@ -91,3 +123,6 @@ def test_shim_matches_oracle_and_throws_like_the_reference(demo):
     P.assert_parity(0, (vals["pose_mu"][None], vals["pose_sigma"].reshape(1, 12, 12)), pose, what="C++ shim PoseUKF")
     P.assert_parity(1, (vals["ori_mu"][None], vals["ori_sigma"].reshape(1, 13, 13)), ori, what="C++ shim OrientationUKF")
     assert np.abs(vals["ori_rate"] - rate[0]).max() < 1e-12
+    K, ref = _oracle_event_queue()
+    assert evq_depth == K == 7
+    P.assert_parity(0, (np.array(evq_mu), np.array(evq_sigma).reshape(3, 12, 12)), ref, what="C++ EventQueue")

@@ -1,0 +1,162 @@
+"""Event streams (ukfb_run_events): per-filter queues of asynchronous sensor samples, each integrated as the reference's
+aggregator callbacks do -- predictionStepFromSampleTime(ts) then integrateMeasurement(sample)
+(UnscentedKalmanFilter.hpp:83-100, PoseUKF.cpp:112-178, OrientationUKF.cpp:53-72).  The oracle runs that loop filter by
+filter; the kernels run all K slots in one launch.  CPU: the kernels' source under tests/simt_emu; GPU: the C ABI."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import parity as P
+from oracle.oracle_lib import OracleBatch
+from slam_pose_estimation_b200 import synthetic as syn
+
+IDLE = syn.EVENT_IDLE
+
+
+def c5(B, n_ticks, first=0):
+    ts, kinds, mu3 = syn.pose_c5_events(B, 1, n_ticks, first=first, dvl_period=7, gps_period=11)
+    return ts, kinds, mu3, syn.sensor_cov_table()
+
+
+def test_pack_events_keeps_per_filter_time_order():
+    ts, kinds, mu3, _ = c5(37, 25)
+    assert (kinds == 8).sum() == 37 * 25 and (kinds == 4).sum() > 0 and (kinds == 1).sum() > 0
+    assert (kinds == IDLE).any()  # ragged queues
+    for b in range(37):
+        live = kinds[:, b] != IDLE
+        assert (np.diff(ts[live, b]) > 0).all()
+        assert not live[np.argmin(live):].any() or live.all()  # padding only at the tail
+
+
+def pose_edge_events(B):
+    """hand-made queues: acceleration samples (finite and the NaN sentinel), a negative time step, a too large one, a
+    repeated timestamp (dt <= min_dt: update without predict), an orientation measurement, predict-only slots."""
+    K = 12
+    ts = np.zeros((K, B), np.int64)
+    kinds = np.full((K, B), IDLE, np.int8)
+    mu3 = np.zeros((K, B, 3))
+    cov = np.zeros((K, B, 3, 3))
+    t = np.full(B, syn.T0_US, np.int64)
+    plan = [(8, 1000), (10, 500), (4, 1500), (-1, 2000), (0, 0), (3, 1000), (10, 700), (8, -4000), (1, 9000), (7, 3_000_000),
+            (2, 1000), (6, 1000)]
+    for k, (kind, step_us) in enumerate(plan):
+        act = (np.arange(B) + k) % 4 != 3  # every filter sits out some slots
+        t = np.where(act, t + step_us, t)
+        ts[k], kinds[k] = t, np.where(act, kind, IDLE)
+        if kind == 10:
+            mu3[k] = 0.05 * syn.noise(np.arange(B), k, 13, 3)
+            if k == 6:
+                mu3[k, ::2] = np.nan  # back to "no acceleration" for every other filter
+            cov[k] = np.eye(3) * 1e-4
+        elif kind >= 0:
+            m = {1: 2, 7: 2, 2: 1, 6: 1}.get(kind, 3)
+            z, R = syn.pose_measurement(kind, B, k + 1)
+            mu3[k, :, :m] = z
+            cov[k, :, :m, :m] = R
+    return ts, kinds, mu3, cov.reshape(K, B, 9)
+
+
+def check_pose(cls, kw, tol):
+    B = 37
+    ts, kinds, mu3, tab = c5(B, 25)
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(cls, B, **kw)
+    for x in (o, e):
+        x.run_events(ts[:40], kinds[:40], mu3[:40], tab)
+        x.run_events(ts[40:], kinds[40:], mu3[40:], tab)  # queues continue across calls
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=tol, what="C5 queues")
+    assert np.array_equal(e.get_last_time(), o.get_last_time()) if hasattr(e, "get_last_time") else True
+    assert not e.get_status().any() and not o.get_status().any()
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+    ts, kinds, mu3, cov = pose_edge_events(B)
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(cls, B, **kw)
+    for x in (o, e):
+        x.set_time_bounds(1e-9, 2.0)
+        x.run_events(ts, kinds, mu3, cov)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=max(tol, 1e-10), what="edge queues")
+    st = o.get_status()
+    assert (st & 1).any() and (st & 2).any()  # the negative and the too large step were seen
+    assert np.array_equal(e.get_status(), st)
+
+
+def check_ori(cls, kw, tol):
+    B = 33
+    K = 30
+    ts = np.zeros((K, B), np.int64)
+    kinds = np.full((K, B), IDLE, np.int8)
+    mu3 = np.zeros((K, B, 3))
+    t = np.full(B, syn.T0_US, np.int64)
+    for k in range(K):
+        tick = k // 3 + 1
+        gyro, acc = syn.orientation_imu(B, tick)
+        act = (np.arange(B) + k) % 5 != 4
+        if k % 3 == 0:
+            kind, z, step = 11, gyro, 400
+        elif k % 3 == 1:
+            kind, z, step = 12, acc, 0
+        else:
+            kind, z, step = (9, syn.orientation_velocity(B, tick)[0], 600) if tick % 2 == 0 else (-1, np.zeros((B, 3)), 600)
+        t = np.where(act, t + step, t)
+        ts[k], kinds[k], mu3[k] = t, np.where(act, kind, IDLE), z
+    mu3[7, 3] = np.inf      # a non-finite acceleration sample: rejected, the old one stays
+    mu3[17, 5, 1] = np.nan  # a non-finite velocity measurement: rejected
+    kinds[4, 2] = 8         # a PoseUKF kind in an OrientationUKF queue
+    tab = syn.sensor_cov_table()
+    o, e = P.make_ori(OracleBatch, B), P.make_ori(cls, B, **kw)
+    for x in (o, e):
+        x.run_events(ts, kinds, mu3, tab)
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=tol, what="orientation queues")
+    st = o.get_status()
+    assert st[3] & 4 and st[5] & 4 and st[2] & 32
+    assert np.array_equal(e.get_status(), st)
+    # the stored IMU samples survive the launch: one more predict-only slot uses them
+    ts2 = (ts.max(axis=0) + 1000)[None]
+    for x in (o, e):
+        x.run_events(ts2, np.full((1, B), -1, np.int8), np.zeros((1, B, 3)), tab)
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=tol, what="orientation queues, next launch")
+
+
+@pytest.mark.parametrize("kernel", ["thread", "fast"])
+def test_emu_pose_event_queues(kernel):
+    from emu_lib import EmuBatch
+    check_pose(EmuBatch, dict(kernel=kernel), 1e-12)
+
+
+def test_emu_orientation_event_queues():
+    from emu_lib import EmuBatch
+    check_ori(EmuBatch, dict(kernel="thread"), 1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_pose_event_queues():
+    from slam_pose_estimation_b200 import UkfBatch
+    check_pose(UkfBatch, {}, P.TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_orientation_event_queues():
+    from slam_pose_estimation_b200 import UkfBatch
+    check_ori(UkfBatch, {}, P.TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_event_queue_equals_single_calls():
+    """one launch over K slots == K x (ukfb_predict_time + ukfb_update_mixed) through the single calls"""
+    from slam_pose_estimation_b200 import UkfBatch
+    B = 70
+    ts, kinds, mu3, tab = c5(B, 12)
+    a, b = P.make_pose(UkfBatch, B), P.make_pose(UkfBatch, B)
+    a.run_events(ts, kinds, mu3, tab)
+    for k in range(ts.shape[0]):
+        live = kinds[k] != IDLE
+        # idle filters: repeat their last timestamp (dt = 0 is a no-op and leaves the latch alone)
+        tk = np.where(live, ts[k], np.maximum(b.get_last_time(), 1))
+        if k == 0:
+            assert live.all()
+        b.predict_time(tk)
+        cov = tab[np.maximum(kinds[k], 0)]
+        b.update_mixed(np.where(live, kinds[k], -1).astype(np.int8), mu3[k], cov)
+    ma, sa = a.get_state()
+    mb, sb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(sa, sb)
