@@ -117,6 +117,22 @@ int ukfb_is_initialized(const ukfb_handle* h);
 int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma);
 int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma);
 
+/* BodyStateMeasurement (pose_with_velocity/BodyStateMeasurement.hpp:12-41), the format the reference's callers
+ * exchange PoseUKF states in, for every filter of a POSE handle.  One base::samples::RigidBodyState is passed as
+ * UKFB_RBS_DOUBLES doubles:
+ *     position[3] orientation[4: x,y,z,w] velocity[3] angular_velocity[3]
+ *     cov_position[9] cov_orientation[9] cov_velocity[9] cov_angular_velocity[9]        (3 x 3 blocks)
+ * ukfb_initialize_from_body_states = fromRigidBodyState (:14-26) + initializeFilter: the four vectors are taken as
+ * they are (the velocity is NOT rotated into the body frame, as in the reference), the covariance is the four
+ * blocks on the diagonal and zero elsewhere.
+ * ukfb_get_body_states = getCurrentState + toRigidBodyState (:28-39): velocity = orientation * body velocity (rotated
+ * into the navigation frame), all else copied; the covariance blocks are NOT rotated. */
+#define UKFB_RBS_DOUBLES 49
+int ukfb_initialize_from_body_states(ukfb_handle* h, const double* rbs);
+int ukfb_initialize_from_body_states_dev(ukfb_handle* h, const double* d_rbs);
+int ukfb_get_body_states(ukfb_handle* h, double* rbs);
+int ukfb_get_body_states_dev(ukfb_handle* h, double* d_rbs);
+
 /* set/getProcessNoiseCovariance (:129-130).  per_filter = 0: Q is n x n and is
  * broadcast; 1: B x n x n.  The lower triangle is used. */
 int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_filter);

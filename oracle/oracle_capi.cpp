@@ -388,6 +388,36 @@ int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const
     return 0;
 }
 
+/* BodyStateMeasurement::fromRigidBodyState (BodyStateMeasurement.hpp:14-26): rbs B x 49 -> mu B x 13, sigma B x 12 x 12 */
+void orc_from_body_states(const double* rbs, int64_t B, double* mu, double* sigma)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        const double* r = rbs + i * 49;
+        for (int k = 0; k < 13; ++k) mu[i * 13 + k] = r[k]; /* position, orientation, velocity, angular_velocity */
+        double* s = sigma + i * 144;
+        for (int k = 0; k < 144; ++k) s[k] = 0.0; /* setZero() */
+        for (int blk = 0; blk < 4; ++blk)
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c) s[(blk * 3 + a) * 12 + blk * 3 + c] = r[13 + blk * 9 + a * 3 + c];
+    }
+}
+
+/* BodyStateMeasurement::toRigidBodyState (BodyStateMeasurement.hpp:28-39) */
+void orc_to_body_states(const double* mu, const double* sigma, int64_t B, double* rbs)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        double* r = rbs + i * 49;
+        const double* m = mu + i * 13;
+        for (int k = 0; k < 13; ++k) r[k] = m[k];
+        const Quat<double> q = {m[3], m[4], m[5], m[6]};
+        quat_rotate(q, m + 7, r + 7); /* body_state.velocity = body_state.orientation * filter_state.velocity */
+        const double* s = sigma + i * 144;
+        for (int blk = 0; blk < 4; ++blk)
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c) r[13 + blk * 9 + a * 3 + c] = s[(blk * 3 + a) * 12 + blk * 3 + c];
+    }
+}
+
 int orc_get_rotation_rate(void* h, double* out)
 {
     Batch* b = static_cast<Batch*>(h);

@@ -140,7 +140,8 @@ class OracleBatch:
         mu3, pm = _p(mu3, np.float64)
         cov, pc = _p(cov, np.float64)
         K = ts.size // self.B
-        per_event = cov.size == K * self.B * 9 and cov.ndim != 3
+        per_event = cov.shape != (13, 3, 3)  # a (13, 3, 3) array is the per-sensor table
+        assert not per_event or cov.size == K * self.B * 9
         self._chk(self.lib.orc_run_events(self.h, C.c_int(K), pt, pk, pm, pc, C.c_int(1 if per_event else 0)),
                   "orc_run_events")
 
@@ -183,3 +184,25 @@ class OracleBatch:
 
     def max_threads(self):
         return int(self.lib.orc_max_threads())
+
+
+def from_body_states(rbs):
+    """BodyStateMeasurement::fromRigidBodyState over B records (B x 49) -> mu (B,13), sigma (B,12,12)"""
+    lib = load()
+    rbs = np.ascontiguousarray(rbs, np.float64).reshape(-1, 49)
+    B = rbs.shape[0]
+    mu, sg = np.empty((B, 13)), np.empty((B, 12, 12))
+    lib.orc_from_body_states(rbs.ctypes.data_as(C.c_void_p), C.c_int64(B), mu.ctypes.data_as(C.c_void_p),
+                             sg.ctypes.data_as(C.c_void_p))
+    return mu, sg
+
+
+def to_body_states(mu, sigma):
+    """BodyStateMeasurement::toRigidBodyState over B filters -> B x 49"""
+    lib = load()
+    mu = np.ascontiguousarray(mu, np.float64).reshape(-1, 13)
+    sigma = np.ascontiguousarray(sigma, np.float64).reshape(-1, 12, 12)
+    out = np.empty((mu.shape[0], 49))
+    lib.orc_to_body_states(mu.ctypes.data_as(C.c_void_p), sigma.ctypes.data_as(C.c_void_p), C.c_int64(mu.shape[0]),
+                           out.ctypes.data_as(C.c_void_p))
+    return out

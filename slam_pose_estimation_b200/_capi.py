@@ -26,6 +26,10 @@ SIGNATURES = {
     "ukfb_is_initialized": (I, [P]),
     "ukfb_get_state": (I, [P, P, P]),
     "ukfb_get_state_dev": (I, [P, P, P]),
+    "ukfb_initialize_from_body_states": (I, [P, P]),
+    "ukfb_initialize_from_body_states_dev": (I, [P, P]),
+    "ukfb_get_body_states": (I, [P, P]),
+    "ukfb_get_body_states_dev": (I, [P, P]),
     "ukfb_set_process_noise": (I, [P, P, I]),
     "ukfb_get_process_noise": (I, [P, P, I]),
     "ukfb_set_time_bounds": (I, [P, D, D]),

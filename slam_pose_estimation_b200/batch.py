@@ -27,6 +27,8 @@ EVENT_IDLE, EVENT_POSE_ACCELERATION, EVENT_ORI_ROTATION_RATE, EVENT_ORI_ACCELERA
 STATUS_NEG_DT, STATUS_DT_TOO_LARGE, STATUS_NONFINITE_MEAS, STATUS_NOT_SPD, STATUS_MEAN_NO_CONVERGE = 1, 2, 4, 8, 16
 STATUS_BAD_EVENT = 32
 
+RBS_DOUBLES = 49
+
 ERR_INVALID, ERR_NOT_INITIALIZED, ERR_CUDA, ERR_NOMEM = -1, -2, -3, -4
 
 
@@ -105,6 +107,18 @@ class UkfBatch:
 
     def get_state_dev(self, d_mu, d_sigma=None):
         self._chk(self.lib.ukfb_get_state_dev(self.h, _dev(d_mu), _dev(d_sigma)))
+
+    def initialize_from_body_states(self, rbs):
+        """BodyStateMeasurement::fromRigidBodyState + initializeFilter; rbs: B x 49 (include/ukf_batch.h)"""
+        rbs, pr = _host(rbs, np.float64)
+        assert rbs.size == self.B * RBS_DOUBLES
+        self._chk(self.lib.ukfb_initialize_from_body_states(self.h, pr))
+
+    def get_body_states(self):
+        """getCurrentState + BodyStateMeasurement::toRigidBodyState; B x 49"""
+        out = np.empty((self.B, RBS_DOUBLES))
+        self._chk(self.lib.ukfb_get_body_states(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def set_process_noise(self, Q):
         Q, pq = _host(Q, np.float64)
@@ -255,9 +269,8 @@ class UkfBatch:
         cov, pc = _host(cov, np.float64)
         K = ts.shape[0] if ts.ndim == 2 else ts.size // self.B
         assert ts.size == K * self.B and kinds.size == K * self.B and mu3.size == K * self.B * 3
-        per_event = cov.size == K * self.B * 9 and cov.ndim != 3
-        if not per_event:
-            assert cov.size == EVENT_KIND_COUNT * 9
+        per_event = cov.shape != (13, 3, 3)  # a (13, 3, 3) array is the per-sensor table
+        assert not per_event or cov.size == K * self.B * 9
         self._chk(self.lib.ukfb_run_events(self.h, K, pt, pk, pm, pc, 1 if per_event else 0))
 
     def run_events_dev(self, K: int, d_ts, d_kinds, d_mu3, d_cov, per_event: bool):

@@ -176,6 +176,58 @@ __global__ void unpack_sigma_kernel(const double* __restrict__ state, double* __
     }
 }
 
+/* BodyStateMeasurement::fromRigidBodyState (BodyStateMeasurement.hpp:14-26): RigidBodyState records -> PoseUKF records */
+__global__ void pack_rbs_kernel(double* __restrict__ state, const double* __restrict__ rbs, long long B, int tiled)
+{
+    const long long total = B * PoseF::REC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / PoseF::REC;
+        const int k = int(i - b * PoseF::REC);
+        const double* r = rbs + b * UKFB_RBS_DOUBLES;
+        double v = 0.0;
+        if (k < PoseF::MU)
+            v = r[k]; /* position, orientation, velocity, angular velocity: the same order as mu */
+        else {
+            const int e = k - PoseF::MU;
+            int row = 0;
+            while ((row + 1) * (row + 2) / 2 <= e) ++row;
+            const int col = e - row * (row + 1) / 2;
+            if (row / 3 == col / 3) v = r[13 + (row / 3) * 9 + (row % 3) * 3 + (col % 3)];
+        }
+        state[rec_index(tiled, b, k, PoseF::REC)] = v;
+    }
+}
+
+/* BodyStateMeasurement::toRigidBodyState (BodyStateMeasurement.hpp:28-39) */
+__global__ void unpack_rbs_kernel(const double* __restrict__ state, double* __restrict__ rbs, long long B, int tiled)
+{
+    const long long total = B * UKFB_RBS_DOUBLES;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / UKFB_RBS_DOUBLES;
+        const int k = int(i - b * UKFB_RBS_DOUBLES);
+        double v;
+        if (k >= 7 && k < 10) { /* velocity: rotated into the navigation frame (:32) */
+            double q[4], bv[3], nv[3];
+            for (int j = 0; j < 4; ++j) q[j] = state[rec_index(tiled, b, 3 + j, PoseF::REC)];
+            for (int j = 0; j < 3; ++j) bv[j] = state[rec_index(tiled, b, 7 + j, PoseF::REC)];
+            quat_rotate(q, bv, nv);
+            v = nv[k - 7];
+        } else if (k < PoseF::MU)
+            v = state[rec_index(tiled, b, k, PoseF::REC)];
+        else {
+            const int blk = (k - 13) / 9, e = (k - 13) % 9;
+            int row = blk * 3 + e / 3, col = blk * 3 + e % 3;
+            if (col > row) {
+                const int t = row;
+                row = col;
+                col = t;
+            }
+            v = state[rec_index(tiled, b, PoseF::MU + tri(row, col), PoseF::REC)];
+        }
+        rbs[i] = v;
+    }
+}
+
 /* packed lower triangle of Q from full n x n matrices */
 __global__ void pack_q_kernel(double* __restrict__ Qp, const double* __restrict__ Q, long long count, int n, int LP)
 {
@@ -563,6 +615,59 @@ extern "C" int ukfb_initialize(ukfb_handle* h, const double* mu, const double* s
     CU(cudaMemcpyAsync(d_sigma, sigma, bs, cudaMemcpyHostToDevice, h->stream));
     rc = initialize_dev(h, d_mu, d_sigma);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_initialize_from_body_states_dev(ukfb_handle* h, const double* d_rbs)
+{
+    CHECK_H(h);
+    if (h->kind != UKFB_POSE) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: BodyStateMeasurement belongs to PoseUKF");
+    if (!d_rbs) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: null argument");
+    pack_rbs_kernel<<<grid_for(h->B * h->REC), 256, 0, h->stream>>>(h->state, d_rbs, h->B, h->tiled);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * h->B, h->stream)); /* initializeFilter, :43 */
+    h->first_init = false;
+    h->initialized = true;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_initialize_from_body_states(ukfb_handle* h, const double* rbs)
+{
+    CHECK_H(h);
+    if (!rbs) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: null argument");
+    const size_t bytes = sizeof(double) * h->B * UKFB_RBS_DOUBLES;
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, rbs, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = ukfb_initialize_from_body_states_dev(h, reinterpret_cast<const double*>(h->stage));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_body_states_dev(ukfb_handle* h, double* d_rbs)
+{
+    CHECK_H(h);
+    if (h->kind != UKFB_POSE) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: BodyStateMeasurement belongs to PoseUKF");
+    NEED_INIT(h);
+    if (!d_rbs) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: null argument");
+    unpack_rbs_kernel<<<grid_for(h->B * UKFB_RBS_DOUBLES), 256, 0, h->stream>>>(h->state, d_rbs, h->B, h->tiled);
+    CU(cudaGetLastError());
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_body_states(ukfb_handle* h, double* rbs)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (!rbs) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: null argument");
+    const size_t bytes = sizeof(double) * h->B * UKFB_RBS_DOUBLES;
+    int rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    rc = ukfb_get_body_states_dev(h, reinterpret_cast<double*>(h->stage));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rbs, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
 }

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <limits>
 
+#include <pose_estimation_b200/BodyStateMeasurement.hpp>
 #include <pose_estimation_b200/EventQueue.hpp>
 #include <pose_estimation_b200/OrientationUKF.hpp>
 #include <pose_estimation_b200/PoseUKF.hpp>
@@ -170,6 +171,25 @@ int main()
             print_state("evq_mu", es[b], 13);
             print_state("evq_sigma", ec[b], 144);
         }
+    }
+    // ---- BodyStateMeasurement: a RigidBodyState in, one predict, a RigidBodyState out ---------------------
+    {
+        RigidBodyState rbs = {};
+        rbs.position[0] = 1.0, rbs.position[1] = 2.0, rbs.position[2] = -3.0;
+        rbs.orientation[2] = std::sin(0.3), rbs.orientation[3] = std::cos(0.3);
+        rbs.velocity[0] = 0.5, rbs.velocity[1] = 0.1;
+        rbs.angular_velocity[2] = 0.02;
+        for (int i = 0; i < 3; ++i)
+            rbs.cov_position[i * 4] = 0.5, rbs.cov_orientation[i * 4] = 0.01, rbs.cov_velocity[i * 4] = 0.1, rbs.cov_angular_velocity[i * 4] = 0.01;
+        rbs.cov_position[1] = rbs.cov_position[3] = 0.05;
+        PoseUKF f(x0, p0);
+        BodyStateMeasurement::fromRigidBodyState(&rbs, f);
+        f.predictionStep(0.05);
+        RigidBodyState out;
+        if (!BodyStateMeasurement::toRigidBodyState(f, &out)) return 5;
+        printf("rbs");
+        for (int i = 0; i < UKFB_RBS_DOUBLES; ++i) printf(" %.17g", out.position[i]);
+        printf("\n");
     }
     printf("caught_total %d\n", caught);
     return caught == 3 ? 0 : 1;

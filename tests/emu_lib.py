@@ -206,7 +206,8 @@ class EmuBatch:
         ts = np.ascontiguousarray(np.asarray(ts, np.int64))
         K, B = ts.size // self.B, self.B
         cov = np.ascontiguousarray(np.asarray(cov, float))
-        per_event = cov.size == K * B * 9 and cov.ndim != 3
+        per_event = cov.shape != (13, 3, 3)
+        assert not per_event or cov.size == K * B * 9
         self._launch(K=K, events=1, do_predict=1, time_mode=1, ts=ts, ts_stride=1, ts_kstride=B, do_update=1, kind=-2,
                      kinds=np.ascontiguousarray(np.asarray(kinds, np.int8)), kinds_kstride=B,
                      z=np.ascontiguousarray(np.asarray(mu3, float)), z_stride=3, z_kstride=3 * B, R=cov, r_ld=3,

@@ -109,6 +109,8 @@ def test_shim_matches_oracle_and_throws_like_the_reference(demo):
             evq_mu.append([float(x) for x in rest])
         elif tag == "evq_sigma":
             evq_sigma.append([float(x) for x in rest])
+        elif tag == "rbs":
+            rbs_out = np.array([float(x) for x in rest])
         elif tag == "evq_depth":
             evq_depth = int(rest[0])
         elif tag == "caught:":
@@ -123,6 +125,17 @@ def test_shim_matches_oracle_and_throws_like_the_reference(demo):
     P.assert_parity(0, (vals["pose_mu"][None], vals["pose_sigma"].reshape(1, 12, 12)), pose, what="C++ shim PoseUKF")
     P.assert_parity(1, (vals["ori_mu"][None], vals["ori_sigma"].reshape(1, 13, 13)), ori, what="C++ shim OrientationUKF")
     assert np.abs(vals["ori_rate"] - rate[0]).max() < 1e-12
+    rbs = np.zeros(49)
+    rbs[0:3], rbs[5:7], rbs[7:9], rbs[12] = [1.0, 2.0, -3.0], [np.sin(0.3), np.cos(0.3)], [0.5, 0.1], 0.02
+    for blk, v in enumerate((0.5, 0.01, 0.1, 0.01)):
+        rbs[13 + 9 * blk:22 + 9 * blk] = (np.eye(3) * v).ravel()
+    rbs[14] = rbs[16] = 0.05
+    from oracle import oracle_lib as O
+    o = OracleBatch(0, 1)
+    o.initialize(*O.from_body_states(rbs[None]))
+    o.predict_dt(0.05)
+    ref_rbs = O.to_body_states(*o.get_state())[0]
+    assert np.abs(rbs_out - ref_rbs).max() < 1e-12
     K, ref = _oracle_event_queue()
     assert evq_depth == K == 7
     P.assert_parity(0, (np.array(evq_mu), np.array(evq_sigma).reshape(3, 12, 12)), ref, what="C++ EventQueue")
