@@ -87,4 +87,4 @@ def test_stream_alignment_verifier(out):
     assert v[7500000] == (0, 2)        # dvl 30/30, gps 16/16
     assert v[10000000] == (1, 0)       # imu 5 % with a 1 % warning threshold
     assert out["verifier_log_lines"][0][0] == 5   # dvl failure, gps too few, dvl + gps critical, imu failure
-    assert out["config"][0] == [LAT0, 22.0]
+    assert out["config"][0] == [LAT0, 26.0]  # 2 x (3 + 3 + 3 + 1) + 3 + 3 doubles
