@@ -76,6 +76,7 @@ typedef struct ukfb_handle ukfb_handle;
 #define UKFB_STATUS_NONFINITE_MEAS 4u    /* "Measurement or covariance contains non-finite values!" :142-147 */
 #define UKFB_STATUS_NOT_SPD 8u           /* ukfom: Cholesky of sigma failed (MTK asserts)               */
 #define UKFB_STATUS_MEAN_NO_CONVERGE 16u /* ukfom: sigma_points_mean hit max_it (MTK asserts)           */
+#define UKFB_STATUS_MEAS_REJECTED 64u     /* not an error: a measurement failed the Mahalanobis gate and was not integrated */
 #define UKFB_STATUS_BAD_EVENT 32u        /* an event stream held a kind this filter class has no overload for (ignored) */
 
 /* error codes */
@@ -145,6 +146,14 @@ int ukfb_get_time_bounds(const ukfb_handle* h, double* min_dt, double* max_dt);
 /* set/getLastMeasurementTime (:131-133), int64 microseconds like base::Time. */
 int ukfb_set_last_time(ukfb_handle* h, const int64_t* ts_us, int per_filter);
 int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us);
+
+/* The `accept` functor slot of ukfom::ukf::update.  The reference always passes
+ * ukfom::accept_any_mahalanobis_distance (PoseUKF.cpp:116, OrientationUKF.cpp:69-71): that is the default here,
+ * max_d2 = +inf.  A finite max_d2 gives ukfom::accept_mahalanobis_distance(max_d2) for every later update of this
+ * handle: a measurement whose squared Mahalanobis distance innov^T S^-1 innov exceeds it is not integrated (state and
+ * covariance untouched) and the filter's UKFB_STATUS_MEAS_REJECTED bit is set.  Lane-per-filter kernels only. */
+int ukfb_set_mahalanobis_gate(ukfb_handle* h, double max_d2);
+int ukfb_get_mahalanobis_gate(const ukfb_handle* h, double* max_d2);
 
 /* OrientationUKF constructor arguments gyro_bias_tau, acc_bias_tau, location.latitude
  * (OrientationUKF.cpp:41-47): earth_rotation = (EARTHW cos lat, 0, EARTHW sin lat). */

@@ -179,6 +179,20 @@ int orc_set_time_bounds(void* h, double min_dt, double max_dt)
     return 0;
 }
 
+/* the accept functor slot of ukfom::ukf::update (PoseUKF.cpp:116 passes accept_any = +inf) */
+int orc_set_mahalanobis_gate(void* h, double max_d2)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (!b->constructed) return -2;
+    for (int64_t i = 0; i < b->B; ++i) {
+        if (b->kind == 0)
+            b->pose[i]->ukf.accept_max_d2 = max_d2;
+        else
+            b->ori[i]->ukf.accept_max_d2 = max_d2;
+    }
+    return 0;
+}
+
 int orc_set_orientation_params(void* h, double tau_g, double tau_a, double latitude)
 {
     Batch* b = static_cast<Batch*>(h);
@@ -268,9 +282,9 @@ int orc_update(void* h, int meas_kind, const double* mu, const double* cov, int 
         const double* zc = cov + (cov_per_filter ? i * m * m : 0);
         guarded(b, i, [&] {
             if (b->kind == 0)
-                b->pose[i]->integrateMeasurement(meas_kind, zm, zc);
+                { b->pose[i]->integrateMeasurement(meas_kind, zm, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
             else
-                b->ori[i]->integrateVelocity(zm, zc);
+                { b->ori[i]->integrateVelocity(zm, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
         });
     }
     return 0;
@@ -291,9 +305,9 @@ int orc_update_mixed(void* h, const int8_t* kinds, const double* mu3, const doub
             for (int c = 0; c < m; ++c) zc[a * m + c] = cov33[i * 9 + a * 3 + c];
         guarded(b, i, [&] {
             if (b->kind == 0)
-                b->pose[i]->integrateMeasurement(k, zm, zc);
+                { b->pose[i]->integrateMeasurement(k, zm, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
             else
-                b->ori[i]->integrateVelocity(zm, zc);
+                { b->ori[i]->integrateVelocity(zm, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
         });
     }
     return 0;
@@ -379,9 +393,9 @@ int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const
                 for (int c = 0; c < m; ++c) zc[a * m + c] = c33[a * 3 + c];
             guarded(b, i, [&] {
                 if (pose)
-                    b->pose[i]->integrateMeasurement(kind, z, zc);
+                    { b->pose[i]->integrateMeasurement(kind, z, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
                 else
-                    b->ori[i]->integrateVelocity(z, zc);
+                    { b->ori[i]->integrateVelocity(z, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
             });
         }
     }

@@ -96,6 +96,9 @@ class OracleBatch:
         self._chk(self.lib.orc_set_orientation_params(self.h, C.c_double(tau_g), C.c_double(tau_a),
                                                       C.c_double(latitude)), "set_orientation_params")
 
+    def set_mahalanobis_gate(self, max_d2):
+        self._chk(self.lib.orc_set_mahalanobis_gate(self.h, C.c_double(max_d2)), "set_mahalanobis_gate")
+
     def set_last_time(self, ts):
         ts = np.atleast_1d(np.asarray(ts, np.int64))
         ts, pt = _p(ts, np.int64)

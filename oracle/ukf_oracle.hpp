@@ -392,6 +392,11 @@ public:
 
     S mu;
     T sigma[n * n];
+    /* the `accept` functor slot of ukfom::ukf::update.  The reference passes accept_any_mahalanobis_distance
+     * (PoseUKF.cpp:116): accept_max_d2 = +inf.  A finite value models ukfom::accept_mahalanobis_distance(threshold):
+     * a measurement with innov^T S^-1 innov > threshold leaves the filter untouched. */
+    double accept_max_d2 = std::numeric_limits<double>::infinity();
+    bool last_update_rejected = false;
     uint32_t status = 0;
     /* histogram of sigma_points_mean trip counts (number of mean passes) */
     uint64_t mean_iters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -527,6 +532,7 @@ public:
     {
         constexpr int m = M::DOF;
         std::vector<S> X;
+        last_update_rejected = false;
         if (!generate_sigma_points(nullptr, X)) return;
         std::vector<M> Z(X.size());
         for (std::size_t p = 0; p < X.size(); ++p) Z[p] = h(X[p]);
@@ -553,7 +559,17 @@ public:
         T innov[m];
         z.boxminus(innov, meanZ);
 
-        /* mahalanobis2 = innov^T Sinv innov is computed by the reference and always accepted. */
+        /* mahalanobis2 = innov^T Sinv innov; the reference's accept functor always accepts */
+        {
+            T d2 = T(0);
+            for (int a = 0; a < m; ++a) {
+                T s = T(0);
+                for (int b = 0; b < m; ++b) s = s + Sinv[a * m + b] * innov[b];
+                d2 = d2 + innov[a] * s;
+            }
+            last_update_rejected = double(d2) > accept_max_d2;
+            if (last_update_rejected) return;
+        }
 
         /* sigma -= (K * S) * K^T  (Eigen evaluates left to right) */
         T KS[n * m];

@@ -25,7 +25,7 @@ MEAS_POSE_XVEL_YAWVEL, MEAS_POSE_ANGULAR_VELOCITY, MEAS_ORI_VELOCITY = 7, 8, 9
 EVENT_IDLE, EVENT_POSE_ACCELERATION, EVENT_ORI_ROTATION_RATE, EVENT_ORI_ACCELERATION, EVENT_KIND_COUNT = -2, 10, 11, 12, 13
 
 STATUS_NEG_DT, STATUS_DT_TOO_LARGE, STATUS_NONFINITE_MEAS, STATUS_NOT_SPD, STATUS_MEAN_NO_CONVERGE = 1, 2, 4, 8, 16
-STATUS_BAD_EVENT = 32
+STATUS_BAD_EVENT, STATUS_MEAS_REJECTED = 32, 64
 
 RBS_DOUBLES = 49
 
@@ -147,6 +147,15 @@ class UkfBatch:
         out = np.empty(self.B, np.int64)
         self._chk(self.lib.ukfb_get_last_time(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def set_mahalanobis_gate(self, max_d2: float):
+        """accept functor of ukfom update: measurements with innov^T S^-1 innov > max_d2 are not integrated (inf = off)"""
+        self._chk(self.lib.ukfb_set_mahalanobis_gate(self.h, float(max_d2)))
+
+    def get_mahalanobis_gate(self) -> float:
+        v = C.c_double()
+        self._chk(self.lib.ukfb_get_mahalanobis_gate(self.h, C.byref(v)))
+        return v.value
 
     def set_orientation_params(self, tau_g: float, tau_a: float, latitude: float):
         self._chk(self.lib.ukfb_set_orientation_params(self.h, tau_g, tau_a, latitude))

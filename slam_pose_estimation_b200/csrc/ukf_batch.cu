@@ -60,6 +60,7 @@ struct ukfb_handle {
     unsigned long long* hist = nullptr;
     double* acc_mu = nullptr;
     double* acc_cov = nullptr;
+    double gate_d2 = HUGE_VAL; /* accept_any_mahalanobis_distance */
     double* gyro_mu = nullptr;
     bool initialized = false, first_init = true;
     double min_dt = UKFB_DEFAULT_MIN_DT, max_dt = DBL_MAX;
@@ -459,6 +460,7 @@ static StepParams base_params(const ukfb_handle* h)
     p.earth[0] = h->earth[0], p.earth[1] = h->earth[1], p.earth[2] = h->earth[2];
     p.kind = -1;
     p.K = 1;
+    p.gate_d2 = h->gate_d2;
     return p;
 }
 
@@ -775,6 +777,22 @@ extern "C" int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us)
     if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_get_last_time: null argument");
     CU(cudaMemcpyAsync(ts_us, h->t_last, sizeof(long long) * h->B, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_mahalanobis_gate(ukfb_handle* h, double max_d2)
+{
+    CHECK_H(h);
+    if (!(max_d2 > 0.0)) return fail(UKFB_ERR_INVALID, "ukfb_set_mahalanobis_gate: the threshold must be positive (+inf accepts everything)");
+    if (!h->tiled && max_d2 < HUGE_VAL) return fail(UKFB_ERR_INVALID, "ukfb_set_mahalanobis_gate: needs a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
+    h->gate_d2 = max_d2;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_mahalanobis_gate(const ukfb_handle* h, double* max_d2)
+{
+    if (!h || !max_d2) return fail(UKFB_ERR_INVALID, "ukfb_get_mahalanobis_gate: null argument");
+    *max_d2 = h->gate_d2;
     return UKFB_OK;
 }
 

@@ -140,6 +140,9 @@ struct StepParams {
      * of an event is at R + tick * r_kstride + b * r_stride + kind * r_kind_stride (per-sensor table or per event). */
     int events;
     long long r_kind_stride;
+    /* the accept functor of ukfom::ukf::update: a measurement with innov^T S^-1 innov > gate_d2 is not integrated
+     * (+inf = accept_any_mahalanobis_distance, the reference's choice at PoseUKF.cpp:116) */
+    double gate_d2;
 };
 
 UKFB_HD int meas_dim(int kind)

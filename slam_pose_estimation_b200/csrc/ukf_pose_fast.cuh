@@ -261,7 +261,7 @@ struct PfDelta {
 };
 
 UKFB_DNI PfLit pf_literal_update(double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma, PoseMu m,
-                                 PfDelta delta, bool first)
+                                 PfDelta delta, bool first, double gate_d2)
 {
     typedef TSmem<PoseF> TS;
     UKFB_PF_COUNT(first ? 1 : 2);
@@ -274,7 +274,8 @@ UKFB_DNI PfLit pf_literal_update(double* sig, int kind, const double* zm, const 
             r.status = UKFB_STATUS_NOT_SPD;
             return r;
         }
-        r.status = update_first_half<PoseF, 1>(loc, 0, sig, kind, zm, Rm, r_ld);
+        r.status = update_first_half<PoseF, 1>(loc, 0, sig, kind, zm, Rm, r_ld, gate_d2);
+        if (r.status & UKFB_STATUS_MEAS_REJECTED) return r; /* gated out: nothing was modified */
     } else {
         UKFB_UNROLL
         for (int i = 0; i < 12; ++i) loc[TS::OFF_DELTA + i] = delta.d[i];
@@ -539,7 +540,7 @@ UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
  * is also in the record.  Returns false when apply_delta left the polynomial range: the record then holds
  * Sigma - K S K^T, `delta` = K innov, m is untouched. */
 UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rmeas, int r_ld, PoseMu& m,
-                      double* delta, uint32_t& status, int& passes_out, bool& spd)
+                      double* delta, uint32_t& status, int& passes_out, bool& spd, double gate_d2)
 {
     const int m_dim = meas_dim(kind);
     int sel[3];
@@ -588,6 +589,16 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
         Si[6] = (S[3] * S[7] - S[4] * S[6]) * invdet;
         Si[7] = (S[6] * S[1] - S[7] * S[0]) * invdet;
         Si[8] = (S[0] * S[4] - S[1] * S[3]) * invdet;
+    }
+    /* the accept functor: squared Mahalanobis distance against the gate (never taken with the reference's accept_any) */
+    {
+        double d2 = 0.0;
+        UKFB_UNROLL
+        for (int a = 0; a < 3; ++a) d2 += innov[a] * (Si[a * 3] * innov[0] + Si[a * 3 + 1] * innov[1] + Si[a * 3 + 2] * innov[2]);
+        if (d2 > gate_d2) {
+            status |= UKFB_STATUS_MEAS_REJECTED;
+            return true; /* nothing was modified */
+        }
     }
     /* K = Sxz S^-1 (in place), KS = K S, delta = K innov */
     double KS[36];
@@ -920,7 +931,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                 UKFB_UNROLL
                 for (int i = 0; i < 12; ++i) delta[i] = 0.0;
                 if (!literal) {
-                    fast_done = pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd);
+                    fast_done = pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd, p.gate_d2);
                     if (fast_done) {
                         if (!spd)
                             status |= UKFB_STATUS_NOT_SPD;
@@ -932,7 +943,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                     PfDelta dl;
                     UKFB_UNROLL
                     for (int i = 0; i < 12; ++i) dl.d[i] = delta[i];
-                    const PfLit r = pf_literal_update(sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal);
+                    const PfLit r = pf_literal_update(sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal, p.gate_d2);
                     status |= r.status;
                     passes_b = r.passes;
                     if (!(r.status & UKFB_STATUS_NOT_SPD)) {

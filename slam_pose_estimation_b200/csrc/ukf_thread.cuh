@@ -257,7 +257,8 @@ UKFB_D void store_noise(const double* sm, int lane, double* sig, const double* Q
 
 /* ---- first half of ukfom update (App. A.4): innovation statistics, gain, sigma <- sigma - K S K^T, delta = K innov */
 template <class F, int ST = TILE>
-UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld)
+UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld,
+                                  double gate_d2)
 {
     typedef TSmem<F> TS;
     const bool rot = (F::KIND == 0) && kind == UKFB_MEAS_POSE_ORIENTATION;
@@ -378,6 +379,13 @@ UKFB_D uint32_t update_first_half(double* sm, int lane, double* sig, int kind, c
             for (int c = 0; c < 3; ++c) zin[c] = c < m ? zm[c] : 0.0;
         }
         meas_boxminus(zin, zref, rot, innov);
+    }
+    /* the accept functor: squared Mahalanobis distance against the gate (never taken with the reference's accept_any) */
+    {
+        double d2 = 0.0;
+        UKFB_UNROLL
+        for (int a = 0; a < 3; ++a) d2 += innov[a] * (Si[a * 3] * innov[0] + Si[a * 3 + 1] * innov[1] + Si[a * 3 + 2] * innov[2]);
+        if (d2 > gate_d2) return st | UKFB_STATUS_MEAS_REJECTED;
     }
     /* K = Sxz S^-1 (in place of Sxz), KS = K S */
     double KS[F::N * 3];
@@ -584,10 +592,13 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
             if (!cholesky_thread<F>(sig, sm, lane)) {
                 status |= UKFB_STATUS_NOT_SPD;
             } else {
-                status |= update_first_half<F>(sm, lane, sig, kind, p.z + tick * p.z_kstride + b * p.z_stride, Rm, p.r_ld);
+                const uint32_t ust = update_first_half<F>(sm, lane, sig, kind, p.z + tick * p.z_kstride + b * p.z_stride, Rm, p.r_ld, p.gate_d2);
+                status |= ust;
                 /* the reference has already replaced sigma by sigma - K S K^T when MTK's assert fires inside
                  * apply_delta: on failure that matrix stays in the record, mu is left alone */
-                if (!cholesky_thread<F>(sig, sm, lane)) {
+                if (ust & UKFB_STATUS_MEAS_REJECTED) {
+                    /* gated out: nothing was modified */
+                } else if (!cholesky_thread<F>(sig, sm, lane)) {
                     status |= UKFB_STATUS_NOT_SPD;
                 } else {
                     status |= mean_and_cov<F, false>(sm, lane, sig, ma, &passes_b);

@@ -30,7 +30,7 @@ class StepParams(C.Structure):
         ("K", C.c_int), ("dt_kstride", C.c_longlong), ("ts_kstride", C.c_longlong), ("z_kstride", C.c_longlong),
         ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
-        ("events", C.c_int), ("r_kind_stride", C.c_longlong),
+        ("events", C.c_int), ("r_kind_stride", C.c_longlong), ("gate_d2", C.c_double),
     ]
 
 
@@ -87,6 +87,7 @@ class EmuBatch:
         self.tau_g = self.tau_a = np.inf
         self.earth = np.zeros(3)
         self._first_init = True
+        self.gate_d2 = np.inf
 
     def initialize(self, mu, sigma):
         mu = np.asarray(mu, float).reshape(self.B, self.MU)
@@ -119,6 +120,9 @@ class EmuBatch:
     def set_time_bounds(self, a, b):
         self.min_dt, self.max_dt = a, b
 
+    def set_mahalanobis_gate(self, max_d2):
+        self.gate_d2 = float(max_d2)
+
     def set_orientation_params(self, tau_g, tau_a, lat):
         self.tau_g, self.tau_a = tau_g, tau_a
         w = 2.0 * np.pi / 86164.0
@@ -148,6 +152,7 @@ class EmuBatch:
         p.t_last = _ptr(self.t_last)
         p.hist = _ptr(self.hist)
         p.min_dt, p.max_dt = self.min_dt, self.max_dt
+        p.gate_d2 = self.gate_d2
         p.acc_mu, p.acc_cov, p.gyro_mu = _ptr(self.acc_mu), _ptr(self.acc_cov), _ptr(self.gyro_mu)
         p.neg_inv_tau_g, p.neg_inv_tau_a = -1.0 / self.tau_g, -1.0 / self.tau_a
         p.earth = (C.c_double * 3)(*self.earth)
