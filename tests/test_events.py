@@ -61,9 +61,10 @@ def check_pose(cls, kw, tol):
     B = 37
     ts, kinds, mu3, tab = c5(B, 25)
     o, e = P.make_pose(OracleBatch, B), P.make_pose(cls, B, **kw)
+    h = ts.shape[0] // 2
     for x in (o, e):
-        x.run_events(ts[:40], kinds[:40], mu3[:40], tab)
-        x.run_events(ts[40:], kinds[40:], mu3[40:], tab)  # queues continue across calls
+        x.run_events(ts[:h], kinds[:h], mu3[:h], tab)
+        x.run_events(ts[h:], kinds[h:], mu3[h:], tab)  # queues continue across calls
     P.assert_parity(0, e.get_state(), o.get_state(), tol=tol, what="C5 queues")
     assert np.array_equal(e.get_last_time(), o.get_last_time()) if hasattr(e, "get_last_time") else True
     assert not e.get_status().any() and not o.get_status().any()
