@@ -19,6 +19,7 @@
 
 #include "ukf_device.cuh"
 #include "ukf_thread.cuh"
+#include "ukf_ori_fast.cuh"
 #include "ukf_pose_fast.cuh"
 
 using namespace ukfb;
@@ -50,7 +51,7 @@ struct ukfb_handle {
     int n = 0, MU = 0, LP = 0, REC = 0;
     int G = 8, WPB = 4, MINB = 3; /* warp kernel launch shape: filters per warp, warps per block, resident blocks per SM */
     int tiled = 1;                /* 1: lane-per-filter kernel, tile-interleaved records; 0: warp-per-group kernel, AoS records */
-    int fast = UKFB_SO3_BOXPLUS_LEFT; /* tiled PoseUKF: 1 = structure-exploiting kernel (ukf_pose_fast.cuh), 0 = literal kernel (ukf_thread.cuh) */
+    int fast = UKFB_SO3_BOXPLUS_LEFT; /* tiled: 1 = structure-exploiting kernels (ukf_pose_fast.cuh, ukf_ori_fast.cuh), 0 = literal kernel (ukf_thread.cuh) */
     cudaStream_t stream = nullptr;
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
@@ -425,11 +426,27 @@ static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p)
     return cudaGetLastError();
 }
 
+static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
+{
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(double) * OF_PER_LANE * TILE;
+    if (!attr_set[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(ukf_ori_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_set[h->device & 63] = true;
+    }
+    const long long grid = (p.B + TILE - 1) / TILE;
+    ukf_ori_fast_kernel<<<unsigned(grid), TILE, smem, h->stream>>>(p);
+    return cudaGetLastError();
+}
+
 static int launch_step(ukfb_handle* h, const StepParams& p)
 {
     cudaError_t e;
     if (h->tiled && h->fast && h->kind == UKFB_POSE)
         e = launch_pose_fast(h, p);
+    else if (h->tiled && h->fast)
+        e = launch_ori_fast(h, p);
     else if (h->tiled)
         e = h->kind == UKFB_POSE ? launch_thread_f<PoseF>(h, p) : launch_thread_f<OriF>(h, p);
     else

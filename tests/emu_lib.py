@@ -44,7 +44,8 @@ def load(sanitize: bool = False):
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/simt.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"),
-            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh")]
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh"),
+            os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_ori_fast.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", _DIR,
                "-o", out, srcs[0]]
@@ -66,7 +67,7 @@ class EmuBatch:
         'fast' (ukf_pose_fast.cuh, PoseUKF only, same tiles)"""
         self.lib = load()
         self.kind, self.B, self.G, self.tiled = kind, B, G, kernel in ("thread", "fast")
-        self.fast = kernel == "fast" and kind == 0
+        self.fast = kernel == "fast"
         self.n, self.MU, self.REC = (12, 13, 91) if kind == 0 else (13, 14, 105)
         self.LP = self.n * (self.n + 1) // 2
         self.tril = np.tril_indices(self.n)
@@ -85,7 +86,7 @@ class EmuBatch:
         self.gyro_mu = np.zeros((B, 3))
         self.min_dt, self.max_dt = 1e-9, np.finfo(float).max
         self.tau_g = self.tau_a = np.inf
-        self.earth = np.zeros(3)
+        self.earth = np.array([2.0 * np.pi / 86164.0, 0.0, 0.0])  # latitude 0 until set_orientation_params
         self._first_init = True
         self.gate_d2 = np.inf
 
@@ -166,7 +167,9 @@ class EmuBatch:
         if self.tiled:  # [tile][entry][lane] in memory
             dev = np.ascontiguousarray(self.state.reshape(-1, 32, self.REC).transpose(0, 2, 1))
             p.state = _ptr(dev)
-            if self.fast:
+            if self.fast and self.kind == 1:
+                rc = self.lib.emu_ori_fast_step(C.byref(p))
+            elif self.fast:
                 rc = self.lib.emu_pose_fast_step(C.byref(p))
             else:
                 rc = self.lib.emu_thread_step(C.c_int(self.kind), C.byref(p))
@@ -222,7 +225,7 @@ class EmuBatch:
     def fallbacks(self):
         """(literal predict, literal update, literal apply_delta) calls made so far by the fast kernel's lanes"""
         out = (C.c_ulonglong * 3)()
-        self.lib.emu_pose_fast_fallbacks(out)
+        (self.lib.emu_ori_fast_fallbacks if self.kind == 1 else self.lib.emu_pose_fast_fallbacks)(out)
         return np.array(list(out), np.int64)
 
     def get_status(self):

@@ -8,6 +8,7 @@
 #include "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"
 #include "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"
 #include "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh"
+#include "../../slam_pose_estimation_b200/csrc/ukf_ori_fast.cuh"
 
 using namespace ukfb;
 
@@ -61,6 +62,19 @@ extern "C" int emu_pose_fast_step(const StepParams* p)
 extern "C" void emu_pose_fast_fallbacks(unsigned long long* out3)
 {
     for (int i = 0; i < 3; ++i) out3[i] = pf_fallbacks[i];
+}
+
+/* the structure-exploiting OrientationUKF kernel (ukf_ori_fast.cuh), same tiles */
+extern "C" int emu_ori_fast_step(const StepParams* p)
+{
+    const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
+    simt_emu::launch(ukf_ori_fast_kernel, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
+    return 0;
+}
+
+extern "C" void emu_ori_fast_fallbacks(unsigned long long* out3)
+{
+    for (int i = 0; i < 3; ++i) out3[i] = of_fallbacks[i];
 }
 
 extern "C" int emu_sizeof_params(void) { return int(sizeof(StepParams)); }

