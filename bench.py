@@ -138,8 +138,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4 sample: PoseUKF predict(dt=1ms) + AngularVelocity update (m=3) per step, CPU oracle port",
-                   "filters": B},
+        "config": {"workload": "C4: PoseUKF Monte-Carlo sweep sharded by filter index; step = predictionStep(1 ms) + "
+                               "AngularVelocityMeasurement update (m=3)",
+                   "sample": f"{B} filters of the sweep per step on the host cores (the reference's CPU path: oracle port, "
+                             "OpenMP over filters)", "filters": B},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{B} filters x {args.steps} steps, OpenMP over filters"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -160,6 +162,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-literal", action="store_true", help="skip the secondary measurement of the literal kernel")
+    ap.add_argument("--no-orientation", action="store_true", help="skip the secondary OrientationUKF (C2) figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -300,6 +303,48 @@ def main():
     else:
         fp64_peak = f.measure_fp64_peak() if rank == 0 else 0.0
 
+    # ---- BASELINE.json config 2 (secondary figure): 65,536 OrientationUKF on a 1 kHz IMU stream ----------------------
+    # 100 ticks per launch (ukfb_run_dev: IMU sample stored + predict every tick, one body-velocity update on the last
+    # tick), state on chip between ticks; ukf_ori_fast_kernel.  Contract flops: SURVEY.md 8(d) 22.7 kflop per predict at
+    # k = 3 mean passes, -1.747 kflop per pass; 27.8 kflop per update likewise.
+    orientation = None
+    if not args.no_orientation and world == 1:
+        Bo, Ko = 65536, 100
+        mu_o, sg_o = syn.orientation_initial(Bo)
+        g = UkfBatch(1, Bo, device=local)
+        g.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+        g.initialize(mu_o, sg_o)
+        g.set_process_noise(syn.ORI_Q)
+        imu = np.empty((4, Bo, 6))
+        for j in range(4):
+            imu[j, :, :3], imu[j, :, 3:] = syn.orientation_imu(Bo, j + 1)
+        d_imu = torch.from_numpy(imu).to(dev)[torch.arange(Ko, device=dev) % 4].contiguous()
+        kinds_o = np.full(Ko, -1, np.int8)
+        kinds_o[Ko - 1] = 9
+        d_zo = torch.from_numpy(syn.orientation_velocity(Bo, 1)[0]).to(dev)[None].expand(Ko, Bo, 3).contiguous()
+        d_Ro = torch.from_numpy(np.tile(np.eye(3) * syn.SIGMA_DVL**2, (Ko, 1, 1))).to(dev)
+        d_dto = torch.full((Ko,), syn.DT, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            g.run_dev(Ko, d_dto, False, kinds_o, d_zo, d_Ro, False, d_imu)
+        g.synchronize()
+        g.clear_mean_iter_hist()
+        reps = 5
+        g.event_record(0)
+        for _ in range(reps):
+            g.run_dev(Ko, d_dto, False, kinds_o, d_zo, d_Ro, False, d_imu)
+        g.event_record(1)
+        g.synchronize()
+        o_ms = g.event_elapsed_ms(0, 1) / reps
+        oh = g.get_mean_iter_hist()
+        o_passes = float((oh * np.arange(8)).sum() / max(1, oh.sum()))
+        o_flops = Ko * (22.7e3 + (o_passes - 3.0) * 1.747e3) + (27.8e3 + (o_passes - 3.0) * 1.747e3)
+        orientation = {"workload": "C2: 65,536 OrientationUKF, 1 kHz IMU stream, 100 ticks per launch (store IMU + predict), "
+                                   "velocity update on the last tick", "kernel": "ukf_ori_fast_kernel",
+                       "value": Bo * Ko / (o_ms * 1e-3), "unit": "filter-ticks/s", "launch_ms": o_ms, "mean_passes_avg": o_passes,
+                       "flops_per_launch_per_filter": o_flops, "achieved_tflops": o_flops * Bo / (o_ms * 1e-3) / 1e12,
+                       "status_flagged": int(g.status_summary()[0])}
+        g.close()
+
     # ---- roofline -------------------------------------------------------------------------------
     passes = float((hist * np.arange(8)).sum() / max(1, hist.sum()))
     flops_step = FLOPS_PER_STEP_K3 + (passes - 3.0) * MEANS_PER_STEP * FLOPS_PER_MEAN_PASS
@@ -323,6 +368,8 @@ def main():
         ex = float(prof["executed_fp64_flops_per_step"]) * B / launch_s
         executed = {"flops_per_step": prof["executed_fp64_flops_per_step"], "achieved": ex / 1e12, "frac": ex / fp64_peak,
                     "source": "ncu op counts of this kernel on this workload (profiles/traffic.json) / this run's launch time"}
+    if orientation and fp64_peak:
+        orientation["roofline_frac"] = orientation["achieved_tflops"] * 1e12 / fp64_peak
     if literal and fp64_peak:
         literal["roofline_frac"] = flops_step * B / (literal["ms_per_step"] * 1e-3) / fp64_peak
 
@@ -352,6 +399,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if orientation:
+        line["orientation_c2"] = orientation
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         v, threads, dt = time_oracle(args.ref_filters, 2, 1)  # calibrate, then ~10 s of CPU work
         nsteps = int(min(20000, max(4, 12.0 / (dt / 2))))  # about 12 s of CPU work
