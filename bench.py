@@ -88,6 +88,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank (and allocate its pinned staging buffers, first touch) on the CPUs NVML reports as closest to its
+    GPU, so that the end-to-end copies of the 8 ranks do not all cross one socket's memory controller."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception as e:  # affinity is an optimisation only
+        return {"error": str(e)[:80]}
+    return None
+
+
 def make_workload(B: int, first: int, pool: int):
     """initial state (perturbed per filter) and `pool` distinct measurement sets for filters first..first+B"""
     from slam_pose_estimation_b200 import synthetic as syn
@@ -178,6 +197,8 @@ def main():
         print(json.dumps({"error": "no CUDA device: the engine has no CPU path"}), flush=True)
         return 2
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -382,7 +403,7 @@ def main():
                                "AngularVelocityMeasurement update (m=3), one fused launch",
                    "filters_per_gpu": B, "filters_total": world * B, "parallelism": f"filter-shard x{world}, no collective on the step path",
                    "l2": "state records 805 MB per GPU >> 126 MB L2 (inputs larger than L2)" if B * 768 > 3 * 126e6 else "inputs smaller than L2",
-                   "mean_passes_avg": passes, "status_flagged": int(n_flag)},
+                   "mean_passes_avg": passes, "status_flagged": int(n_flag), "rank0_cpu_affinity": numa},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved_flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
@@ -402,6 +423,7 @@ def main():
     if orientation:
         line["orientation_c2"] = orientation
     if rank == 0 and not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core
         v, threads, dt = time_oracle(args.ref_filters, 2, 1)  # calibrate, then ~10 s of CPU work
         nsteps = int(min(20000, max(4, 12.0 / (dt / 2))))  # about 12 s of CPU work
         v, threads, dt = time_oracle(args.ref_filters, nsteps, 1)
