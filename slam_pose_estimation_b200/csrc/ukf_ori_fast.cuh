@@ -446,9 +446,7 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
     /* ---- new covariance = 1/2 C + process noise dt^2 Q' (OrientationUKF.cpp:81-86), committed to the record */
     {
         const double scale = dt * dt;
-        double nz[OriF::LP];
-        UKFB_UNROLL
-        for (int e = 0; e < OriF::LP; ++e) nz[e] = scale * UKFB_LDG(Qp + e);
+        double nb[12]; /* the two rotated blocks of the noise; every other entry is scale * Q */
         UKFB_UNROLL
         for (int blk = 0; blk < 2; ++blk) {
             const int off = blk * 3;
@@ -470,7 +468,7 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
                     double s = 0.0;
                     UKFB_UNROLL
                     for (int k = 0; k < 3; ++k) s += t[r * 3 + k] * Rm[cc * 3 + k];
-                    nz[tri(off + r, off + cc)] = scale * s;
+                    nb[blk * 6 + tri(r, cc)] = scale * s;
                 }
             }
         }
@@ -481,13 +479,14 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
             for (int k = 0; k <= i; ++k) {
                 const int e = tri(i, k);
                 const double dk = k < 9 ? cg : (k < 12 ? ca : 1.0);
+                const double nz = (i < 6 && i / 3 == k / 3) ? nb[(i / 3) * 6 + tri(i % 3, k % 3)] : scale * UKFB_LDG(Qp + e);
                 double s;
                 if (i < 6)
-                    s = fma(0.5, C[e], nz[e]);
+                    s = fma(0.5, C[e], nz);
                 else if (k < 6)
-                    s = fma(0.5 * di, X[(i - 6) * 6 + k], nz[e]);
+                    s = fma(0.5 * di, X[(i - 6) * 6 + k], nz);
                 else
-                    s = fma(di * dk, sig[e * TILE], nz[e]);
+                    s = fma(di * dk, sig[e * TILE], nz);
                 sig[e * TILE] = s;
             }
         }
@@ -653,11 +652,11 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
             return true;
         }
     }
-    /* K = Sxz S^-1 (in place), KS = K S, delta = K innov */
-    double KS[39];
+    /* Row by row: K[i,:] = Sxz[i,:] S^-1 (in place of Sxz), (K S)[i,:], delta_i, and row i of
+     * Sigma <- Sigma - (K S) K^T -- to the record, and kept in registers for the factorisation */
     UKFB_UNROLL
     for (int i = 0; i < 13; ++i) {
-        double k3[3];
+        double k3[3], ks3[3];
         UKFB_UNROLL
         for (int cc = 0; cc < 3; ++cc) {
             double s = 0.0;
@@ -671,20 +670,16 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
             double ks = 0.0;
             UKFB_UNROLL
             for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + cc];
-            KS[i * 3 + cc] = ks;
+            ks3[cc] = ks;
             Sxz[i * 3 + cc] = k3[cc];
             dl += k3[cc] * innov[cc];
         }
         delta[i] = dl;
-    }
-    /* Sigma <- Sigma - (K S) K^T: to the record, and kept in registers for the factorisation */
-    UKFB_UNROLL
-    for (int i = 0; i < 13; ++i) {
         UKFB_UNROLL
         for (int j = 0; j <= i; ++j) {
             double s = 0.0;
             UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) s += KS[i * 3 + k] * Sxz[j * 3 + k];
+            for (int k = 0; k < 3; ++k) s += ks3[k] * Sxz[j * 3 + k];
             const double x = sig[tri(i, j) * TILE] - s;
             a[tri(i, j)] = x;
             sig[tri(i, j) * TILE] = x;

@@ -446,9 +446,12 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
     /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record */
     {
         const double scale = ma.has_acc ? 1.0 : dt;
-        double nz[PoseF::LP];
+        /* the entries of the noise that are not plain scale * Q: the two rotated blocks, or 2 acc.cov */
+        double nb[12], na[6];
         UKFB_UNROLL
-        for (int e = 0; e < PoseF::LP; ++e) nz[e] = scale * UKFB_LDG(Qp + e);
+        for (int i = 0; i < 12; ++i) nb[i] = 0.0;
+        UKFB_UNROLL
+        for (int i = 0; i < 6; ++i) na[i] = 0.0;
         if (!ma.has_acc) {
             UKFB_UNROLL
             for (int blk = 0; blk < 2; ++blk) {
@@ -471,7 +474,7 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
                         double s = 0.0;
                         UKFB_UNROLL
                         for (int k = 0; k < 3; ++k) s += t[r * 3 + k] * Rm[cc * 3 + k];
-                        nz[tri(off + r, off + cc)] = scale * s;
+                        nb[blk * 6 + tri(r, cc)] = scale * s;
                     }
                 }
             }
@@ -479,7 +482,7 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
             UKFB_UNROLL
             for (int r = 0; r < 3; ++r) {
                 UKFB_UNROLL
-                for (int cc = 0; cc <= r; ++cc) nz[tri(6 + r, 6 + cc)] = 2.0 * acov[r * 3 + cc];
+                for (int cc = 0; cc <= r; ++cc) na[tri(r, cc)] = 2.0 * acov[r * 3 + cc];
             }
         }
         UKFB_UNROLL
@@ -487,13 +490,16 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
             UKFB_UNROLL
             for (int k = 0; k <= i; ++k) {
                 const int e = tri(i, k);
+                double nz = scale * UKFB_LDG(Qp + e);
+                if (i < 6 && i / 3 == k / 3) nz = ma.has_acc ? nz : nb[(i / 3) * 6 + tri(i % 3, k % 3)];
+                if (i >= 6 && i < 9 && k >= 6) nz = ma.has_acc ? na[tri(i - 6, k - 6)] : nz;
                 double s;
                 if (i < 6)
-                    s = fma(0.5, C[e], nz[e]);
+                    s = fma(0.5, C[e], nz);
                 else if (k < 6)
-                    s = fma(0.5, X[(i - 6) * 6 + k], nz[e]);
+                    s = fma(0.5, X[(i - 6) * 6 + k], nz);
                 else
-                    s = sig[e * TILE] + nz[e];
+                    s = sig[e * TILE] + nz;
                 sig[e * TILE] = s;
                 if (to_smem) UKFB_PS(e) = s;
             }
@@ -600,11 +606,14 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             return true; /* nothing was modified */
         }
     }
-    /* K = Sxz S^-1 (in place), KS = K S, delta = K innov */
-    double KS[36];
+    /* Row by row: K[i,:] = Sxz[i,:] S^-1 (in place of Sxz), (K S)[i,:], delta_i = K[i,:] innov, and row i of
+     * Sigma <- Sigma - (K S) K^T -- to the record, and kept in registers for the factorisation.  (K S)[i,:] is only
+     * needed for row i, so it is never stored: the same operations as the reference's expression order, fewer live
+     * registers. */
+    double a[PoseF::LP];
     UKFB_UNROLL
     for (int i = 0; i < 12; ++i) {
-        double k3[3];
+        double k3[3], ks3[3];
         UKFB_UNROLL
         for (int cc = 0; cc < 3; ++cc) {
             double s = 0.0;
@@ -618,21 +627,16 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             double ks = 0.0;
             UKFB_UNROLL
             for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + c];
-            KS[i * 3 + c] = ks;
+            ks3[c] = ks;
             Sxz[i * 3 + c] = k3[c];
             dl += k3[c] * innov[c];
         }
         delta[i] = dl;
-    }
-    /* Sigma <- Sigma - (K S) K^T: to the record, and kept in registers for the factorisation */
-    double a[PoseF::LP];
-    UKFB_UNROLL
-    for (int i = 0; i < 12; ++i) {
         UKFB_UNROLL
         for (int j = 0; j <= i; ++j) {
             double s = 0.0;
             UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) s += KS[i * 3 + k] * Sxz[j * 3 + k];
+            for (int k = 0; k < 3; ++k) s += ks3[k] * Sxz[j * 3 + k];
             const double x = UKFB_PS(tri(i, j)) - s;
             a[tri(i, j)] = x;
             sig[tri(i, j) * TILE] = x;
@@ -911,13 +915,14 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
                 if (!sigma_in_smem) {
                     /* no fast predict ran on this covariance in this tick: it has not been shown to be SPD yet, and the
                      * reference's update factorises it first */
-                    if (do_pred) { /* the literal predict rewrote the record */
-                        UKFB_UNROLL
-                        for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
-                    }
+                    /* read from the record again (it is current whichever predict ran, or none): keeping the
+                     * tick's first copy alive across the predict only costs spills */
+                    double a2[F::LP];
                     UKFB_UNROLL
-                    for (int e = 0; e < F::LP; ++e) UKFB_PS(e) = a[e];
-                    if (!pf_cholesky<12>(a)) {
+                    for (int e = 0; e < F::LP; ++e) a2[e] = sig[e * TILE];
+                    UKFB_UNROLL
+                    for (int e = 0; e < F::LP; ++e) UKFB_PS(e) = a2[e];
+                    if (!pf_cholesky<12>(a2)) {
                         status |= UKFB_STATUS_NOT_SPD;
                         do_upd = false;
                     }

@@ -295,6 +295,52 @@ def test_large_batch_invariants(Ukf):
         P.assert_parity(0, (mu[i:i + 1], sg[i:i + 1]), o.get_state(), what=f"filter {i} of 65536")
 
 
+def test_full_size_c4_invariants_and_shards(Ukf):
+    """BASELINE config 4 at its full size (1,048,576 PoseUKF, Monte-Carlo initial states): size-independent
+    properties -- finite, unit quaternions, symmetric positive definite covariances, no status bits, one mean pass --
+    a strided sample against the oracle, and a shard of the sweep run on its own is bitwise equal to its slice."""
+    B = 1 << 20
+    g = P.make_pose(Ukf, B)
+    for k in range(1, 4):
+        z, R = syn.pose_measurement(8, B, k)
+        g.step(syn.DT, 8, z, R)
+    mu, sg = g.get_state()
+    assert np.isfinite(mu).all() and np.isfinite(sg).all()
+    assert np.abs(np.linalg.norm(mu[:, 3:7], axis=1) - 1.0).max() < 1e-12
+    assert P.spd_ok(sg[::4099])
+    assert not g.get_status().any()
+    assert g.get_mean_iter_hist()[1] == 2 * 3 * B
+    for i in np.arange(0, B, 65_537):
+        o = P.make_pose(OracleBatch, 1, first=int(i))
+        for k in range(1, 4):
+            z, R = syn.pose_measurement(8, 1, k, first=int(i))
+            o.step(syn.DT, 8, z, R)
+        P.assert_parity(0, (mu[i:i + 1], sg[i:i + 1]), o.get_state(), what=f"filter {i} of 1 Mi")
+    lo, n = 5 * (B // 8), 4096  # inside the shard rank 5 of 8 owns
+    part = P.make_pose(Ukf, n, first=lo)
+    for k in range(1, 4):
+        z, R = syn.pose_measurement(8, n, k, first=lo)
+        part.step(syn.DT, 8, z, R)
+    mu_p, sg_p = part.get_state()
+    assert np.array_equal(mu[lo:lo + n], mu_p) and np.array_equal(sg[lo:lo + n], sg_p)
+
+
+def test_full_size_c2_orientation_invariants(Ukf):
+    """BASELINE config 2 at its full size (65,536 OrientationUKF on the IMU stream)."""
+    B = 65_536
+    g = P.make_ori(Ukf, B)
+    P.run_ori_c1(g, B, 20, every=10)
+    mu, sg = g.get_state()
+    assert np.isfinite(mu).all() and np.isfinite(sg).all()
+    assert np.abs(np.linalg.norm(mu[:, 0:4], axis=1) - 1.0).max() < 1e-12
+    assert P.spd_ok(sg[::257])
+    assert not g.get_status().any()
+    for i in np.arange(0, B, 8191):
+        o = P.make_ori(OracleBatch, 1)
+        P.run_ori_c1(o, 1, 20, first=int(i), every=10)
+        P.assert_parity(1, (mu[i:i + 1], sg[i:i + 1]), o.get_state(), what=f"filter {i} of 65536")
+
+
 # ---- kernel variants and the streaming calls ------------------------------------------------------
 
 @pytest.mark.parametrize("kernel", ["fast", "thread", "warp"])
