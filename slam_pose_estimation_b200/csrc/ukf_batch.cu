@@ -19,6 +19,9 @@
 
 #include "ukf_device.cuh"
 #include "ukf_thread.cuh"
+#ifndef UKFB_DEFAULT_WPB
+#define UKFB_DEFAULT_WPB 1
+#endif
 #include "ukf_ori_fast.cuh"
 #include "ukf_pose_fast.cuh"
 
@@ -412,32 +415,44 @@ static cudaError_t launch_thread_f(const ukfb_handle* h, const StepParams& p)
     return cudaGetLastError();
 }
 
-static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p)
+/* warps per block of the two fast kernels: UKFB_WPB = 1, 2 or 4 (read once) */
+static int fast_wpb()
 {
-    static bool attr_set[64] = {};
-    const size_t smem = sizeof(double) * PF_PER_LANE * TILE;
+    static int wpb = 0;
+    if (!wpb) {
+        const char* e = getenv("UKFB_WPB");
+        const int v = e ? atoi(e) : UKFB_DEFAULT_WPB;
+        wpb = (v == 1 || v == 2 || v == 4) ? v : UKFB_DEFAULT_WPB;
+    }
+    return wpb;
+}
+
+template <class K>
+static cudaError_t launch_fast(K kernel, int per_lane, const ukfb_handle* h, const StepParams& p, bool* attr_set)
+{
+    const int wpb = fast_wpb();
+    const size_t smem = sizeof(double) * per_lane * TILE * wpb;
     if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(ukf_pose_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         attr_set[h->device & 63] = true;
     }
-    const long long grid = (p.B + TILE - 1) / TILE;
-    ukf_pose_fast_kernel<<<unsigned(grid), TILE, smem, h->stream>>>(p);
+    const long long tiles = (p.B + TILE - 1) / TILE;
+    const long long grid = (tiles + wpb - 1) / wpb; /* warps past the last tile return at once */
+    kernel<<<unsigned(grid), TILE * wpb, smem, h->stream>>>(p);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p)
+{
+    static bool attr_set[64] = {};
+    return launch_fast(ukf_pose_fast_kernel, PF_PER_LANE, h, p, attr_set);
 }
 
 static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
 {
     static bool attr_set[64] = {};
-    const size_t smem = sizeof(double) * OF_PER_LANE * TILE;
-    if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(ukf_ori_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        attr_set[h->device & 63] = true;
-    }
-    const long long grid = (p.B + TILE - 1) / TILE;
-    ukf_ori_fast_kernel<<<unsigned(grid), TILE, smem, h->stream>>>(p);
-    return cudaGetLastError();
+    return launch_fast(ukf_ori_fast_kernel, OF_PER_LANE, h, p, attr_set);
 }
 
 static int launch_step(ukfb_handle* h, const StepParams& p)

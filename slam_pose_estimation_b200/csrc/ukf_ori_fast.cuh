@@ -45,16 +45,17 @@ constexpr int OF_OB = 39;
 constexpr int OF_OC = 99;
 constexpr int OF_PER_LANE = 109;
 
-/* Cholesky of a packed lower N x N in registers, first NCOL columns (LAPACK dpotf2('L') order) */
-template <int N, int NCOL>
-UKFB_D bool reg_cholesky(double* a)
+/* Cholesky of a packed lower N x N in registers, first NCOL columns.  Right-looking: as soon as column j is final the
+ * columns to its right are updated with it, so every entry receives the subtractions a_ik a_jk in the order
+ * k = 0, 1, ... of LAPACK dpotf2('L') -- bit for bit the same factor -- while finished columns can leave the register
+ * file early (STORE(j) is called right after column j is final). */
+template <int N, int NCOL, class Store>
+UKFB_D bool reg_cholesky(double* a, Store store)
 {
     bool ok = true;
     UKFB_UNROLL
     for (int j = 0; j < NCOL; ++j) {
         double ajj = a[tri(j, j)];
-        UKFB_UNROLL
-        for (int k = 0; k < j; ++k) ajj -= a[tri(j, k)] * a[tri(j, k)];
         if (!(ajj > 0.0) || !(ajj < 1.0e300)) {
             ok = false;
             ajj = 1.0;
@@ -63,14 +64,21 @@ UKFB_D bool reg_cholesky(double* a)
         fast_sqrt_rsqrt(ajj, d, rinv);
         a[tri(j, j)] = d;
         UKFB_UNROLL
-        for (int i = j + 1; i < N; ++i) {
-            double s = a[tri(i, j)];
+        for (int i = j + 1; i < N; ++i) a[tri(i, j)] *= rinv;
+        UKFB_UNROLL
+        for (int l = j + 1; l < NCOL; ++l) {
             UKFB_UNROLL
-            for (int k = 0; k < j; ++k) s -= a[tri(i, k)] * a[tri(j, k)];
-            a[tri(i, j)] = s * rinv;
+            for (int i = l; i < N; ++i) a[tri(i, l)] -= a[tri(i, j)] * a[tri(l, j)];
         }
+        store(j);
     }
     return ok;
+}
+
+template <int N, int NCOL>
+UKFB_D bool reg_cholesky(double* a)
+{
+    return reg_cholesky<N, NCOL>(a, [](int) {});
 }
 
 struct OriMu {
@@ -266,26 +274,22 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
     UKFB_UNROLL
     for (int i = 0; i < 3; ++i) cx.omega[i] = ma.omega[i], cx.acc[i] = ma.acc[i], cx.earth[i] = ma.earth[i];
     const double dt = ma.dt;
-    spd = reg_cholesky<13, 13>(a);
-    if (!spd) return true;
-    UKFB_UNROLL
-    for (int j = 0; j < 3; ++j) {
-        UKFB_UNROLL
-        for (int i = 0; i < 13; ++i) UKFB_OS(j * 13 + i) = i >= j ? a[tri(i, j)] : 0.0;
-    }
-    UKFB_UNROLL
-    for (int j = 3; j < 9; ++j) {
-        UKFB_UNROLL
-        for (int i = 3; i < 13; ++i) UKFB_OS(OF_OB + (j - 3) * 10 + (i - 3)) = i >= j ? a[tri(i, j)] : 0.0;
-    }
-    {
-        int s = OF_OC;
-        UKFB_UNROLL
-        for (int j = 9; j < 13; ++j) {
+    /* the factor goes to the OA / OB / OC blocks column by column as it is produced (nothing outside shared memory is
+     * modified before the factorisation has succeeded) */
+    spd = reg_cholesky<13, 13>(a, [&](int j) {
+        if (j < 3) {
             UKFB_UNROLL
-            for (int i = j; i < 13; ++i) UKFB_OS(s++) = a[tri(i, j)];
+            for (int i = 0; i < 13; ++i) UKFB_OS(j * 13 + i) = i >= j ? a[tri(i >= j ? i : j, j)] : 0.0;
+        } else if (j < 9) {
+            UKFB_UNROLL
+            for (int i = 3; i < 13; ++i) UKFB_OS(OF_OB + (j - 3) * 10 + (i - 3)) = i >= j ? a[tri(i >= j ? i : j, j)] : 0.0;
+        } else {
+            const int base = OF_OC + (j == 9 ? 0 : (j == 10 ? 4 : (j == 11 ? 7 : 9)));
+            UKFB_UNROLL
+            for (int i = j; i < 13; ++i) UKFB_OS(base + i - j) = a[tri(i, j)];
         }
-    }
+    });
+    if (!spd) return true;
     bool slow = false;
     double Rm[9];
     quat_matrix(m.q, Rm);
@@ -800,16 +804,20 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef OriF F;
     UKFB_SMEM_DECL
-    double* sm = ukfb_smem;
-    const int lane = threadIdx.x;
-    const long long b = (long long)blockIdx.x * TILE + lane;
+    /* a block is 1..4 independent warps (no barrier between them: warps of one block merely start together, which keeps
+     * their instruction fetches close); each warp owns one tile of 32 filters and its own slice of shared memory */
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    double* sm = ukfb_smem + wib * (OF_PER_LANE * TILE);
+    if (tile * TILE >= p.B) return; /* a warp past the last tile (no barriers in this kernel) */
+    const long long b = tile * TILE + lane;
     const bool valid = b < p.B;
     const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
-    double* rec = p.state + (long long)blockIdx.x * (TILE * F::REC) + lane; /* entry e at rec[e * TILE] */
+    double* rec = p.state + tile * (TILE * F::REC) + lane; /* entry e at rec[e * TILE] */
     double* sig = rec + F::MU * TILE;
 
     OriMu m;
@@ -1020,7 +1028,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_ori_fast_kernel(const UKFB_GRID
     }
     if (valid && status) p.status[b] |= status;
     if (p.hist && valid) {
-        unsigned long long* hs = p.hist + (blockIdx.x % HIST_SLOTS) * 8;
+        unsigned long long* hs = p.hist + (tile % HIST_SLOTS) * 8;
         UKFB_UNROLL
         for (int k = 1; k < 8; ++k)
             if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);

@@ -767,16 +767,20 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef PoseF F;
     UKFB_SMEM_DECL
-    double* sm = ukfb_smem;
-    const int lane = threadIdx.x;
-    const long long b = (long long)blockIdx.x * TILE + lane;
+    /* a block is 1..4 independent warps (no barrier between them: warps of one block merely start together, which keeps
+     * their instruction fetches close); each warp owns one tile of 32 filters and its own slice of shared memory */
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    double* sm = ukfb_smem + wib * (PF_PER_LANE * TILE);
+    if (tile * TILE >= p.B) return; /* a warp past the last tile (no barriers in this kernel) */
+    const long long b = tile * TILE + lane;
     const bool valid = b < p.B;
     const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
-    double* rec = p.state + (long long)blockIdx.x * (TILE * F::REC) + lane; /* entry e at rec[e * TILE] */
+    double* rec = p.state + tile * (TILE * F::REC) + lane; /* entry e at rec[e * TILE] */
     double* sig = rec + F::MU * TILE;
 
     PoseMu m;
@@ -978,7 +982,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_pose_fast_kernel(const UKFB_GRI
     }
     if (valid && status) p.status[b] |= status;
     if (p.hist && valid) {
-        unsigned long long* hs = p.hist + (blockIdx.x % HIST_SLOTS) * 8;
+        unsigned long long* hs = p.hist + (tile % HIST_SLOTS) * 8;
         UKFB_UNROLL
         for (int k = 1; k < 8; ++k)
             if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);
