@@ -151,6 +151,8 @@ class Ukf:
         self.mu = np.array(mu, float)
         self.sigma = np.array(sigma, float)
         self.passes = []
+        self.accept_max_d2 = np.inf  # ukfom::accept_any_mahalanobis_distance (PoseUKF.cpp:116)
+        self.rejected = 0
 
     def sigma_points(self, delta=None):
         n = self.man.dof
@@ -208,6 +210,9 @@ class Ukf:
         Sinv = np.linalg.inv(S)
         K = Sxz @ Sinv
         innov = zman.boxminus(np.asarray(z, float), zbar)
+        if float(innov @ Sinv @ innov) > self.accept_max_d2:  # the accept functor slot
+            self.rejected += 1
+            return
         self.sigma = self.sigma - K @ S @ K.T
         self.apply_delta(K @ innov)
 

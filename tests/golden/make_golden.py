@@ -57,12 +57,54 @@ def scenario_ori_c1_10k(x, B):
     P.run_ori_c1(x, B, 10_000)
 
 
+def scenario_pose_c5_events(x, B):
+    """per-filter queues of asynchronous IMU / DVL / GPS samples (BASELINE config 5), two launches"""
+    ts, kinds, mu3 = syn.pose_c5_events(B, 1, 24, dvl_period=7, gps_period=11)
+    tab = syn.sensor_cov_table()
+    h = ts.shape[0] // 2
+    x.run_events(ts[:h], kinds[:h], mu3[:h], tab)
+    x.run_events(ts[h:], kinds[h:], mu3[h:], tab)
+
+
+def scenario_pose_gate(x, B):
+    """Mahalanobis gate at 16: every third filter receives gross outliers, which must leave it untouched"""
+    x.set_mahalanobis_gate(16.0)
+    out = np.arange(B) % 3 == 0
+    for k in range(1, 5):
+        for kind in (8, 4, 1):
+            z, R = syn.pose_measurement(kind, B, k)
+            z = z.copy()
+            if kind != 8:
+                z[out] += 500.0
+            x.step(syn.DT, kind, z, R)
+
+
+def scenario_ori_events(x, B):
+    """OrientationUKF queues: rotation-rate and acceleration samples stored, velocity updates, idle slots"""
+    K = 24
+    ts = np.zeros((K, B), np.int64)
+    kinds = np.full((K, B), syn.EVENT_IDLE, np.int8)
+    mu3 = np.zeros((K, B, 3))
+    t = np.full(B, syn.T0_US, np.int64)
+    for k in range(K):
+        tick = k // 3 + 1
+        gyro, acc = syn.orientation_imu(B, tick)
+        act = (np.arange(B) + k) % 5 != 4
+        kind, z, step = ((11, gyro, 400), (12, acc, 0), (9, syn.orientation_velocity(B, tick)[0], 600))[k % 3]
+        t = np.where(act, t + step, t)
+        ts[k], kinds[k], mu3[k] = t, np.where(act, kind, syn.EVENT_IDLE), z
+    x.run_events(ts, kinds, mu3, syn.sensor_cov_table())
+
+
 SCENARIOS = {
     "pose_c3": (0, 16, scenario_pose_c3),
     "pose_all_kinds": (0, 9, scenario_pose_all_kinds),
     "pose_acceleration": (0, 6, scenario_pose_acceleration),
     "ori_stream": (1, 4, scenario_ori_stream),
     "ori_c1_10k": (1, 1, scenario_ori_c1_10k),
+    "pose_c5_events": (0, 12, scenario_pose_c5_events),
+    "pose_gate": (0, 9, scenario_pose_gate),
+    "ori_events": (1, 7, scenario_ori_events),
 }
 
 
@@ -123,6 +165,34 @@ class NumpyBatch:
     def set_rotation_rate(self, mu, cov=None, mask=None):
         for b, f in enumerate(self.f):
             f.gyro = np.array(mu[b], float)
+
+    def set_mahalanobis_gate(self, max_d2):
+        for f in self.f:
+            f.ukf.accept_max_d2 = float(max_d2)
+
+    def run_events(self, ts, kinds, mu3, cov):
+        """the caller loop of the reference, filter by filter: predictionStepFromSampleTime, then integrateMeasurement"""
+        K = ts.shape[0]
+        for b, f in enumerate(self.f):
+            for k in range(K):
+                kind = int(kinds[k, b])
+                if kind == syn.EVENT_IDLE:
+                    continue
+                f.predict_time(int(ts[k, b]))
+                if kind < 0:
+                    continue
+                R = cov[kind] if cov.shape == (13, 3, 3) else cov[k, b].reshape(3, 3)
+                m = {1: 2, 5: 2, 7: 2, 2: 1, 6: 1}.get(kind, 3)
+                if kind == 10:
+                    f.set_acceleration(mu3[k, b], R)
+                elif kind == 11:
+                    f.gyro = np.array(mu3[k, b], float)
+                elif kind == 12:
+                    f.acc = np.array(mu3[k, b], float)
+                elif kind == 9:
+                    f.update_velocity(mu3[k, b], R)
+                else:
+                    f.update(kind, mu3[k, b, :m], R[:m, :m])
 
     def get_state(self):
         return np.stack([f.ukf.mu for f in self.f]), np.stack([f.ukf.sigma for f in self.f])
