@@ -34,7 +34,6 @@
 #define UKFB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define UKFB_SMEM_DECL extern __shared__ __align__(16) double ukfb_smem[];
 #define UKFB_LDG(p) __ldg(p)
-#define UKFB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define UKFB_UNROLL _Pragma("unroll")
 #define UKFB_NOUNROLL _Pragma("unroll 1")
 
@@ -105,7 +104,6 @@ UKFB_D void fast_sqrt_rsqrt(double x, double& s, double& r)
 #define UKFB_LAUNCH_BOUNDS(t, b)
 #define UKFB_SMEM_DECL double* ukfb_smem = ::simt_emu::smem_base();
 #define UKFB_LDG(p) (*(p))
-#define UKFB_PREFETCH_L2(p) ((void)(p))
 #define UKFB_UNROLL
 #define UKFB_NOUNROLL
 

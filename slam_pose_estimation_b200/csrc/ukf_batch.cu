@@ -65,7 +65,6 @@ struct ukfb_handle {
     double* acc_mu = nullptr;
     double* acc_cov = nullptr;
     double gate_d2 = HUGE_VAL; /* accept_any_mahalanobis_distance */
-    int sm_count = 148;
     double* gyro_mu = nullptr;
     bool initialized = false, first_init = true;
     double min_dt = UKFB_DEFAULT_MIN_DT, max_dt = DBL_MAX;
@@ -439,18 +438,7 @@ static cudaError_t launch_fast(K kernel, int per_lane, const ukfb_handle* h, con
         attr_set[h->device & 63] = true;
     }
     const long long tiles = (p.B + TILE - 1) / TILE;
-    long long grid = (tiles + wpb - 1) / wpb;
-    /* persistent warps: 8 resident warps per SM (registers and shared memory both allow exactly that); UKFB_PERSIST=0
-     * launches one warp per tile instead */
-    static int persist = -1;
-    if (persist < 0) {
-        const char* e = getenv("UKFB_PERSIST");
-        persist = e ? atoi(e) : 1;
-    }
-    if (persist) {
-        const long long resident = (long long)h->sm_count * 8 / wpb;
-        if (grid > resident) grid = resident;
-    }
+    const long long grid = (tiles + wpb - 1) / wpb; /* warps past the last tile return at once */
     kernel<<<unsigned(grid), TILE * wpb, smem, h->stream>>>(p);
     return cudaGetLastError();
 }
@@ -537,7 +525,6 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
     if (!h) return fail(UKFB_ERR_NOMEM, "ukfb_create: out of host memory");
     h->kind = filter_kind;
     h->device = device;
-    h->sm_count = prop.multiProcessorCount;
     h->B = batch;
     if (filter_kind == UKFB_POSE)
         h->n = PoseF::N, h->MU = PoseF::MU, h->LP = PoseF::LP, h->REC = PoseF::REC;

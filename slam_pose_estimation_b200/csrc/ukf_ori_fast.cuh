@@ -804,10 +804,16 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
-/* one tile of 32 filters through K ticks; lane = this thread's filter inside the tile */
-UKFB_D void ukf_ori_fast_tile(const StepParams& p, double* sm, const int lane, const long long tile)
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef OriF F;
+    UKFB_SMEM_DECL
+    /* a block is 1..4 independent warps (no barrier between them: warps of one block merely start together, which keeps
+     * their instruction fetches close); each warp owns one tile of 32 filters and its own slice of shared memory */
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    double* sm = ukfb_smem + wib * (OF_PER_LANE * TILE);
+    if (tile * TILE >= p.B) return; /* a warp past the last tile (no barriers in this kernel) */
     const long long b = tile * TILE + lane;
     const bool valid = b < p.B;
     const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
@@ -1026,26 +1032,6 @@ UKFB_D void ukf_ori_fast_tile(const StepParams& p, double* sm, const int lane, c
         UKFB_UNROLL
         for (int k = 1; k < 8; ++k)
             if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);
-    }
-}
-
-/* ---- the kernel: persistent warps, each steps whole tiles ---------------------------------------------------------
- * A block is 1..4 independent warps (no barrier anywhere); every warp has its own slice of shared memory and walks
- * the tiles warp_id, warp_id + total_warps, ...  While a tile is being stepped the record of the warp's next tile is
- * prefetched into L2, so that only the first tile of a warp pays the DRAM latency of its loads. */
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
-{
-    UKFB_SMEM_DECL
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* sm = ukfb_smem + wib * (OF_PER_LANE * TILE);
-    const long long ntiles = (p.B + TILE - 1) / TILE, stride = (long long)gridDim.x * wpb;
-    for (long long tile = (long long)blockIdx.x * wpb + wib; tile < ntiles; tile += stride) {
-        if (tile + stride < ntiles) {
-            const double* nxt = p.state + (tile + stride) * (TILE * OriF::REC) + lane;
-            UKFB_UNROLL
-            for (int e = 0; e < OriF::REC; ++e) UKFB_PREFETCH_L2(nxt + e * TILE);
-        }
-        ukf_ori_fast_tile(p, sm, lane, tile);
     }
 }
 

@@ -5,8 +5,6 @@
  * nothing in the product links or loads this.
  */
 #define UKFB_SIMT_EMU 1
-#include <cstdlib>
-
 #include "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"
 #include "../../slam_pose_estimation_b200/csrc/ukf_thread.cuh"
 #include "../../slam_pose_estimation_b200/csrc/ukf_pose_fast.cuh"
@@ -54,18 +52,9 @@ extern "C" int emu_thread_step(int filter_kind, const StepParams* p)
 }
 
 /* the structure-exploiting PoseUKF kernel (ukf_pose_fast.cuh), same tiles */
-/* the fast kernels walk tiles with persistent warps: EMU_GRID_CAP (set by a test) caps the grid so that one warp
- * steps several tiles, as it does on the GPU for large batches */
-static unsigned capped(unsigned grid)
-{
-    const char* e = getenv("EMU_GRID_CAP");
-    const unsigned cap = e ? unsigned(atoi(e)) : 0u;
-    return (cap && grid > cap) ? cap : grid;
-}
-
 extern "C" int emu_pose_fast_step(const StepParams* p)
 {
-    const unsigned grid = capped(unsigned((p->B + TILE - 1) / TILE));
+    const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
     simt_emu::launch(ukf_pose_fast_kernel, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
     return 0;
 }
@@ -78,7 +67,7 @@ extern "C" void emu_pose_fast_fallbacks(unsigned long long* out3)
 /* the structure-exploiting OrientationUKF kernel (ukf_ori_fast.cuh), same tiles */
 extern "C" int emu_ori_fast_step(const StepParams* p)
 {
-    const unsigned grid = capped(unsigned((p->B + TILE - 1) / TILE));
+    const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
     simt_emu::launch(ukf_ori_fast_kernel, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
     return 0;
 }

@@ -228,22 +228,3 @@ def test_orientation_not_spd_leaves_the_filter_untouched(kernel):
         assert np.array_equal(e.get_state()[0][1], mu[1]) and np.array_equal(np.tril(e.get_state()[1][1]), np.tril(sg[1]))
         P.assert_parity(1, (e.get_state()[0][[0, 2]], e.get_state()[1][[0, 2]]),
                         (o.get_state()[0][[0, 2]], o.get_state()[1][[0, 2]]), tol=TOL, what="neighbours of a non-SPD filter")
-
-
-@pytest.mark.parametrize("kind", [0, 1])
-def test_persistent_warps_walk_several_tiles(kind, monkeypatch):
-    """the fast kernels run a fixed number of resident warps, each stepping the tiles w, w + W, ...: with the grid
-    capped at 2 warps, 5 tiles (one ragged) are stepped by two warps and must equal the oracle filter by filter"""
-    monkeypatch.setenv("EMU_GRID_CAP", "2")
-    B = 4 * 32 + 9
-    if kind == 0:
-        o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel="fast")
-        P.run_pose_c3(o, B, 10)
-        P.run_pose_c3(e, B, 10)
-    else:
-        o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel="fast")
-        P.run_ori_c1(o, B, 6, every=3)
-        P.run_ori_c1(e, B, 6, every=3)
-    P.assert_parity(kind, e.get_state(), o.get_state(), tol=TOL, what="persistent warps")
-    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
-    assert not e.get_status().any()
