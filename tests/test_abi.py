@@ -83,3 +83,36 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(base, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """the boundary is a C ABI: a C99 translation unit includes the header, links libukfb.so and gets the documented
+    refusal (UKFB_ERR_CUDA) or a working handle, with no C++ or Python in between"""
+    import subprocess
+
+    from slam_pose_estimation_b200 import _build
+
+    src = tmp_path / "abi.c"
+    src.write_text('''#include <stdio.h>
+#include <ukf_batch.h>
+int main(void) {
+    ukfb_handle* h = 0;
+    int rc = ukfb_create(UKFB_POSE, 4, 0, &h);
+    printf("%d %d %d %d\\n", rc, ukfb_meas_dim(UKFB_MEAS_POSE_XY), UKFB_RBS_DOUBLES, UKFB_EVENT_KIND_COUNT);
+    if (rc == UKFB_OK) { printf("%d %d\\n", ukfb_dof(h), ukfb_mu_size(h)); ukfb_destroy(h); }
+    else printf("%s\\n", ukfb_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_build.LIB)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lukfb", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    rc, m, rbs, nk = (int(v) for v in out[0].split())
+    assert (m, rbs, nk) == (2, 49, 13)
+    assert rc in (0, -3)
+    if rc == 0:
+        assert out[1].split() == ["12", "13"]
+    else:
+        assert "CUDA" in out[1] or "device" in out[1]
