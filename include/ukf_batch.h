@@ -247,6 +247,10 @@ int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us, const int
                         const double* d_cov, int cov_mode);
 int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3,
                     const double* cov, int cov_mode);
+/* the same, enqueue only (rules of ukfb_step_async: pinned host arrays that stay valid until ukfb_synchronize; the
+ * queues of the next window are copied while the current one is being integrated) */
+int ukfb_run_events_async(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3,
+                          const double* cov, int cov_mode);
 
 /* ---- status ------------------------------------------------------------------ */
 

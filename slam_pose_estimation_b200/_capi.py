@@ -60,6 +60,7 @@ SIGNATURES = {
     "ukfb_run_dev": (I, [P, I, P, I, P, P, P, I, P]),
     "ukfb_run_events_dev": (I, [P, I, P, P, P, P, I]),
     "ukfb_run_events": (I, [P, I, P, P, P, P, I]),
+    "ukfb_run_events_async": (I, [P, I, P, P, P, P, I]),
     "ukfb_get_status": (I, [P, P]),
     "ukfb_clear_status": (I, [P]),
     "ukfb_status_summary": (I, [P, C.POINTER(L), C.POINTER(C.c_uint32)]),

@@ -282,6 +282,17 @@ class UkfBatch:
         assert not per_event or cov.size == K * self.B * 9
         self._chk(self.lib.ukfb_run_events(self.h, K, pt, pk, pm, pc, 1 if per_event else 0))
 
+    def run_events_async(self, ts, kinds, mu3, cov):
+        """ukfb_run_events_async: enqueue only; pass pinned C-contiguous arrays and keep them unchanged until synchronize()"""
+        ts, pt = _host(ts, np.int64)
+        kinds, pk = _host(kinds, np.int8)
+        mu3, pm = _host(mu3, np.float64)
+        cov, pc = _host(cov, np.float64)
+        K = ts.size // self.B
+        per_event = cov.shape != (13, 3, 3)
+        self._inflight.append((ts, kinds, mu3, cov))
+        self._chk(self.lib.ukfb_run_events_async(self.h, K, pt, pk, pm, pc, 1 if per_event else 0))
+
     def run_events_dev(self, K: int, d_ts, d_kinds, d_mu3, d_cov, per_event: bool):
         self._chk(self.lib.ukfb_run_events_dev(self.h, int(K), _dev(d_ts), _dev(d_kinds), _dev(d_mu3), _dev(d_cov),
                                                1 if per_event else 0))

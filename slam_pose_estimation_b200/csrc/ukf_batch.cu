@@ -1342,6 +1342,41 @@ extern "C" int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, cons
     return UKFB_OK;
 }
 
+/* ukfb_run_events without the final synchronisation: the queues travel on the copy-in stream into one of the two
+ * staging slots while the previous launch runs (same slots and rules as ukfb_step_async) */
+extern "C" int ukfb_run_events_async(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3,
+                                     const double* cov, int cov_mode)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: K must be >= 1");
+    if (!ts_us || !kinds || !mu3 || !cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: null argument");
+    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: cov_mode must be 0 (per-kind table) or 1 (per event)");
+    int rc = pipe_make(h);
+    if (rc) return rc;
+    const int slot = int(h->pipe.n_in & 1);
+    const size_t n = size_t(K) * size_t(h->B);
+    const size_t bt = align256(sizeof(int64_t) * n), bk = align256(n), bm = align256(sizeof(double) * n * 3);
+    const size_t bc = sizeof(double) * (cov_mode ? n * 9 : size_t(UKFB_EVENT_KIND_COUNT) * 9);
+    rc = pipe_reserve(h, &h->pipe.in[slot], &h->pipe.in_bytes[slot], bt + bk + bm + bc);
+    if (rc) return rc;
+    char* base = h->pipe.in[slot];
+    cudaStream_t si = h->pipe.s_in;
+    if (h->pipe.n_in >= 2) CU(cudaStreamWaitEvent(si, h->pipe.in_consumed[slot], 0)); /* the launch that read this slot is done */
+    CU(cudaMemcpyAsync(base, ts_us, sizeof(int64_t) * n, cudaMemcpyHostToDevice, si));
+    CU(cudaMemcpyAsync(base + bt, kinds, n, cudaMemcpyHostToDevice, si));
+    CU(cudaMemcpyAsync(base + bt + bk, mu3, sizeof(double) * n * 3, cudaMemcpyHostToDevice, si));
+    CU(cudaMemcpyAsync(base + bt + bk + bm, cov, bc, cudaMemcpyHostToDevice, si));
+    CU(cudaEventRecord(h->pipe.in_ready[slot], si));
+    CU(cudaStreamWaitEvent(h->stream, h->pipe.in_ready[slot], 0));
+    rc = ukfb_run_events_dev(h, K, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const int8_t*>(base + bt),
+                             reinterpret_cast<const double*>(base + bt + bk), reinterpret_cast<const double*>(base + bt + bk + bm), cov_mode);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->pipe.in_consumed[slot], h->stream));
+    h->pipe.n_in++;
+    return UKFB_OK;
+}
+
 /* ---- status ------------------------------------------------------------------------------------------------ */
 extern "C" int ukfb_get_status(ukfb_handle* h, uint32_t* flags)
 {

@@ -162,3 +162,27 @@ def test_gpu_event_queue_equals_single_calls():
     ma, sa = a.get_state()
     mb, sb = b.get_state()
     assert np.array_equal(ma, mb) and np.array_equal(sa, sb)
+
+
+@pytest.mark.gpu
+def test_gpu_event_queue_streaming_calls():
+    """ukfb_run_events_async + ukfb_get_state_async over three windows == the blocking calls, bit for bit"""
+    import torch
+    from slam_pose_estimation_b200 import UkfBatch
+    B = 70
+    ts, kinds, mu3, tab = c5(B, 18)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    K = ts.shape[0]
+    cuts = [0, K // 3, 2 * K // 3, K]
+    a, b = P.make_pose(UkfBatch, B), P.make_pose(UkfBatch, B)
+    outs = [pin(np.zeros((B, 13))) for _ in range(3)]
+    tabp = pin(tab)
+    parts = [(pin(ts[lo:hi]), pin(kinds[lo:hi]), pin(mu3[lo:hi])) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    for i, (t, k, m) in enumerate(parts):
+        a.run_events_async(t, k, m, tabp)
+        a.get_state_async(outs[i])
+    a.synchronize()
+    for i, (t, k, m) in enumerate(parts):
+        b.run_events(t, k, m, tab)
+        assert np.array_equal(outs[i], b.get_state()[0])
+    assert np.array_equal(a.get_state()[1], b.get_state()[1])
