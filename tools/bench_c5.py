@@ -85,9 +85,16 @@ def main():
         f.synchronize()
         for a in ts_h:
             a += nrep * period
+        for r in range(2):  # warm-up: the pipeline's staging slots are allocated on first use
+            f.run_events_async(ts_h[r], kinds_h, mu3_h, tab)
+            f.get_state_async(out[r & 1])
+        f.synchronize()
+        ts_h[0] += nrep * period
+        ts_h[1] += nrep * period
+        order = [2, 3, 0, 1]
         t0 = time.perf_counter()
         for r in range(nrep):
-            f.run_events_async(ts_h[r], kinds_h, mu3_h, tab)
+            f.run_events_async(ts_h[order[r]], kinds_h, mu3_h, tab)
             f.get_state_async(out[r & 1])
         f.synchronize()
         ms_e2e = (time.perf_counter() - t0) * 1e3 / nrep
