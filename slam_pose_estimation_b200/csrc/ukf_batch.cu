@@ -431,7 +431,15 @@ template <class K>
 static cudaError_t launch_fast(K kernel, int per_lane, const ukfb_handle* h, const StepParams& p, bool* attr_set)
 {
     const int wpb = fast_wpb();
-    const size_t smem = sizeof(double) * per_lane * TILE * wpb;
+    size_t smem = sizeof(double) * per_lane * TILE * wpb;
+    {   /* occupancy experiments: UKFB_SMEM_PAD_KB adds unused dynamic shared memory per block (fewer resident warps) */
+        static long pad = -1;
+        if (pad < 0) {
+            const char* e = getenv("UKFB_SMEM_PAD_KB");
+            pad = e ? atol(e) : 0;
+        }
+        smem += size_t(pad) * 1024;
+    }
     if (!attr_set[h->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
