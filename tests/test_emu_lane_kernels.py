@@ -228,3 +228,30 @@ def test_orientation_not_spd_leaves_the_filter_untouched(kernel):
         assert np.array_equal(e.get_state()[0][1], mu[1]) and np.array_equal(np.tril(e.get_state()[1][1]), np.tril(sg[1]))
         P.assert_parity(1, (e.get_state()[0][[0, 2]], e.get_state()[1][[0, 2]]),
                         (o.get_state()[0][[0, 2]], o.get_state()[1][[0, 2]]), tol=TOL, what="neighbours of a non-SPD filter")
+
+
+def test_pose_orientation_measurement_runs_the_structured_path():
+    """OrientationMeasurement (PoseUKF.cpp:133-138), the one manifold-valued measurement: the fast kernel evaluates it
+    from the 12 points that perturb the orientation; no literal fallback is taken, the measured rotation vector may be
+    any angle, and a filter far from its measurement (innovation outside the log polynomial) still falls back."""
+    B = 40
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel="fast")
+    before = e.fallbacks()
+    for k in range(1, 7):
+        z, R = syn.pose_measurement(3, B, k)
+        mu = o.get_state()[0]
+        # rotation vector of the current estimate plus noise: large absolute angles, small innovations
+        q = mu[:, 3:7]
+        ang = 2.0 * np.arctan2(np.linalg.norm(q[:, :3], axis=1), q[:, 3])
+        axis = q[:, :3] / np.maximum(np.linalg.norm(q[:, :3], axis=1, keepdims=True), 1e-300)
+        zz = axis * ang[:, None] + (z - z.mean(axis=0)) * 0.5
+        for x in (o, e):
+            x.step(syn.DT * 5, 3, zz, R)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what="orientation measurement, structured path")
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert not (e.fallbacks() - before).any(), e.fallbacks() - before
+    far = np.tile([0.0, 0.0, 2.5], (B, 1))  # 2.5 rad away from every estimate: the innovation leaves the polynomial
+    for x in (o, e):
+        x.step(syn.DT, 3, far, np.eye(3) * 1e-2)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=1e-10, what="orientation measurement, far innovation")
+    assert (e.fallbacks() - before)[1] > 0
