@@ -542,129 +542,6 @@ UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
     return r;
 }
 
-/* ---- first half of the update with the orientation measurement (PoseUKF.cpp:28-33, 133-138), out of line so that the
- * selector kinds' code is not scheduled around it.  Slots 0..77 hold the prior covariance. */
-struct PfOriMeas {
-    double Sxz[36], S[9], innov[3];
-    uint32_t status;
-    bool spd, slow;
-};
-
-UKFB_DNI PfOriMeas pf_orientation_first_half(double* sm, int lane, const double* q, const double* zm, const double* Rmeas, int r_ld)
-{
-    PfOriMeas o;
-    o.status = 0, o.spd = true, o.slow = false;
-    /* h(X) = orientation (PoseUKF.cpp:28-33), a manifold-valued measurement: Z_p = exp(+-L_ori[:,j]) q for the 12
-     * points of columns 0..5, q for X0 and the other 12.  zbar by the iterative SO(3) mean, S = 1/2 sum dz dz^T + R,
-     * Sxz = 1/2 sum_{j<6} L[:,j] (dz+_j - dz-_j)^T (deviations from the prior mu are +-L[:,j] exactly under the
-     * trace guard), innovation = exp(z) [-] zbar (PoseUKF.cpp:135). */
-    bool slow = false;
-    double a[PoseF::LP];
-    UKFB_UNROLL
-    for (int e = 0; e < PoseF::LP; ++e) a[e] = UKFB_PS(e);
-    o.spd = pf_cholesky<6>(a);
-    if (!o.spd) return o;
-    constexpr int PF_E = 78; /* exp(L_ori[:,j]), then dz+_j - dz-_j, in the slots above the packed covariance */
-    UKFB_UNROLL
-    for (int j = 0; j < 6; ++j) {
-        double e[4];
-        const double Lo[3] = {j <= 3 ? a[tri(3, j <= 3 ? j : 3)] : 0.0, j <= 4 ? a[tri(4, j <= 4 ? j : 4)] : 0.0, a[tri(5, j)]};
-        pf_exp(Lo, 1.0, e, slow);
-        UKFB_UNROLL
-        for (int i = 0; i < 4; ++i) UKFB_PS(PF_E + 4 * j + i) = e[i];
-    }
-    double zin[4];
-    {
-        const double v[3] = {zm[0], zm[1], zm[2]};
-        so3_exp(v, 1.0, zin); /* the measured rotation vector may be any angle: the general exp (PoseUKF.cpp:135) */
-    }
-    double zref[4] = {q[0], q[1], q[2], q[3]};
-    int it = 0;
-    while (!slow) {
-        double c[4], d0[3], md[3];
-        quat_mul_conj(q, zref, c);
-        pf_log(c, d0, slow);
-        md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
-        UKFB_NOUNROLL
-        for (int j = 0; j < 6; ++j) {
-            double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
-            UKFB_UNROLL
-            for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
-            en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
-            quat_mul(e, c, rp);
-            quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
-            md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
-        }
-        UKFB_UNROLL
-        for (int i = 0; i < 3; ++i) md[i] = div_ns<PoseF::NS>(md[i]);
-        const double n2 = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
-        {
-            double e[4], rr[4];
-            pf_exp(md, 1.0, e, slow);
-            quat_mul(e, zref, rr);
-            zref[0] = rr[0], zref[1] = rr[1], zref[2] = rr[2], zref[3] = rr[3];
-        }
-        if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
-        if (++it >= UKFB_MEAN_MAX_IT) {
-            o.status |= UKFB_STATUS_MEAN_NO_CONVERGE;
-            break;
-        }
-    }
-    {
-        double c[4], d0[3];
-        quat_mul_conj(q, zref, c);
-        pf_log(c, d0, slow);
-        UKFB_UNROLL
-        for (int r = 0; r < 3; ++r) {
-            UKFB_UNROLL
-            for (int cc = 0; cc < 3; ++cc) o.S[r * 3 + cc] = 13.0 * d0[r] * d0[cc];
-        }
-        UKFB_NOUNROLL
-        for (int j = 0; j < 6; ++j) {
-            double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
-            UKFB_UNROLL
-            for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
-            en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
-            quat_mul(e, c, rp);
-            quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
-            UKFB_UNROLL
-            for (int r = 0; r < 3; ++r) {
-                UKFB_UNROLL
-                for (int cc = 0; cc < 3; ++cc) o.S[r * 3 + cc] = fma(dp[r], dp[cc], fma(dn[r], dn[cc], o.S[r * 3 + cc]));
-                UKFB_PS(PF_E + 4 * j + r) = dp[r] - dn[r];
-            }
-        }
-        double r4[4];
-        quat_mul_conj(zin, zref, r4);
-        pf_log(r4, o.innov, slow);
-    }
-    o.slow = slow;
-    if (slow) return o;
-    UKFB_UNROLL
-    for (int r = 0; r < 3; ++r) {
-        UKFB_UNROLL
-        for (int cc = 0; cc < 3; ++cc) o.S[r * 3 + cc] = fma(0.5, o.S[r * 3 + cc], Rmeas[r * r_ld + cc]);
-    }
-    UKFB_UNROLL
-    for (int i = 0; i < 36; ++i) o.Sxz[i] = 0.0;
-    UKFB_UNROLL
-    for (int j = 0; j < 6; ++j) {
-        UKFB_UNROLL
-        for (int cc = 0; cc < 3; ++cc) {
-            const double ddz = UKFB_PS(PF_E + 4 * j + cc);
-            UKFB_UNROLL
-            for (int i = j; i < 12; ++i) o.Sxz[i * 3 + cc] = fma(a[tri(i, j)], ddz, o.Sxz[i * 3 + cc]);
-        }
-    }
-    UKFB_UNROLL
-    for (int i = 0; i < 36; ++i) o.Sxz[i] *= 0.5;
-    return o;
-}
-
 /* ---- structured update with a selector measurement.  Slots 0..77 hold the prior covariance (packed lower), which
  * is also in the record.  Returns false when apply_delta left the polynomial range: the record then holds
  * Sigma - K S K^T, `delta` = K innov, m is untouched. */
@@ -679,16 +556,113 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
 
     double Sxz[36], S[9], innov[3];
     if (kind == UKFB_MEAS_POSE_ORIENTATION) {
-        const PfOriMeas o = pf_orientation_first_half(sm, lane, m.q, zm, Rmeas, r_ld);
-        status |= o.status;
-        spd = o.spd;
-        if (!o.spd) return true;
-        if (o.slow) return false; /* stage 0: the caller runs the whole literal update */
+        /* h(X) = orientation (PoseUKF.cpp:28-33), a manifold-valued measurement: Z_p = exp(+-L_ori[:,j]) q for the 12
+         * points of columns 0..5, q for X0 and the other 12.  zbar by the iterative SO(3) mean, S = 1/2 sum dz dz^T + R,
+         * Sxz = 1/2 sum_{j<6} L[:,j] (dz+_j - dz-_j)^T (deviations from the prior mu are +-L[:,j] exactly under the
+         * trace guard), innovation = exp(z) [-] zbar (PoseUKF.cpp:135). */
+        bool slow = false;
+        double a[PoseF::LP];
         UKFB_UNROLL
-        for (int i = 0; i < 36; ++i) Sxz[i] = o.Sxz[i];
+        for (int e = 0; e < PoseF::LP; ++e) a[e] = UKFB_PS(e);
+        spd = pf_cholesky<6>(a);
+        if (!spd) return true;
+        constexpr int PF_E = 78; /* exp(L_ori[:,j]), then dz+_j - dz-_j, in the slots above the packed covariance */
         UKFB_UNROLL
-        for (int i = 0; i < 9; ++i) S[i] = o.S[i];
-        innov[0] = o.innov[0], innov[1] = o.innov[1], innov[2] = o.innov[2];
+        for (int j = 0; j < 6; ++j) {
+            double e[4];
+            const double Lo[3] = {j <= 3 ? a[tri(3, j <= 3 ? j : 3)] : 0.0, j <= 4 ? a[tri(4, j <= 4 ? j : 4)] : 0.0, a[tri(5, j)]};
+            pf_exp(Lo, 1.0, e, slow);
+            UKFB_UNROLL
+            for (int i = 0; i < 4; ++i) UKFB_PS(PF_E + 4 * j + i) = e[i];
+        }
+        double zin[4];
+        {
+            const double v[3] = {zm[0], zm[1], zm[2]};
+            so3_exp(v, 1.0, zin); /* the measured rotation vector may be any angle: the general exp (PoseUKF.cpp:135) */
+        }
+        double zref[4] = {m.q[0], m.q[1], m.q[2], m.q[3]};
+        int it = 0;
+        while (!slow) {
+            double c[4], d0[3], md[3];
+            quat_mul_conj(m.q, zref, c);
+            pf_log(c, d0, slow);
+            md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
+            UKFB_NOUNROLL
+            for (int j = 0; j < 6; ++j) {
+                double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
+                UKFB_UNROLL
+                for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
+                en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
+                quat_mul(e, c, rp);
+                quat_mul(en, c, rn);
+                pf_log(rp, dp, slow);
+                pf_log(rn, dn, slow);
+                md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
+            }
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) md[i] = div_ns<PoseF::NS>(md[i]);
+            const double n2 = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
+            {
+                double e[4], rr[4];
+                pf_exp(md, 1.0, e, slow);
+                quat_mul(e, zref, rr);
+                zref[0] = rr[0], zref[1] = rr[1], zref[2] = rr[2], zref[3] = rr[3];
+            }
+            if (!(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
+            if (++it >= UKFB_MEAN_MAX_IT) {
+                status |= UKFB_STATUS_MEAN_NO_CONVERGE;
+                break;
+            }
+        }
+        {
+            double c[4], d0[3];
+            quat_mul_conj(m.q, zref, c);
+            pf_log(c, d0, slow);
+            UKFB_UNROLL
+            for (int r = 0; r < 3; ++r) {
+                UKFB_UNROLL
+                for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = 13.0 * d0[r] * d0[cc];
+            }
+            UKFB_NOUNROLL
+            for (int j = 0; j < 6; ++j) {
+                double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
+                UKFB_UNROLL
+                for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
+                en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
+                quat_mul(e, c, rp);
+                quat_mul(en, c, rn);
+                pf_log(rp, dp, slow);
+                pf_log(rn, dn, slow);
+                UKFB_UNROLL
+                for (int r = 0; r < 3; ++r) {
+                    UKFB_UNROLL
+                    for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = fma(dp[r], dp[cc], fma(dn[r], dn[cc], S[r * 3 + cc]));
+                    UKFB_PS(PF_E + 4 * j + r) = dp[r] - dn[r];
+                }
+            }
+            double r4[4];
+            quat_mul_conj(zin, zref, r4);
+            pf_log(r4, innov, slow);
+        }
+        if (slow) return false; /* stage 0: the caller runs the whole literal update */
+        UKFB_UNROLL
+        for (int r = 0; r < 3; ++r) {
+            UKFB_UNROLL
+            for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = fma(0.5, S[r * 3 + cc], Rmeas[r * r_ld + cc]);
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 36; ++i) Sxz[i] = 0.0;
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) {
+            UKFB_UNROLL
+            for (int cc = 0; cc < 3; ++cc) {
+                const double ddz = UKFB_PS(PF_E + 4 * j + cc);
+                UKFB_UNROLL
+                for (int i = j; i < 12; ++i) Sxz[i * 3 + cc] = fma(a[tri(i, j)], ddz, Sxz[i * 3 + cc]);
+            }
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 36; ++i) Sxz[i] *= 0.5;
     } else {
     /* S = Sigma[sel,sel] + R, Sxz = Sigma[:,sel] (identity / zero padded to 3 like the reference's 3-vectors) */
     UKFB_UNROLL
