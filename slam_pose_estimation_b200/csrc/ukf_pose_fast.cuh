@@ -545,6 +545,7 @@ UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
 /* ---- structured update with a selector measurement.  Slots 0..77 hold the prior covariance (packed lower), which
  * is also in the record.  Returns false when apply_delta left the polynomial range: the record then holds
  * Sigma - K S K^T, `delta` = K innov, m is untouched. */
+template <bool ORI_MEAS>
 UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rmeas, int r_ld, PoseMu& m,
                       double* delta, uint32_t& status, int& passes_out, bool& spd, double gate_d2, int& stage)
 {
@@ -555,7 +556,7 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
     for (int c = 0; c < 3; ++c) sel[c] = pf_sel(kind, c);
 
     double Sxz[36], S[9], innov[3];
-    if (kind == UKFB_MEAS_POSE_ORIENTATION) {
+    if (ORI_MEAS) {
         /* h(X) = orientation (PoseUKF.cpp:28-33), a manifold-valued measurement: Z_p = exp(+-L_ori[:,j]) q for the 12
          * points of columns 0..5, q for X0 and the other 12.  zbar by the iterative SO(3) mean, S = 1/2 sum dz dz^T + R,
          * Sxz = 1/2 sum_{j<6} L[:,j] (dz+_j - dz-_j)^T (deviations from the prior mu are +-L[:,j] exactly under the
@@ -878,6 +879,28 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
     return true;
 }
 
+/* the update with the orientation measurement, out of line (called where few registers are live, like the literal
+ * fallbacks), so that the selector kinds' instance of pf_update carries none of its code */
+struct PfUpd {
+    PoseMu m;
+    double delta[12];
+    uint32_t status;
+    int passes, stage;
+    bool spd, done;
+};
+
+UKFB_DNI PfUpd pf_update_orientation(double* sm, int lane, double* sig, const double* zm, const double* Rmeas, int r_ld, PoseMu m,
+                                     double gate_d2)
+{
+    PfUpd r;
+    r.m = m, r.status = 0, r.passes = 0, r.stage = 0, r.spd = true;
+    UKFB_UNROLL
+    for (int i = 0; i < 12; ++i) r.delta[i] = 0.0;
+    r.done = pf_update<true>(sm, lane, sig, UKFB_MEAS_POSE_ORIENTATION, zm, Rmeas, r_ld, r.m, r.delta, r.status, r.passes, r.spd, gate_d2,
+                             r.stage);
+    return r;
+}
+
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
@@ -1053,7 +1076,15 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
                 UKFB_UNROLL
                 for (int i = 0; i < 12; ++i) delta[i] = 0.0;
                 if (!literal) {
-                    fast_done = pf_update(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd, p.gate_d2, stage);
+                    if (kind == UKFB_MEAS_POSE_ORIENTATION) {
+                        const PfUpd r = pf_update_orientation(sm, lane, sig, zm, Rmeas, p.r_ld, m, p.gate_d2);
+                        fast_done = r.done, spd = r.spd, stage = r.stage, passes_b = r.passes;
+                        status |= r.status;
+                        UKFB_UNROLL
+                        for (int i = 0; i < 12; ++i) delta[i] = r.delta[i];
+                        if (r.done && r.spd) m = r.m;
+                    } else
+                        fast_done = pf_update<false>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd, p.gate_d2, stage);
                     if (fast_done) {
                         if (!spd)
                             status |= UKFB_STATUS_NOT_SPD;
