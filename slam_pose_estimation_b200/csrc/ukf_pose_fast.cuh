@@ -565,7 +565,7 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
         double a[PoseF::LP];
         UKFB_UNROLL
         for (int e = 0; e < PoseF::LP; ++e) a[e] = UKFB_PS(e);
-        spd = pf_cholesky<6>(a);
+        spd = pf_cholesky<12>(a); /* all of it, as the reference does before an update: NOT_SPD is reported here */
         if (!spd) return true;
         constexpr int PF_E = 78; /* exp(L_ori[:,j]), then dz+_j - dz-_j, in the slots above the packed covariance */
         UKFB_UNROLL
@@ -879,26 +879,33 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
     return true;
 }
 
-/* the update with the orientation measurement, out of line (called where few registers are live, like the literal
- * fallbacks), so that the selector kinds' instance of pf_update carries none of its code */
-struct PfUpd {
-    PoseMu m;
-    double delta[12];
-    uint32_t status;
-    int passes, stage;
-    bool spd, done;
-};
-
-UKFB_DNI PfUpd pf_update_orientation(double* sm, int lane, double* sig, const double* zm, const double* Rmeas, int r_ld, PoseMu m,
-                                     double gate_d2)
+/* Everything the selector kinds' structured update does not do, out of line (one call site, where few registers are
+ * live): the update with the orientation measurement -- its own structured instance pf_update<true>, tried first -- and
+ * the literal code of ukf_thread.cuh for lanes that failed a guard or left a polynomial range.
+ * first = true: nothing has been modified yet; false: the record holds Sigma - K S K^T and `delta` = K innov. */
+UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma,
+                              PoseMu m, PfDelta delta, bool first, double gate_d2)
 {
-    PfUpd r;
-    r.m = m, r.status = 0, r.passes = 0, r.stage = 0, r.spd = true;
-    UKFB_UNROLL
-    for (int i = 0; i < 12; ++i) r.delta[i] = 0.0;
-    r.done = pf_update<true>(sm, lane, sig, UKFB_MEAS_POSE_ORIENTATION, zm, Rmeas, r_ld, r.m, r.delta, r.status, r.passes, r.spd, gate_d2,
-                             r.stage);
-    return r;
+    if (first && kind == UKFB_MEAS_POSE_ORIENTATION) {
+        /* the prior covariance into slots 0..77, as the structured update expects it; under the trace guard
+         * (mu [+] L_j) [-] mu = L_j holds and the structured instance applies */
+        UKFB_UNROLL
+        for (int e = 0; e < PoseF::LP; ++e) UKFB_PS(e) = sig[e * TILE];
+        const double tr = UKFB_PS(tri(3, 3)) + UKFB_PS(tri(4, 4)) + UKFB_PS(tri(5, 5));
+        if (tr < PF_PI2_GUARD) {
+            PfLit r;
+            r.m = m, r.status = 0, r.passes = 0;
+            bool spd = true;
+            int stage = 0;
+            const bool done = pf_update<true>(sm, lane, sig, kind, zm, Rm, r_ld, r.m, delta.d, r.status, r.passes, spd, gate_d2, stage);
+            if (done) {
+                if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+                return r;
+            }
+            first = stage == 0; /* a polynomial range was left: literal from where the structured code stopped */
+        }
+    }
+    return pf_literal_update(sig, kind, zm, Rm, r_ld, ma, m, delta, first, gate_d2);
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
@@ -1013,7 +1020,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
         if (do_pred) {
             ma.has_acc = (fabs(ma.acc[0]) <= big) && (fabs(ma.acc[1]) <= big) && (fabs(ma.acc[2]) <= big);
             bool spd = true;
-            const bool want_smem = do_upd;
+            const bool want_smem = do_upd && kind != UKFB_MEAS_POSE_ORIENTATION;
             if (pf_predict(sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
@@ -1049,8 +1056,8 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
         /* ---- update (ukfom update + apply_delta, App. A.4) --------------------------------------------------- */
         if (do_upd) {
             const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-            bool literal = false;
-            {
+            bool literal = kind == UKFB_MEAS_POSE_ORIENTATION; /* handled out of line, below */
+            if (!literal) {
                 if (!sigma_in_smem) {
                     /* no fast predict ran on this covariance in this tick: it has not been shown to be SPD yet, and the
                      * reference's update factorises it first */
@@ -1076,15 +1083,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
                 UKFB_UNROLL
                 for (int i = 0; i < 12; ++i) delta[i] = 0.0;
                 if (!literal) {
-                    if (kind == UKFB_MEAS_POSE_ORIENTATION) {
-                        const PfUpd r = pf_update_orientation(sm, lane, sig, zm, Rmeas, p.r_ld, m, p.gate_d2);
-                        fast_done = r.done, spd = r.spd, stage = r.stage, passes_b = r.passes;
-                        status |= r.status;
-                        UKFB_UNROLL
-                        for (int i = 0; i < 12; ++i) delta[i] = r.delta[i];
-                        if (r.done && r.spd) m = r.m;
-                    } else
-                        fast_done = pf_update<false>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd, p.gate_d2, stage);
+                    fast_done = pf_update<false>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, m, delta, status, passes_b, spd, p.gate_d2, stage);
                     if (fast_done) {
                         if (!spd)
                             status |= UKFB_STATUS_NOT_SPD;
@@ -1092,11 +1091,11 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
                             dirty_mu = true;
                     }
                 }
-                if (!fast_done) { /* failed guard, or a polynomial range was left (stage 0: before anything was modified) */
+                if (!fast_done) { /* orientation measurement, failed guard, or a polynomial range was left */
                     PfDelta dl;
                     UKFB_UNROLL
                     for (int i = 0; i < 12; ++i) dl.d[i] = delta[i];
-                    const PfLit r = pf_literal_update(sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal || stage == 0, p.gate_d2);
+                    const PfLit r = pf_update_slow(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal || stage == 0, p.gate_d2);
                     status |= r.status;
                     passes_b = r.passes;
                     if (!(r.status & UKFB_STATUS_NOT_SPD)) {
