@@ -65,6 +65,7 @@ struct ukfb_handle {
     double* acc_mu = nullptr;
     double* acc_cov = nullptr;
     double gate_d2 = HUGE_VAL; /* accept_any_mahalanobis_distance */
+    bool tick_kinds_have_orientation = false; /* set by ukfb_run_dev from its host-side kinds */
     double* gyro_mu = nullptr;
     bool initialized = false, first_init = true;
     double min_dt = UKFB_DEFAULT_MIN_DT, max_dt = DBL_MAX;
@@ -451,10 +452,11 @@ static cudaError_t launch_fast(K kernel, int per_lane, const ukfb_handle* h, con
     return cudaGetLastError();
 }
 
-static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p)
+static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p, bool may_have_orientation_meas)
 {
-    static bool attr_set[64] = {};
-    return launch_fast(ukf_pose_fast_kernel, PF_PER_LANE, h, p, attr_set);
+    static bool attr_set[2][64] = {};
+    if (may_have_orientation_meas) return launch_fast(ukf_pose_fast_kernel<true>, PF_PER_LANE, h, p, attr_set[1]);
+    return launch_fast(ukf_pose_fast_kernel<false>, PF_PER_LANE, h, p, attr_set[0]);
 }
 
 static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
@@ -466,8 +468,12 @@ static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
 static int launch_step(ukfb_handle* h, const StepParams& p)
 {
     cudaError_t e;
-    if (h->tiled && h->fast && h->kind == UKFB_POSE)
-        e = launch_pose_fast(h, p);
+    if (h->tiled && h->fast && h->kind == UKFB_POSE) {
+        /* can an OrientationMeasurement occur in this launch?  per-filter kinds live on the device: assume yes */
+        bool ori_meas = p.do_update && (p.kind == UKFB_MEAS_POSE_ORIENTATION || p.kind == -2 || p.events);
+        if (p.do_update && p.tick_kinds) ori_meas = h->tick_kinds_have_orientation;
+        e = launch_pose_fast(h, p, ori_meas);
+    }
     else if (h->tiled && h->fast)
         e = launch_ori_fast(h, p);
     else if (h->tiled)
@@ -1257,13 +1263,15 @@ extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_pe
     NEED_INIT(h);
     if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run: K must be >= 1");
     if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_run: null dt");
-    bool any = false;
+    bool any = false, has_ori = false;
     if (kinds_host)
         for (int k = 0; k < K; ++k) {
             if (kinds_host[k] == UKFB_MEAS_NONE) continue;
             if (!kind_ok(h, kinds_host[k])) return fail(UKFB_ERR_INVALID, "ukfb_run: kinds[%d] = %d does not belong to this filter kind", k, int(kinds_host[k]));
             any = true;
+            if (h->kind == UKFB_POSE && kinds_host[k] == UKFB_MEAS_POSE_ORIENTATION) has_ori = true;
         }
+    h->tick_kinds_have_orientation = has_ori;
     if (any && (!d_mu3 || !d_cov33)) return fail(UKFB_ERR_INVALID, "ukfb_run: null measurement stream");
     if (d_imu && h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_run: imu stream on a POSE handle");
     StepParams p = base_params(h);

@@ -883,10 +883,11 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
  * live): the update with the orientation measurement -- its own structured instance pf_update<true>, tried first -- and
  * the literal code of ukf_thread.cuh for lanes that failed a guard or left a polynomial range.
  * first = true: nothing has been modified yet; false: the record holds Sigma - K S K^T and `delta` = K innov. */
+template <bool WITH_ORI>
 UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma,
                               PoseMu m, PfDelta delta, bool first, double gate_d2)
 {
-    if (first && kind == UKFB_MEAS_POSE_ORIENTATION) {
+    if (WITH_ORI && first && kind == UKFB_MEAS_POSE_ORIENTATION) {
         /* the prior covariance into slots 0..77, as the structured update expects it; under the trace guard
          * (mu [+] L_j) [-] mu = L_j holds and the structured instance applies */
         UKFB_UNROLL
@@ -909,6 +910,11 @@ UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
+/* WITH_ORI = false: the instance the host launches when no orientation measurement can occur in the launch (a uniform
+ * kind other than 3): an orientation measurement would run the literal code.  WITH_ORI = true: its structured instance
+ * is compiled into the slow-path call; the larger callee costs the hot path about 3 % (register allocation around the
+ * call), which is why there are two instances. */
+template <bool WITH_ORI>
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef PoseF F;
@@ -1095,7 +1101,8 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
                     PfDelta dl;
                     UKFB_UNROLL
                     for (int i = 0; i < 12; ++i) dl.d[i] = delta[i];
-                    const PfLit r = pf_update_slow(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal || stage == 0, p.gate_d2);
+                    /* the selector instance only gives up after the downdate (stage 1), so `literal` alone tells the stage */
+                    const PfLit r = pf_update_slow<WITH_ORI>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal, p.gate_d2);
                     status |= r.status;
                     passes_b = r.passes;
                     if (!(r.status & UKFB_STATUS_NOT_SPD)) {

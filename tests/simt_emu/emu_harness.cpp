@@ -55,7 +55,7 @@ extern "C" int emu_thread_step(int filter_kind, const StepParams* p)
 extern "C" int emu_pose_fast_step(const StepParams* p)
 {
     const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
-    simt_emu::launch(ukf_pose_fast_kernel, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
+    simt_emu::launch(ukf_pose_fast_kernel<true>, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
     return 0;
 }
 
