@@ -19,13 +19,16 @@
  *     Z_p = mu[sel] +- L[sel,j], so zbar = mu[sel], S = Sigma[sel,sel] + R and Sigma_xz = Sigma[:,sel] exactly
  *     (valid while every |L_ori[:,j]| < pi, guaranteed by trace(Sigma_ori) < pi^2, else the literal path runs);
  *     gain, Sigma - K S K^T and delta = K innov follow the reference's expression order.
+ *   update with the orientation measurement (PoseUKF.cpp:28-33,133-138): Z_p = exp(+-L_ori[:,j]) q for columns 0..5, q
+ *     otherwise; iterative SO(3) mean, S and Sigma_xz from the 12 evaluated points (pf_update<true>, reached through the
+ *     out-of-line slow-path call of the kernel instance ukf_pose_fast_kernel<true>).
  *   apply_delta: the Euclidean components of mu [+] (delta +- L[:,j]) have mean mu + delta and deviations +-L, so
  *     the Euclidean block of the new covariance is that of Sigma - K S K^T; only the orientation rows/columns are
  *     recomputed, from the 12 points of columns 0..5 (the others carry the orientation of X_0), and only the first
  *     six columns of the second Cholesky factor are needed.
  *
  * All SO(3) exp/log calls here are the branch-free polynomial kernels of so3.cuh; a lane whose argument leaves the
- * polynomial range, an orientation measurement (kind 3) or a failed guard falls back to the literal code of
+ * polynomial range or that fails a guard falls back to the literal code of
  * ukf_thread.cuh (out of line, cold), which is also what UKFB_KERNEL=thread runs for every filter.
  * Covariance accumulators (57 / 33 doubles) and the state stay in registers, both Cholesky factorisations run in
  * registers on statically indexed arrays; shared memory ([entry][lane], conflict free) only holds the factor
