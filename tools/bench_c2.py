@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cases", default="c2,c3")
+    ap.add_argument("--update-every-tick", action="store_true", help="C2 with a velocity update on every tick")
     args = ap.parse_args()
     import torch
 
@@ -41,7 +42,7 @@ def main():
                 f.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
                 f.initialize(mu, sg)
                 f.set_process_noise(syn.ORI_Q)
-                kinds = np.full(Kc, -1, np.int8)
+                kinds = np.full(Kc, 9 if args.update_every_tick else -1, np.int8)
                 kinds[Kc - 1] = 9
                 imu = np.empty((4, B, 6))  # four distinct IMU sample sets, cycled over the ticks
                 for j in range(4):
@@ -51,7 +52,7 @@ def main():
                 z = syn.orientation_velocity(B, 1)[0]
                 d_z = torch.from_numpy(z).to(dev)[None].expand(Kc, B, 3).contiguous()
                 R = np.eye(3) * syn.SIGMA_DVL**2
-                updates = 1
+                updates = Kc if args.update_every_tick else 1
             else:
                 mu, sg = syn.pose_initial(B, perturb=True)
                 f = UkfBatch(0, B)
