@@ -265,6 +265,18 @@ def test_pose_10k_steps_run_dev(Ukf):
     assert not g.get_status().any()
 
 
+def test_pose_c3_10k_steps_mixed_updates(Ukf):
+    """north star: 1e-9 after 10k steps on the C3 schedule (angular velocity every tick, velocity every 10th, position
+    every 100th), through the single calls"""
+    B = 6
+    g, o = both(Ukf, 0, B)
+    P.run_pose_c3(g, B, 10_000)
+    P.run_pose_c3(o, B, 10_000)
+    em, es = P.assert_parity(0, g.get_state(), o.get_state(), what="C3, 10k steps")
+    assert not g.get_status().any()
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
 def test_shard_invariance(Ukf):
     """a filter's result does not depend on the batch it is in or its position in it (section 8e)"""
     B = 101
