@@ -209,6 +209,21 @@ int orc_set_orientation_params(void* h, double tau_g, double tau_a, double latit
     return 0;
 }
 
+int orc_set_orientation_params_per_filter(void* h, const double* tau_g, const double* tau_a, const double* latitude)
+{
+    Batch* b = static_cast<Batch*>(h);
+    if (b->kind != 1) return -1;
+    if (!b->constructed) return -2; /* the oracle's objects exist after the first initialize */
+    for (int64_t i = 0; i < b->B; ++i) {
+        b->ori[i]->gyro_bias_tau = tau_g[i];
+        b->ori[i]->acc_bias_tau = tau_a[i];
+        b->ori[i]->earth_rotation[0] = UKFB_EARTHW * std::cos(latitude[i]);
+        b->ori[i]->earth_rotation[1] = 0.;
+        b->ori[i]->earth_rotation[2] = UKFB_EARTHW * std::sin(latitude[i]);
+    }
+    return 0;
+}
+
 int orc_set_last_time(void* h, const int64_t* ts, int per_filter)
 {
     Batch* b = static_cast<Batch*>(h);

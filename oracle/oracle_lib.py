@@ -93,8 +93,13 @@ class OracleBatch:
         self._chk(self.lib.orc_set_time_bounds(self.h, C.c_double(min_dt), C.c_double(max_dt)), "set_time_bounds")
 
     def set_orientation_params(self, tau_g, tau_a, latitude):
-        self._chk(self.lib.orc_set_orientation_params(self.h, C.c_double(tau_g), C.c_double(tau_a),
-                                                      C.c_double(latitude)), "set_orientation_params")
+        if np.ndim(tau_g) == 0 and np.ndim(tau_a) == 0 and np.ndim(latitude) == 0:
+            self._chk(self.lib.orc_set_orientation_params(self.h, C.c_double(tau_g), C.c_double(tau_a),
+                                                          C.c_double(latitude)), "set_orientation_params")
+            return
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.B,))) for a in (tau_g, tau_a, latitude)]
+        self._chk(self.lib.orc_set_orientation_params_per_filter(self.h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]),
+                  "set_orientation_params_per_filter")
 
     def set_mahalanobis_gate(self, max_d2):
         self._chk(self.lib.orc_set_mahalanobis_gate(self.h, C.c_double(max_d2)), "set_mahalanobis_gate")

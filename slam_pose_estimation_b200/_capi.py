@@ -37,6 +37,7 @@ SIGNATURES = {
     "ukfb_set_last_time": (I, [P, P, I]),
     "ukfb_get_last_time": (I, [P, P]),
     "ukfb_set_orientation_params": (I, [P, D, D, D]),
+    "ukfb_set_orientation_params_per_filter": (I, [P, P, P, P]),
     "ukfb_set_mahalanobis_gate": (I, [P, D]),
     "ukfb_get_mahalanobis_gate": (I, [P, C.POINTER(D)]),
     "ukfb_predict_dt": (I, [P, P, I]),

@@ -157,10 +157,14 @@ class UkfBatch:
         self._chk(self.lib.ukfb_get_mahalanobis_gate(self.h, C.byref(v)))
         return v.value
 
-    def set_orientation_params(self, tau_g: float, tau_a: float, latitude: float):
-        self._chk(self.lib.ukfb_set_orientation_params(self.h, tau_g, tau_a, latitude))
+    def set_orientation_params(self, tau_g, tau_a, latitude):
+        """scalars: one parameter set for all filters; arrays of B values: one per filter"""
+        if np.ndim(tau_g) == 0 and np.ndim(tau_a) == 0 and np.ndim(latitude) == 0:
+            self._chk(self.lib.ukfb_set_orientation_params(self.h, float(tau_g), float(tau_a), float(latitude)))
+            return
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.B,))) for a in (tau_g, tau_a, latitude)]
+        self._chk(self.lib.ukfb_set_orientation_params_per_filter(self.h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
 
-    # ---- predict -------------------------------------------------------------------------
     def predict_dt(self, dt):
         dt = np.atleast_1d(np.asarray(dt, np.float64))
         per = int(dt.size == self.B)

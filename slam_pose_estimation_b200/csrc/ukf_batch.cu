@@ -12,6 +12,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -65,6 +66,7 @@ struct ukfb_handle {
     double* acc_mu = nullptr;
     double* acc_cov = nullptr;
     double gate_d2 = HUGE_VAL; /* accept_any_mahalanobis_distance */
+    double* ori_params = nullptr; /* B x 5 per-filter (-1/tau_g, -1/tau_a, earth xyz), or null: the scalars above */
     bool tick_kinds_have_orientation = false; /* set by ukfb_run_dev from its host-side kinds */
     double* gyro_mu = nullptr;
     bool initialized = false, first_init = true;
@@ -305,12 +307,13 @@ __global__ void store_vec3_kernel(double* __restrict__ dst_mu, double* __restric
 
 /* OrientationUKF::getRotationRate (OrientationUKF.cpp:74-77) */
 __global__ void rotation_rate_kernel(const double* __restrict__ state, const double* __restrict__ gyro, double e0, double e1,
-                                     double e2, double* __restrict__ out, long long B, int tiled)
+                                     double e2, const double* __restrict__ ori_params, double* __restrict__ out, long long B, int tiled)
 {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
         double q[4];
         for (int i = 0; i < 4; ++i) q[i] = state[rec_index(tiled, b, i, OriF::REC)];
-        const double e[3] = {e0, e1, e2};
+        double e[3] = {e0, e1, e2};
+        if (ori_params) e[0] = ori_params[b * 5 + 2], e[1] = ori_params[b * 5 + 3], e[2] = ori_params[b * 5 + 4];
         double r[3];
         quat_inv_rotate(q, e, r);
         for (int i = 0; i < 3; ++i) out[b * 3 + i] = gyro[b * 3 + i] - state[rec_index(tiled, b, 7 + i, OriF::REC)] - r[i];
@@ -507,6 +510,7 @@ static StepParams base_params(const ukfb_handle* h)
     p.kind = -1;
     p.K = 1;
     p.gate_d2 = h->gate_d2;
+    p.ori_params = h->ori_params;
     return p;
 }
 
@@ -613,7 +617,7 @@ extern "C" int ukfb_destroy(ukfb_handle* h)
     Bind bind_(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist);
-    cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary);
+    cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary), cudaFree(h->ori_params);
     for (int i = 0; i < 16; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->pipe.made) {
@@ -852,6 +856,36 @@ extern "C" int ukfb_set_orientation_params(ukfb_handle* h, double gyro_bias_tau,
     h->earth[0] = UKFB_EARTHW * cos(latitude);
     h->earth[1] = 0.0;
     h->earth[2] = UKFB_EARTHW * sin(latitude);
+    if (h->ori_params) { /* back to one parameter set for all filters */
+        Bind bind_(h);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(h->ori_params);
+        h->ori_params = nullptr;
+    }
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_orientation_params_per_filter(ukfb_handle* h, const double* gyro_bias_tau, const double* acc_bias_tau,
+                                                      const double* latitude)
+{
+    CHECK_H(h);
+    if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: not an ORIENTATION handle");
+    if (!gyro_bias_tau || !acc_bias_tau || !latitude) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: null argument");
+    if (!h->tiled) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: needs a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
+    std::vector<double> packed(size_t(h->B) * 5);
+    for (long long b = 0; b < h->B; ++b) {
+        packed[b * 5] = -1.0 / gyro_bias_tau[b];
+        packed[b * 5 + 1] = -1.0 / acc_bias_tau[b];
+        packed[b * 5 + 2] = UKFB_EARTHW * cos(latitude[b]);
+        packed[b * 5 + 3] = 0.0;
+        packed[b * 5 + 4] = UKFB_EARTHW * sin(latitude[b]);
+    }
+    if (!h->ori_params) {
+        cudaError_t e = cudaMalloc(&h->ori_params, sizeof(double) * h->B * 5);
+        if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "ukfb_set_orientation_params_per_filter: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemcpyAsync(h->ori_params, packed.data(), sizeof(double) * h->B * 5, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
 }
 
@@ -1096,7 +1130,7 @@ extern "C" int ukfb_get_rotation_rate(ukfb_handle* h, double* out)
     if (!out) return fail(UKFB_ERR_INVALID, "ukfb_get_rotation_rate: null argument");
     int rc = stage_reserve(h, sizeof(double) * h->B * 3);
     if (rc) return rc;
-    rotation_rate_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->gyro_mu, h->earth[0], h->earth[1], h->earth[2],
+    rotation_rate_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->gyro_mu, h->earth[0], h->earth[1], h->earth[2], h->ori_params,
                                                                reinterpret_cast<double*>(h->stage), h->B, h->tiled);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, h->stage, sizeof(double) * h->B * 3, cudaMemcpyDeviceToHost, h->stream));

@@ -143,6 +143,8 @@ struct StepParams {
     /* the accept functor of ukfom::ukf::update: a measurement with innov^T S^-1 innov > gate_d2 is not integrated
      * (+inf = accept_any_mahalanobis_distance, the reference's choice at PoseUKF.cpp:116) */
     double gate_d2;
+    /* ORIENTATION, one parameter set per filter: B x 5 (-1/tau_g, -1/tau_a, earth rotation xyz), or null */
+    const double* ori_params;
 };
 
 UKFB_HD int meas_dim(int kind)

@@ -838,6 +838,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
         ma.acc[i] = p.acc_mu[bb * 3 + i];
         ma.omega[i] = p.gyro_mu[bb * 3 + i];
     }
+    if (p.ori_params) { /* this filter's own constructor arguments (OrientationUKF.cpp:41-47) */
+        ma.neg_inv_tau_g = p.ori_params[bb * 5], ma.neg_inv_tau_a = p.ori_params[bb * 5 + 1];
+        ma.earth[0] = p.ori_params[bb * 5 + 2], ma.earth[1] = p.ori_params[bb * 5 + 3], ma.earth[2] = p.ori_params[bb * 5 + 4];
+    }
     const double big = 1.79769313486231570e308;
     uint32_t status = 0;
     bool dirty_mu = false;

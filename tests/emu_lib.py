@@ -31,6 +31,7 @@ class StepParams(C.Structure):
         ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
         ("events", C.c_int), ("r_kind_stride", C.c_longlong), ("gate_d2", C.c_double),
+        ("ori_params", C.c_void_p),
     ]
 
 
@@ -89,6 +90,7 @@ class EmuBatch:
         self.earth = np.array([2.0 * np.pi / 86164.0, 0.0, 0.0])  # latitude 0 until set_orientation_params
         self._first_init = True
         self.gate_d2 = np.inf
+        self.ori_params = None
 
     def initialize(self, mu, sigma):
         mu = np.asarray(mu, float).reshape(self.B, self.MU)
@@ -125,8 +127,13 @@ class EmuBatch:
         self.gate_d2 = float(max_d2)
 
     def set_orientation_params(self, tau_g, tau_a, lat):
-        self.tau_g, self.tau_a = tau_g, tau_a
         w = 2.0 * np.pi / 86164.0
+        if np.ndim(tau_g) or np.ndim(tau_a) or np.ndim(lat):
+            tg, ta, la = (np.broadcast_to(np.asarray(a, float), (self.B,)) for a in (tau_g, tau_a, lat))
+            self.ori_params = np.ascontiguousarray(np.stack([-1.0 / tg, -1.0 / ta, w * np.cos(la), np.zeros(self.B), w * np.sin(la)], axis=1))
+            return
+        self.ori_params = None
+        self.tau_g, self.tau_a = tau_g, tau_a
         self.earth = np.array([w * np.cos(lat), 0.0, w * np.sin(lat)])
 
     def set_acceleration(self, mu, cov=None, mask=None):
@@ -154,6 +161,7 @@ class EmuBatch:
         p.hist = _ptr(self.hist)
         p.min_dt, p.max_dt = self.min_dt, self.max_dt
         p.gate_d2 = self.gate_d2
+        p.ori_params = _ptr(self.ori_params)
         p.acc_mu, p.acc_cov, p.gyro_mu = _ptr(self.acc_mu), _ptr(self.acc_cov), _ptr(self.gyro_mu)
         p.neg_inv_tau_g, p.neg_inv_tau_a = -1.0 / self.tau_g, -1.0 / self.tau_a
         p.earth = (C.c_double * 3)(*self.earth)

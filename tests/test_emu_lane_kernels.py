@@ -255,3 +255,26 @@ def test_pose_orientation_measurement_runs_the_structured_path():
         x.step(syn.DT, 3, far, np.eye(3) * 1e-2)
     P.assert_parity(0, e.get_state(), o.get_state(), tol=1e-10, what="orientation measurement, far innovation")
     assert (e.fallbacks() - before)[1] > 0
+
+
+def _per_filter_orientation(cls, B, **kw):
+    rng = np.random.default_rng(17)
+    tg, ta, lat = 10.0 ** rng.uniform(0, 3, B), 10.0 ** rng.uniform(0, 3, B), rng.uniform(-1.5, 1.5, B)
+    mu, sg = syn.orientation_initial(B)
+    x = cls(1, B, **kw)
+    x.initialize(mu, sg)
+    x.set_process_noise(syn.ORI_Q)
+    x.set_orientation_params(tg, ta, lat)  # one constructor-argument set per filter (OrientationUKF.cpp:41-47)
+    P.run_ori_c1(x, B, 8, every=4)
+    return x
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_orientation_per_filter_parameters(kernel):
+    B = 37
+    o, e = _per_filter_orientation(OracleBatch, B), _per_filter_orientation(EmuBatch, B, kernel=kernel)
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=TOL, what=f"{kernel} per-filter tau / latitude")
+    # and they matter: the same run with one shared parameter set differs
+    s = P.make_ori(OracleBatch, B)
+    P.run_ori_c1(s, B, 8, every=4)
+    assert np.abs(s.get_state()[0] - o.get_state()[0]).max() > 1e-9

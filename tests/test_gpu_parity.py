@@ -412,6 +412,16 @@ def test_orientation_kernels_agree_with_the_oracle(Ukf, kernel, monkeypatch):
     assert not g.get_status().any()
 
 
+def test_orientation_per_filter_parameters(Ukf):
+    """one (gyro_bias_tau, acc_bias_tau, latitude) per filter, as separately constructed reference objects would have"""
+    from test_emu_lane_kernels import _per_filter_orientation
+
+    B = 200
+    g, o = _per_filter_orientation(Ukf, B), _per_filter_orientation(OracleBatch, B)
+    P.assert_parity(1, g.get_state(), o.get_state(), what="per-filter tau / latitude")
+    assert np.abs(g.get_rotation_rate() - o.get_rotation_rate()).max() < 1e-12
+
+
 def test_orientation_fast_kernel_fallback_lanes(Ukf):
     """lanes that leave the polynomial ranges / the update guard run the literal code inside ukf_ori_fast_kernel"""
     B = 64
