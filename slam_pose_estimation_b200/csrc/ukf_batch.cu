@@ -464,8 +464,9 @@ static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p, b
 
 static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
 {
-    static bool attr_set[64] = {};
-    return launch_fast(ukf_ori_fast_kernel, OF_PER_LANE, h, p, attr_set);
+    static bool attr_set[2][64] = {};
+    if (p.ori_params) return launch_fast(ukf_ori_fast_kernel<true>, OF_PER_LANE, h, p, attr_set[1]);
+    return launch_fast(ukf_ori_fast_kernel<false>, OF_PER_LANE, h, p, attr_set[0]);
 }
 
 static int launch_step(ukfb_handle* h, const StepParams& p)

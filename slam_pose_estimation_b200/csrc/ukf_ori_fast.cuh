@@ -804,6 +804,10 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
+/* PER_FILTER_PARAMS = false: time constants and earth rotation are launch constants (constant-bank operands, no
+ * registers); true: each filter's own set is loaded (ukfb_set_orientation_params_per_filter).  Two instances because the
+ * ten extra live registers cost the common case 3 %. */
+template <bool PER_FILTER_PARAMS>
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef OriF F;
@@ -838,7 +842,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
         ma.acc[i] = p.acc_mu[bb * 3 + i];
         ma.omega[i] = p.gyro_mu[bb * 3 + i];
     }
-    if (p.ori_params) { /* this filter's own constructor arguments (OrientationUKF.cpp:41-47) */
+    if (PER_FILTER_PARAMS) { /* this filter's own constructor arguments (OrientationUKF.cpp:41-47) */
         ma.neg_inv_tau_g = p.ori_params[bb * 5], ma.neg_inv_tau_a = p.ori_params[bb * 5 + 1];
         ma.earth[0] = p.ori_params[bb * 5 + 2], ma.earth[1] = p.ori_params[bb * 5 + 3], ma.earth[2] = p.ori_params[bb * 5 + 4];
     }

@@ -68,7 +68,10 @@ extern "C" void emu_pose_fast_fallbacks(unsigned long long* out3)
 extern "C" int emu_ori_fast_step(const StepParams* p)
 {
     const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
-    simt_emu::launch(ukf_ori_fast_kernel, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
+    if (p->ori_params)
+        simt_emu::launch(ukf_ori_fast_kernel<true>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
+    else
+        simt_emu::launch(ukf_ori_fast_kernel<false>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
     return 0;
 }
 
