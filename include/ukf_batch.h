@@ -151,7 +151,7 @@ int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us);
  * ukfom::accept_any_mahalanobis_distance (PoseUKF.cpp:116, OrientationUKF.cpp:69-71): that is the default here,
  * max_d2 = +inf.  A finite max_d2 gives ukfom::accept_mahalanobis_distance(max_d2) for every later update of this
  * handle: a measurement whose squared Mahalanobis distance innov^T S^-1 innov exceeds it is not integrated (state and
- * covariance untouched) and the filter's UKFB_STATUS_MEAS_REJECTED bit is set.  Lane-per-filter kernels only. */
+ * covariance untouched) and the filter's UKFB_STATUS_MEAS_REJECTED bit is set. */
 int ukfb_set_mahalanobis_gate(ukfb_handle* h, double max_d2);
 int ukfb_get_mahalanobis_gate(const ukfb_handle* h, double* max_d2);
 

@@ -835,7 +835,6 @@ extern "C" int ukfb_set_mahalanobis_gate(ukfb_handle* h, double max_d2)
 {
     CHECK_H(h);
     if (!(max_d2 > 0.0)) return fail(UKFB_ERR_INVALID, "ukfb_set_mahalanobis_gate: the threshold must be positive (+inf accepts everything)");
-    if (!h->tiled && max_d2 < HUGE_VAL) return fail(UKFB_ERR_INVALID, "ukfb_set_mahalanobis_gate: needs a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
     h->gate_d2 = max_d2;
     return UKFB_OK;
 }
@@ -1344,7 +1343,6 @@ extern "C" int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us
     if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: K must be >= 1");
     if (!d_ts_us || !d_kinds || !d_mu3 || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events: null argument");
     if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: cov_mode must be 0 (per-kind table) or 1 (per event)");
-    if (!h->tiled) return fail(UKFB_ERR_INVALID, "ukfb_run_events: event streams need a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
     StepParams p = base_params(h);
     p.K = K;
     p.events = 1;

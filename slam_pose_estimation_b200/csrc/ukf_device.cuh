@@ -87,8 +87,8 @@ struct Smem {
     static constexpr int OFF_MD = OFF_SM + 10;     /* mean delta broadcast */
     static constexpr int OFF_BC = OFF_MD + 16;     /* state broadcast */
     static constexpr int OFF_NT = OFF_BC + 16;     /* this predict's process noise, packed lower */
-    static constexpr int OFF_CTL = OFF_NT + F::LP + (F::LP & 1); /* ints: flags[G], kind[G], status[G], mean-pass histogram[8] */
-    static constexpr int TOTAL_RAW = OFF_CTL + (3 * G + 8 + 1) / 2;
+    static constexpr int OFF_CTL = OFF_NT + F::LP + (F::LP & 1); /* ints: flags[G], kind[G], status[G], mean-pass histogram[8], store[G] */
+    static constexpr int TOTAL_RAW = OFF_CTL + (4 * G + 8 + 1) / 2;
     static constexpr int TOTAL = (TOTAL_RAW + 1) & ~1;
 };
 
@@ -633,6 +633,18 @@ UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b
             }
             meas_boxminus(zin, zref, rot, innov);
         }
+        /* the accept functor (every lane holds the same innov and S^-1): a rejected measurement leaves the filter as it
+         * was -- the shared-memory covariance, overwritten by the factor, comes back from the record */
+        {
+            double d2 = 0.0;
+            UKFB_UNROLL
+            for (int a = 0; a < 3; ++a) d2 += innov[a] * (Si[a * 3] * innov[0] + Si[a * 3 + 1] * innov[1] + Si[a * 3 + 2] * innov[2]);
+            if (d2 > p.gate_d2) {
+                for (int e = lane; e < F::LP; e += 32) sig[e] = UKFB_LDCG(sigma_prior + e);
+                __syncwarp();
+                return st | UKFB_STATUS_MEAS_REJECTED;
+            }
+        }
         /* K = Sxz S^-1, KS = K S */
         for (int e = lane; e < 3 * F::N; e += 32) {
             const int i = e / 3, c = e % 3;
@@ -804,6 +816,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
     int* ckind = cflag + G;
     int* cstat = ckind + G;
     w.HP = cstat + G;
+    int* cstore = w.HP + 8; /* a storing event (UKFB_EVENT_* >= 10) of this slot, applied after the predict */
     if (lane < 8) w.HP[lane] = 0;
     if (lane < G) cstat[lane] = 0, cflag[lane] = 0;
     for (int i = lane; i < DT_ROWS * DT_LD; i += 32) w.D[i] = 0.0; /* padding columns / rows stay zero */
@@ -833,11 +846,26 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
     for (int tick = 0; tick < p.K; ++tick) {
         /* ---- per-filter control: time guards (UnscentedKalmanFilter.hpp:83-125), masks, checks */
         if (lane < G) {
-            int flags = cflag[lane] & CF_DIRTY, kind = -1, st = 0;
+            int flags = cflag[lane] & CF_DIRTY, kind = -1, st = 0, store = -1;
             if (lane < cnt) {
                 const long long b = first + lane;
                 double* fr = wsm + lane * SM::FS;
                 flags |= CF_VALID;
+                bool idle = false;
+                const double* Rev = p.R + tick * p.r_kstride + b * p.r_stride;
+                if (p.events) { /* one queued sample per filter and slot; UKFB_EVENT_IDLE: nothing happens */
+                    kind = int(p.kinds[tick * p.kinds_kstride + b]);
+                    idle = kind == UKFB_EVENT_IDLE;
+                    if (kind >= UKFB_EVENT_KIND_COUNT || kind < UKFB_EVENT_IDLE
+                        || (kind >= 0 && (F::KIND == 0 ? (kind == UKFB_MEAS_ORI_VELOCITY || kind > UKFB_EVENT_POSE_ACCELERATION)
+                                                       : (kind < UKFB_MEAS_ORI_VELOCITY || kind == UKFB_EVENT_POSE_ACCELERATION)))) {
+                        st |= UKFB_STATUS_BAD_EVENT;
+                        idle = true;
+                    }
+                    if (idle) kind = -1;
+                    if (kind >= 0) Rev += kind * p.r_kind_stride;
+                    if (kind >= UKFB_EVENT_POSE_ACCELERATION) store = kind, kind = -1;
+                }
                 if (F::KIND == 1 && p.imu) { /* integrateMeasurement(RotationRate / Acceleration): check, store */
                     const double* s6 = p.imu + tick * p.imu_kstride + b * 6;
                     double* fimu = fr + SM::OFF_IMU;
@@ -852,7 +880,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                     else
                         st |= UKFB_STATUS_NONFINITE_MEAS;
                 }
-                if (p.do_predict) {
+                if (p.do_predict && !idle) {
                     double dt;
                     bool have_dt = true;
                     if (p.time_mode) {
@@ -882,15 +910,17 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                         }
                     }
                 }
-                if (p.do_update) {
-                    kind = p.tick_kinds ? int(p.tick_kinds[tick])
-                                        : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
-                    if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
-                    if (kind >= 0) {
+                if (p.do_update && !idle) {
+                    if (!p.events) {
+                        kind = p.tick_kinds ? int(p.tick_kinds[tick])
+                                            : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                        if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
+                    }
+                    if (kind >= 0 || store >= 0) {
                         /* stage the measurement: z zero padded to 3, R identity padded to 3x3 */
-                        const int m = meas_dim(kind);
+                        const int m = store >= 0 ? 3 : meas_dim(kind);
                         const double* zm = p.z + tick * p.z_kstride + b * p.z_stride;
-                        const double* Rm = p.R + tick * p.r_kstride + b * p.r_stride;
+                        const double* Rm = Rev;
                         bool ok = true;
                         UKFB_UNROLL
                         for (int a = 0; a < 3; ++a) {
@@ -904,12 +934,12 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                                 fr[SM::OFF_R + a * 3 + c] = rv;
                             }
                         }
-                        /* checkMeasurment: OrientationUKF only (OrientationUKF.cpp:67); PoseUKF never checks */
-                        if (F::KIND == 0 || ok)
-                            flags |= CF_UPD;
-                        else {
+                        /* checkMeasurment: OrientationUKF only (OrientationUKF.cpp:55,61,67); PoseUKF never checks */
+                        if (F::KIND == 0 || ok) {
+                            if (kind >= 0) flags |= CF_UPD;
+                        } else {
                             st |= UKFB_STATUS_NONFINITE_MEAS;
-                            kind = -1;
+                            kind = -1, store = -1;
                         }
                     }
                 }
@@ -917,6 +947,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
             cflag[lane] = flags;
             ckind[lane] = kind;
             cstat[lane] |= st;
+            cstore[lane] = store;
         }
         __syncwarp();
 
@@ -930,6 +961,19 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                     cstat[g] |= int(st);
                     cflag[g] |= CF_DIRTY;
                 }
+            }
+            __syncwarp();
+        }
+
+        /* ---- storing events: the sample is kept for the next predict (PoseUKF.cpp:175-178, OrientationUKF.cpp:53-63) */
+        if (p.events) {
+            if (lane < cnt && cstore[lane] >= 0) {
+                double* fr = wsm + lane * SM::FS;
+                double* fimu = fr + SM::OFF_IMU;
+                const int off = cstore[lane] == UKFB_EVENT_ORI_ROTATION_RATE ? 3 : 0;
+                fimu[off] = fr[SM::OFF_Z], fimu[off + 1] = fr[SM::OFF_Z + 1], fimu[off + 2] = fr[SM::OFF_Z + 2];
+                if (F::KIND == 0)
+                    for (int i = 0; i < 9; ++i) p.acc_cov[(first + lane) * 9 + i] = fr[SM::OFF_R + i];
             }
             __syncwarp();
         }
@@ -948,7 +992,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
             for (int g = 0; g < cnt; ++g) {
                 if (!(cflag[g] & CF_UPD)) continue;
                 const uint32_t st = sigma_pass<F, G, MODE_UPDATE>(w, &p, first + g, ckind[g], wsm + g * SM::FS, rec + g * F::REC + F::MU);
-                if (lane == 0) cstat[g] |= int(st);
+                if (lane == 0) {
+                    cstat[g] |= int(st);
+                    if (st & UKFB_STATUS_MEAS_REJECTED) cflag[g] &= ~CF_UPD; /* gated out: no apply_delta */
+                }
             }
             __syncwarp();
             /* the reference has already replaced sigma by sigma - K S K^T when MTK's assert fires inside
@@ -974,13 +1021,13 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
             if (!(cflag[g] & CF_DIRTY)) continue;
             rec[i] = wsm[g * SM::FS + k];
         }
-        if (F::KIND == 1 && p.imu) {
+        if ((F::KIND == 1 && p.imu) || p.events) {
             for (int i = lane; i < cnt * 6; i += 32) {
                 const int g = i / 6, k = i - g * 6;
                 const double v = wsm[g * SM::FS + SM::OFF_IMU + k];
                 if (k < 3)
                     p.acc_mu[(first + g) * 3 + k] = v;
-                else
+                else if (F::KIND == 1)
                     p.gyro_mu[(first + g) * 3 + (k - 3)] = v;
             }
         }

@@ -217,8 +217,7 @@ class EmuBatch:
         self._launch(do_predict=1, time_mode=0, dt=dt, dt_stride=1 if dt.size == self.B else 0, **a)
 
     def run_events(self, ts, kinds, mu3, cov):
-        """same arguments as UkfBatch.run_events (lane-per-filter kernels only)"""
-        assert self.tiled
+        """same arguments as UkfBatch.run_events"""
         ts = np.ascontiguousarray(np.asarray(ts, np.int64))
         K, B = ts.size // self.B, self.B
         cov = np.ascontiguousarray(np.asarray(cov, float))

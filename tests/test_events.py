@@ -118,13 +118,13 @@ def check_ori(cls, kw, tol):
     P.assert_parity(1, e.get_state(), o.get_state(), tol=tol, what="orientation queues, next launch")
 
 
-@pytest.mark.parametrize("kernel", ["thread", "fast"])
+@pytest.mark.parametrize("kernel", ["thread", "fast", "warp"])
 def test_emu_pose_event_queues(kernel):
     from emu_lib import EmuBatch
     check_pose(EmuBatch, dict(kernel=kernel), 1e-12)
 
 
-@pytest.mark.parametrize("kernel", ["thread", "fast"])
+@pytest.mark.parametrize("kernel", ["thread", "fast", "warp"])
 def test_emu_orientation_event_queues(kernel):
     from emu_lib import EmuBatch
     check_ori(EmuBatch, dict(kernel=kernel), 1e-12)

@@ -58,13 +58,13 @@ def check_ori(cls, kw, tol):
     assert np.array_equal(e.get_status(), st)
 
 
-@pytest.mark.parametrize("kernel", ["thread", "fast"])
+@pytest.mark.parametrize("kernel", ["thread", "fast", "warp"])
 def test_emu_pose_gate(kernel):
     from emu_lib import EmuBatch
     check_pose(EmuBatch, dict(kernel=kernel), 1e-12)
 
 
-@pytest.mark.parametrize("kernel", ["thread", "fast"])
+@pytest.mark.parametrize("kernel", ["thread", "fast", "warp"])
 def test_emu_orientation_gate(kernel):
     from emu_lib import EmuBatch
     check_ori(EmuBatch, dict(kernel=kernel), 1e-12)
