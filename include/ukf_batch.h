@@ -159,7 +159,7 @@ int ukfb_get_mahalanobis_gate(const ukfb_handle* h, double* max_d2);
  * (OrientationUKF.cpp:41-47): earth_rotation = (EARTHW cos lat, 0, EARTHW sin lat). */
 int ukfb_set_orientation_params(ukfb_handle* h, double gyro_bias_tau, double acc_bias_tau, double latitude);
 /* the same constructor arguments, one set per filter (B values each): every OrientationUKF object of the reference is
- * built with its own time constants and location.  Lane-per-filter kernels only. */
+ * built with its own time constants and location. */
 int ukfb_set_orientation_params_per_filter(ukfb_handle* h, const double* gyro_bias_tau, const double* acc_bias_tau,
                                            const double* latitude);
 

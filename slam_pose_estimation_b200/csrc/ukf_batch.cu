@@ -871,7 +871,6 @@ extern "C" int ukfb_set_orientation_params_per_filter(ukfb_handle* h, const doub
     CHECK_H(h);
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: not an ORIENTATION handle");
     if (!gyro_bias_tau || !acc_bias_tau || !latitude) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: null argument");
-    if (!h->tiled) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: needs a lane-per-filter kernel (UKFB_KERNEL=fast|thread)");
     std::vector<double> packed(size_t(h->B) * 5);
     for (long long b = 0; b < h->B; ++b) {
         packed[b * 5] = -1.0 / gyro_bias_tau[b];

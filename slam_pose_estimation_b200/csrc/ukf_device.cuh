@@ -485,13 +485,18 @@ UKFB_D uint32_t sigma_pass(const Warp w, const StepParams* pp, const long long b
         }
         if (F::KIND == 0 && has_acc && lane < 9) {
             const int r = lane / 3, c = lane % 3;
-            if (c <= r) w.NT[tri(6 + r, 6 + c)] = 2.0 * UKFB_LDG(p.acc_cov + b * 9 + r * 3 + c);
+            if (c <= r) w.NT[tri(6 + r, 6 + c)] = 2.0 * p.acc_cov[b * 9 + r * 3 + c]; /* plain load: an event of this launch may have written it */
         }
         if (F::KIND == 0) {
             process_model_pose(x, dt, has_acc, acc);
         } else {
             const double omega[3] = {fimu[3], fimu[4], fimu[5]};
-            process_model_ori(x, dt, acc, omega, p.neg_inv_tau_g, p.neg_inv_tau_a, p.earth);
+            if (p.ori_params) { /* this filter's own constructor arguments (OrientationUKF.cpp:41-47) */
+                const double* op = p.ori_params + b * 5;
+                const double earth[3] = {op[2], op[3], op[4]};
+                process_model_ori(x, dt, acc, omega, op[0], op[1], earth);
+            } else
+                process_model_ori(x, dt, acc, omega, p.neg_inv_tau_g, p.neg_inv_tau_a, p.earth);
         }
     }
 

@@ -269,7 +269,7 @@ def _per_filter_orientation(cls, B, **kw):
     return x
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", KERNELS + ["warp"])
 def test_orientation_per_filter_parameters(kernel):
     B = 37
     o, e = _per_filter_orientation(OracleBatch, B), _per_filter_orientation(EmuBatch, B, kernel=kernel)
