@@ -341,6 +341,16 @@ class UkfBatch:
     def launch_count(self) -> int:
         return int(self.lib.ukfb_launch_count(self.h))
 
+    def selftest_so3(self, v, x):
+        """device exp / log / reciprocal / sqrt of csrc/so3.cuh and simt.cuh on n inputs -> (n, 10), see the header"""
+        v, pv = _host(v, np.float64)
+        x, px = _host(x, np.float64)
+        n = x.size
+        assert v.size == 3 * n
+        out = np.empty((n, 10))
+        self._chk(self.lib.ukfb_selftest_so3(self.h, n, pv, px, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self._chk(self.lib.ukfb_measure_fp64_peak(self.h, C.byref(v)))

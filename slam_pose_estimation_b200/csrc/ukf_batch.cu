@@ -1509,6 +1509,37 @@ extern "C" int ukfb_event_elapsed_ms(ukfb_handle* h, int slot_begin, int slot_en
 
 extern "C" int64_t ukfb_launch_count(const ukfb_handle* h) { return h ? h->launches : 0; }
 
+/* self-test of the device SO(3) kernels (so3.cuh): q = exp(v), w = log(q), rc = 1 / x, (sq, rs) = sqrt / rsqrt of x */
+__global__ void so3_selftest_kernel(const double* __restrict__ v, const double* __restrict__ x, double* __restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double q[4], w[3], sq, rs;
+        so3_exp(v + 3 * i, 1.0, q);
+        so3_log(q, w);
+        fast_sqrt_rsqrt(x[i], sq, rs);
+        double* o = out + 10 * i;
+        o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
+        o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
+    }
+}
+
+extern "C" int ukfb_selftest_so3(ukfb_handle* h, int64_t n, const double* v, const double* x, double* out)
+{
+    CHECK_H(h);
+    if (n < 1 || !v || !x || !out) return fail(UKFB_ERR_INVALID, "ukfb_selftest_so3: bad argument");
+    const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * 10;
+    int rc = stage_reserve(h, bv + bx + bo);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->stage, v, sizeof(double) * n * 3, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->stage + bv, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    so3_selftest_kernel<<<grid_for(n), 256, 0, h->stream>>>(reinterpret_cast<const double*>(h->stage), reinterpret_cast<const double*>(h->stage + bv),
+                                                            reinterpret_cast<double*>(h->stage + bv + bx), n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, h->stage + bv + bx, bo, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
 extern "C" int ukfb_measure_fp64_peak(ukfb_handle* h, double* flops_per_s)
 {
     CHECK_H(h);

@@ -80,4 +80,18 @@ extern "C" void emu_ori_fast_fallbacks(unsigned long long* out3)
     for (int i = 0; i < 3; ++i) out3[i] = of_fallbacks[i];
 }
 
+/* the SO(3) kernels of so3.cuh as the host build evaluates them (same layout as ukfb_selftest_so3) */
+extern "C" void emu_selftest_so3(long long n, const double* v, const double* x, double* out)
+{
+    for (long long i = 0; i < n; ++i) {
+        double q[4], w[3], sq, rs;
+        so3_exp(v + 3 * i, 1.0, q);
+        so3_log(q, w);
+        fast_sqrt_rsqrt(x[i], sq, rs);
+        double* o = out + 10 * i;
+        o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
+        o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
+    }
+}
+
 extern "C" int emu_sizeof_params(void) { return int(sizeof(StepParams)); }
