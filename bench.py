@@ -144,7 +144,9 @@ def run_reference(args, rank, world):
         return
     B = args.ref_filters
     per_step_s = None
-    value, threads, _ = time_oracle(B, 2, 1)  # calibrate
+    # every host thread this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank)
+    ncpu = len(os.sched_getaffinity(0))
+    value, threads, _ = time_oracle(B, 2, 1, threads=ncpu)  # calibrate
     per_step_s = B / value
     # bound the whole run to ~ 2 minutes
     budget = 120.0
@@ -152,7 +154,7 @@ def run_reference(args, rank, world):
     while B > 256 and per_step_s * total_steps > budget:
         B //= 2
         per_step_s /= 2
-    value, threads, dt = time_oracle(B, args.steps, args.warmup)
+    value, threads, dt = time_oracle(B, args.steps, args.warmup, threads=ncpu)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -424,9 +426,9 @@ def main():
         line["orientation_c2"] = orientation
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core
-        v, threads, dt = time_oracle(args.ref_filters, 2, 1)  # calibrate, then ~10 s of CPU work
+        v, threads, dt = time_oracle(args.ref_filters, 2, 1, threads=len(all_cpus))  # calibrate, then ~10 s of CPU work
         nsteps = int(min(20000, max(4, 12.0 / (dt / 2))))  # about 12 s of CPU work
-        v, threads, dt = time_oracle(args.ref_filters, nsteps, 1)
+        v, threads, dt = time_oracle(args.ref_filters, nsteps, 1, threads=len(all_cpus))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{args.ref_filters} filters x {nsteps} steps of the same workload, oracle port, "
                                           f"OpenMP over filters, {dt:.1f} s"}
