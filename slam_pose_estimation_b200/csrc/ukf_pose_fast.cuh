@@ -126,11 +126,11 @@ struct PoseMu {
 UKFB_D void pf_point(const double* qs, const double* ps, const double* vs, const double* ws, double dt, const double* ref_p,
                      const double* ref_q, double* d, bool& slow)
 {
-    double rv[3], rw[3], e[4], qn[4], r[4];
+    double rv[3], e[4], qn[4], r[4];
     quat_rotate(qs, vs, rv);
-    quat_rotate(qs, ws, rw);
-    pf_exp(rw, dt, e, slow);
-    quat_mul(e, qs, qn);
+    /* q [+] (q w) dt = exp((q w) dt) q = q exp(w dt) q^-1 q = q exp(w dt) for a unit q: w needs no rotation */
+    pf_exp(ws, dt, e, slow);
+    quat_mul(qs, e, qn);
     d[0] = fma(dt, rv[0], ps[0]) - ref_p[0];
     d[1] = fma(dt, rv[1], ps[1]) - ref_p[1];
     d[2] = fma(dt, rv[2], ps[2]) - ref_p[2];

@@ -9,7 +9,7 @@ import sys
 import tempfile
 
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(root, "slam_pose_estimation_b200", "lib", "libukfb.so")
+lib = os.environ.get("UKFB_LIB") or os.path.join(root, "slam_pose_estimation_b200", "lib", "libukfb.so")
 name, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25
 with tempfile.TemporaryDirectory() as d:
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, stdout=subprocess.DEVNULL)
