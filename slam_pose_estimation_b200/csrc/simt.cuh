@@ -41,6 +41,9 @@ namespace ukfb {
 
 UKFB_D void ukfb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 
+/* hint: bring the line at p into L2 */
+UKFB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 /* value of `v` held by lane `src` (all 32 lanes must call) */
 UKFB_D double warp_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -112,6 +115,7 @@ using std::atan;
 using std::fabs;
 using std::fma;
 using std::sqrt;
+inline void prefetch_l2(const void*) {}
 inline void ukfb_sincos(double x, double* s, double* c)
 {
     *s = std::sin(x);

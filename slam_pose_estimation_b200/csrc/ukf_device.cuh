@@ -145,6 +145,11 @@ struct StepParams {
     double gate_d2;
     /* ORIENTATION, one parameter set per filter: B x 5 (-1/tau_g, -1/tau_a, earth rotation xyz), or null */
     const double* ori_params;
+    /* fast kernels: a starting warp asks L2 for the record of the tile `prefetch_tiles` ahead of its own -- the tile a
+     * warp of the next wave will start on (0 = off; set by the launcher to the number of resident warps) -- one request
+     * per `prefetch_bytes` of the record */
+    long long prefetch_tiles;
+    int prefetch_bytes;
 };
 
 UKFB_HD int meas_dim(int kind)

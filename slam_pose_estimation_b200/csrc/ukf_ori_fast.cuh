@@ -830,6 +830,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
     UKFB_UNROLL
     for (int i = 0; i < 3; ++i) m.v[i] = rec[(4 + i) * TILE], m.bg[i] = rec[(7 + i) * TILE], m.ba[i] = rec[(10 + i) * TILE];
     m.g = rec[13 * TILE];
+    prefetch_next_wave<F>(p, tile, lane);
 
     ModelArgs ma;
     ma.dt = 0.0;

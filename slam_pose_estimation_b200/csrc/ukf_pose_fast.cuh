@@ -122,6 +122,21 @@ struct PoseMu {
     double p[3], q[4], v[3], w[3];
 };
 
+/* A warp that starts on `tile` asks L2 for the record of tile + p.prefetch_tiles, the one a warp of the next wave starts
+ * on about when this one retires: that warp's first loads then cost an L2 hit instead of a DRAM access.  Lane l requests
+ * the addresses (l + 32 i) * prefetch_bytes of the record. */
+template <class F>
+UKFB_D void prefetch_next_wave(const StepParams& p, long long tile, int lane)
+{
+    if (p.prefetch_tiles <= 0) return;
+    const long long nt = tile + p.prefetch_tiles;
+    if ((nt + 1) * TILE > p.B) return;
+    const char* rec = reinterpret_cast<const char*>(p.state + nt * (TILE * F::REC));
+    const int bytes = TILE * F::REC * int(sizeof(double));
+    UKFB_NOUNROLL
+    for (int o = lane * p.prefetch_bytes; o < bytes; o += TILE * p.prefetch_bytes) prefetch_l2(rec + o);
+}
+
 /* one propagated sigma point: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
 UKFB_D void pf_point(const double* qs, const double* ps, const double* vs, const double* ws, double dt, const double* ref_p,
                      const double* ref_q, double* d, bool& slow)
@@ -939,6 +954,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
     for (int i = 0; i < 3; ++i) m.p[i] = rec[i * TILE], m.v[i] = rec[(7 + i) * TILE], m.w[i] = rec[(10 + i) * TILE];
     UKFB_UNROLL
     for (int i = 0; i < 4; ++i) m.q[i] = rec[(3 + i) * TILE];
+    prefetch_next_wave<F>(p, tile, lane);
 
     ModelArgs ma;
     ma.dt = 0.0;

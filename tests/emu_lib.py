@@ -31,7 +31,7 @@ class StepParams(C.Structure):
         ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
         ("events", C.c_int), ("r_kind_stride", C.c_longlong), ("gate_d2", C.c_double),
-        ("ori_params", C.c_void_p),
+        ("ori_params", C.c_void_p), ("prefetch_tiles", C.c_longlong), ("prefetch_bytes", C.c_int),
     ]
 
 
