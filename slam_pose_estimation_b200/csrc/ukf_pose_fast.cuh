@@ -135,6 +135,13 @@ UKFB_D void prefetch_next_wave(const StepParams& p, long long tile, int lane)
     const int bytes = TILE * F::REC * int(sizeof(double));
     UKFB_NOUNROLL
     for (int o = lane * p.prefetch_bytes; o < bytes; o += TILE * p.prefetch_bytes) prefetch_l2(rec + o);
+    /* the per-filter inputs of that tile's first tick: stored IMU sample, measurement, time step (a few lines each) */
+    const long long nb = nt * TILE;
+    const int o = lane * p.prefetch_bytes;
+    if (p.acc_mu && o < TILE * 24) prefetch_l2(reinterpret_cast<const char*>(p.acc_mu + nb * 3) + o);
+    if (F::KIND == 1 && p.gyro_mu && o < TILE * 24) prefetch_l2(reinterpret_cast<const char*>(p.gyro_mu + nb * 3) + o);
+    if (p.do_update && p.z && o < TILE * 8 * p.z_stride) prefetch_l2(reinterpret_cast<const char*>(p.z + nb * p.z_stride) + o);
+    if (p.do_predict && !p.time_mode && p.dt && o < TILE * 8 * p.dt_stride) prefetch_l2(reinterpret_cast<const char*>(p.dt + nb * p.dt_stride) + o);
 }
 
 /* one propagated sigma point: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
