@@ -105,6 +105,13 @@ UKFB_CONSTANT double SO3_ATAN_C[10] = {1.0, -0x1.5555555555500p-2, 0x1.999999998
                                        0x1.c71c6cf04ff82p-4, -0x1.745c4ca68d45dp-4, 0x1.3aff6b481f0f7p-4,
                                        -0x1.0fcd05c851591p-4, 0x1.c90783e417298p-5, -0x1.229f36308eeefp-5};
 
+/* 2 asin(s)/s as a function of y = s*s, y <= SO3_LOG_FAST_Y (the same angles as the atan kernel: tan^2 <= 0.09), degree 8:
+ * 4e-17 from the function, and log(exp(v)) through pf_exp / pf_log within 7e-16 |v| of v (tests/test_so3_kernels.py) */
+constexpr double SO3_LOG_FAST_Y = 0.09 / 1.09;
+UKFB_CONSTANT double SO3_ASIN_C[9] = {0x1.0000000000000p+1, 0x1.555555555503dp-2, 0x1.333333340075ap-3, 0x1.6db6daa72c4afp-4,
+                                      0x1.f1c77c63fd8f8p-5, 0x1.6e7ea9f45b674p-5, 0x1.1d54d58e79ab9p-5, 0x1.b1cba0f288f34p-6,
+                                      0x1.05955d9d4e360p-5};
+
 /* the coefficient arrays are named directly (not passed as pointers) so that the compiler can address them
  * as constant-bank operands */
 #define UKFB_POLY6(C, v, v2) \
@@ -119,6 +126,16 @@ UKFB_D double atan_over_t_poly(double u)
     const double p89 = fma(SO3_ATAN_C[9], u, SO3_ATAN_C[8]);
     const double q0 = fma(p23, u2, p01), q1 = fma(p67, u2, p45);
     return fma(fma(p89, u4, q1), u4, q0);
+}
+
+/* 2 asin(sqrt y)/sqrt y, y <= SO3_LOG_FAST_Y */
+UKFB_D double two_asin_over_s_poly(double y)
+{
+    const double y2 = y * y, y4 = y2 * y2;
+    const double p01 = fma(SO3_ASIN_C[1], y, SO3_ASIN_C[0]), p23 = fma(SO3_ASIN_C[3], y, SO3_ASIN_C[2]);
+    const double p45 = fma(SO3_ASIN_C[5], y, SO3_ASIN_C[4]), p67 = fma(SO3_ASIN_C[7], y, SO3_ASIN_C[6]);
+    const double q0 = fma(p23, y2, p01), q1 = fma(p67, y2, p45);
+    return fma(fma(SO3_ASIN_C[8], y4, q1), y4, q0);
 }
 
 /* MTK cos_sinc_sqrt: (cos sqrt(x2), sinc sqrt(x2)), the literal expressions (Taylor pair below 2^-13).

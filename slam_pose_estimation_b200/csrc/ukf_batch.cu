@@ -1551,9 +1551,15 @@ __global__ void so3_selftest_kernel(const double* __restrict__ v, const double* 
         so3_exp(v + 3 * i, 1.0, q);
         so3_log(q, w);
         fast_sqrt_rsqrt(x[i], sq, rs);
-        double* o = out + 10 * i;
+        double* o = out + 14 * i;
         o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
         o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
+        /* the branch-free pair of the fast kernels (ukf_pose_fast.cuh): polynomial exp, reciprocal-free log */
+        double qf[4], wf[3];
+        bool slow = false;
+        pf_exp(v + 3 * i, 1.0, qf, slow);
+        pf_log(qf, wf, slow);
+        o[10] = wf[0], o[11] = wf[1], o[12] = wf[2], o[13] = slow ? 1.0 : 0.0;
     }
 }
 
@@ -1561,7 +1567,7 @@ extern "C" int ukfb_selftest_so3(ukfb_handle* h, int64_t n, const double* v, con
 {
     CHECK_H(h);
     if (n < 1 || !v || !x || !out) return fail(UKFB_ERR_INVALID, "ukfb_selftest_so3: bad argument");
-    const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * 10;
+    const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * 14;
     int rc = stage_reserve(h, bv + bx + bo);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->stage, v, sizeof(double) * n * 3, cudaMemcpyHostToDevice, h->stream));

@@ -290,7 +290,7 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
         }
     });
     if (!spd) return true;
-    bool slow = false;
+    bool slow = !pf_unit(m.q);
     double Rm[9];
     quat_matrix(m.q, Rm);
     /* X0' = g(mu) */
@@ -518,7 +518,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
     stage = 0;
     spd = reg_cholesky<13, 13>(a);
     if (!spd) return true;
-    bool slow = false;
+    bool slow = !pf_unit(m.q);
     /* Z of X0, of the 6 points of columns 0..2, and the linear offsets of columns 3..5.  The factor stays in registers:
      * every index below is static */
 #define OF_L(i, j) ((i) >= (j) ? a[tri((i) >= (j) ? (i) : (j), (j))] : 0.0)

@@ -88,9 +88,15 @@ extern "C" void emu_selftest_so3(long long n, const double* v, const double* x, 
         so3_exp(v + 3 * i, 1.0, q);
         so3_log(q, w);
         fast_sqrt_rsqrt(x[i], sq, rs);
-        double* o = out + 10 * i;
+        double* o = out + 14 * i;
         o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
         o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
+        /* the branch-free pair of the fast kernels (ukf_pose_fast.cuh): polynomial exp, reciprocal-free log */
+        double qf[4], wf[3];
+        bool slow = false;
+        pf_exp(v + 3 * i, 1.0, qf, slow);
+        pf_log(qf, wf, slow);
+        o[10] = wf[0], o[11] = wf[1], o[12] = wf[2], o[13] = slow ? 1.0 : 0.0;
     }
 }
 

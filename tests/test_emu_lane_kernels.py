@@ -278,3 +278,32 @@ def test_orientation_per_filter_parameters(kernel):
     s = P.make_ori(OracleBatch, B)
     P.run_ori_c1(s, B, 8, every=4)
     assert np.abs(s.get_state()[0] - o.get_state()[0]).max() > 1e-9
+
+
+@pytest.mark.parametrize("filt", ["pose", "orientation"])
+def test_unnormalised_quaternions_take_the_literal_expressions(filt):
+    """The fast kernels' log has no reciprocal and assumes |q| = 1 (to 1e-8); the reference's log is scale invariant.  A
+    state initialised with an unnormalised quaternion must therefore run the literal code, and agree with the oracle."""
+    B = 6
+    if filt == "pose":
+        mu, sg = syn.pose_initial(B)
+        mu[1, 3:7] *= 1.001
+        mu[4, 3:7] *= 0.98
+        o, e = OracleBatch(0, B), EmuBatch(0, B, kernel="fast")
+    else:
+        mu, sg = syn.orientation_initial(B)
+        mu[1, 0:4] *= 1.001
+        mu[4, 0:4] *= 0.98
+        o, e = OracleBatch(1, B), EmuBatch(1, B, kernel="fast")
+    before = e.fallbacks()
+    for x in (o, e):
+        x.initialize(mu, sg)
+        if filt == "pose":
+            P.run_pose_c3(x, B, 4)
+        else:
+            x.set_process_noise(syn.ORI_Q)
+            x.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+            P.run_ori_c1(x, B, 4, every=2)
+    P.assert_parity(0 if filt == "pose" else 1, e.get_state(), o.get_state(), tol=TOL, what=f"{filt} unnormalised q")
+    fb = e.fallbacks() - before
+    assert fb[0] >= 2 and fb.sum() < 3 * 4 * B, f"fallbacks {fb}"

@@ -391,6 +391,29 @@ def test_pose_fast_kernel_fallback_lanes(Ukf):
     assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
 
 
+@pytest.mark.parametrize("filt", [0, 1])
+def test_unnormalised_quaternions_match_the_scale_invariant_log(Ukf, filt):
+    """the fast kernels' reciprocal-free log assumes |q| = 1; states initialised with other norms run the literal code
+    (the reference's log is scale invariant) and agree with the oracle"""
+    B = 96
+    mu, sg = syn.pose_initial(B) if filt == 0 else syn.orientation_initial(B)
+    qs = slice(3, 7) if filt == 0 else slice(0, 4)
+    mu[1::3, qs] *= 1.001
+    mu[2::7, qs] *= 0.97
+    g, o = Ukf(filt, B), OracleBatch(filt, B)
+    for x in (g, o):
+        if filt == 1:
+            x.set_process_noise(syn.ORI_Q)
+            x.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+        x.initialize(mu, sg)
+        if filt == 0:
+            P.run_pose_c3(x, B, 20)
+        else:
+            P.run_ori_c1(x, B, 20, every=5)
+    P.assert_parity(filt, g.get_state(), o.get_state(), tol=1e-9, what="unnormalised quaternions")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
 @pytest.mark.parametrize("kernel", ["fast", "thread", "warp"])
 def test_orientation_kernels_agree_with_the_oracle(Ukf, kernel, monkeypatch):
     """OrientationUKF through each step kernel ('fast' = ukf_ori_fast.cuh): IMU stream with velocity updates, finite

@@ -47,6 +47,11 @@ def check(got, v, x):
     el = np.abs(got[:, 4:7] - ref[:, 4:7]).max(axis=1) / ang
     bound = 1e-15 * np.maximum(1.0, 0.2 / (np.pi - ang))
     assert (el < bound).all(), f"log: {el.max():.2e} at angle {ang[(el / bound).argmax()]}"
+    # the fast kernels' pair: polynomial exp, reciprocal-free log (valid below 0.58 rad; flagged above)
+    fast = got[:, 13] == 0.0
+    assert fast[ang < 0.57].all() and not fast[ang > 0.6].any()
+    ef = np.abs(got[fast, 10:13] - ref[fast, 4:7]).max(axis=1) / ang[fast]
+    assert ef.max() < 8e-16, f"fast log: {ef.max():.2e} at angle {ang[fast][ef.argmax()]}"
     for col, name in ((7, "rcp"), (8, "sqrt"), (9, "rsqrt")):
         rel = np.abs(got[:, col] / ref[:, col] - 1.0)
         assert rel.max() < 3e-16, f"{name}: {rel.max():.2e}"
@@ -58,7 +63,7 @@ def test_host_build_of_the_so3_kernels():
     lib = emu_lib.load()
     v, x = inputs()
     v, x = np.ascontiguousarray(v), np.ascontiguousarray(x)
-    out = np.empty((x.size, 10))
+    out = np.empty((x.size, 14))
     lib.emu_selftest_so3(C.c_longlong(x.size), v.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     check(out, v, x)
 

@@ -27,3 +27,7 @@ def emit(name, c):
 emit("ATAN_OVER_T, u = t^2 in [0, 0.09], degree 9", fit(lambda u: mp.atan(mp.sqrt(u)) / mp.sqrt(u), mp.mpf("0.09"), 9))
 emit("COS_SQRT, v in [0, 0.25], degree 6", fit(lambda v: mp.cos(mp.sqrt(v)), mp.mpf("0.25"), 6))
 emit("SINC_SQRT, v in [0, 0.25], degree 6", fit(lambda v: mp.sin(mp.sqrt(v)) / mp.sqrt(v), mp.mpf("0.25"), 6))
+# log of a UNIT quaternion without a reciprocal: 2 asin(|vec|)/|vec| as a function of y = |vec|^2 = sin^2(theta/2),
+# on the same angle range as the atan kernel (tan^2(theta/2) <= 0.09  <=>  y <= 0.09 / 1.09)
+emit("TWO_ASIN_OVER_S, y = s^2 in [0, 0.09/1.09], degree 8",
+     fit(lambda y: 2 * mp.asin(mp.sqrt(y)) / mp.sqrt(y), mp.mpf("0.09") / mp.mpf("1.09"), 8))
