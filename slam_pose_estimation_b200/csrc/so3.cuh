@@ -105,6 +105,15 @@ UKFB_CONSTANT double SO3_ATAN_C[10] = {1.0, -0x1.5555555555500p-2, 0x1.999999998
                                        0x1.c71c6cf04ff82p-4, -0x1.745c4ca68d45dp-4, 0x1.3aff6b481f0f7p-4,
                                        -0x1.0fcd05c851591p-4, 0x1.c90783e417298p-5, -0x1.229f36308eeefp-5};
 
+/* cos / sinc for the fast kernels: half angle <= 0.3 rad, i.e. the same rotation angles (0.6 rad) as their log; degree 5
+ * is 2e-18 / 4e-19 from the functions on that range */
+constexpr double SO3_EXP5_FAST_X2 = 0.09;
+UKFB_CONSTANT double SO3_COS5_C[6] = {0x1.0000000000000p+0, -0x1.ffffffffffff8p-2, 0x1.55555555535c1p-5, -0x1.6c16c160642f9p-10,
+                                      0x1.a019c2f382291p-16, -0x1.274a2f4d3cb99p-22};
+UKFB_CONSTANT double SO3_SINC5_C[6] = {0x1.0000000000000p+0, -0x1.5555555555554p-3, 0x1.1111111110759p-7, -0x1.a01a0198e6dbbp-13,
+                                       0x1.71de13c236539p-19, -0x1.ada5cb577b3e1p-26};
+#define UKFB_POLY5(C, v, v2) fma(fma(C[5], v, C[4]), (v2) * (v2), fma(fma(C[3], v, C[2]), v2, fma(C[1], v, C[0])))
+
 /* 2 asin(s)/s as a function of y = s*s, y <= SO3_LOG_FAST_Y (the same angles as the atan kernel: tan^2 <= 0.09), degree 8:
  * 4e-17 from the function, and log(exp(v)) through pf_exp / pf_log within 7e-16 |v| of v (tests/test_so3_kernels.py) */
 constexpr double SO3_LOG_FAST_Y = 0.09 / 1.09;

@@ -60,10 +60,10 @@ UKFB_D void pf_exp(const double* v, double scale, double* q, bool& slow)
     const double half = scale * 0.5;
     const double norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     const double x2 = half * half * norm2;
-    slow = slow || !(x2 <= SO3_EXP_FAST_X2);
+    slow = slow || !(x2 <= SO3_EXP5_FAST_X2);
     const double x4 = x2 * x2;
-    const double c = UKFB_POLY6(SO3_COS_C, x2, x4);
-    const double mult = UKFB_POLY6(SO3_SINC_C, x2, x4) * half;
+    const double c = UKFB_POLY5(SO3_COS5_C, x2, x4);
+    const double mult = UKFB_POLY5(SO3_SINC5_C, x2, x4) * half;
     q[0] = mult * v[0];
     q[1] = mult * v[1];
     q[2] = mult * v[2];
