@@ -97,11 +97,11 @@ UKFB_D void of_point(const double* qs, const double* vs, const double* wb, const
                      const double* ref_q, const double* ref_v, double* d, bool& slow)
 {
     double av[3], e[4], qn[4], an[3], r[4];
-    quat_rotate(qs, wb, av);
+    pf_rotate(qs, wb, av);
     av[0] -= cx.earth[0], av[1] -= cx.earth[1], av[2] -= cx.earth[2];
     pf_exp(av, cx.dt, e, slow);
     quat_mul(e, qs, qn);
-    quat_rotate(qn, ab, an); /* with the UPDATED orientation (:22-23) */
+    pf_rotate(qn, ab, an); /* with the UPDATED orientation (:22-23) */
     an[2] -= gs;
     d[3] = fma(cx.dt, an[0], vs[0]) - ref_v[0];
     d[4] = fma(cx.dt, an[1], vs[1]) - ref_v[1];
@@ -157,7 +157,7 @@ UKFB_D void of_pair_b(const double* sm, int lane, int j, const OriMu& m, const O
         pf_exp(av, cx.dt, e, slow);
         quat_mul(e, m.q, qn);
         const double ab[3] = {cx.acc[0] - (m.ba[0] + sg * L[6]), cx.acc[1] - (m.ba[1] + sg * L[7]), cx.acc[2] - (m.ba[2] + sg * L[8])};
-        quat_rotate(qn, ab, an);
+        pf_rotate(qn, ab, an);
         an[2] -= m.g + sg * L[9];
         d[3] = fma(cx.dt, an[0], m.v[0] + sg * L[0]) - ref_v[0];
         d[4] = fma(cx.dt, an[1], m.v[1] + sg * L[1]) - ref_v[1];
@@ -671,10 +671,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         double dl = 0.0;
         UKFB_UNROLL
         for (int cc = 0; cc < 3; ++cc) {
-            double ks = 0.0;
-            UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) ks += k3[k] * S[k * 3 + cc];
-            ks3[cc] = ks;
+            ks3[cc] = Sxz[i * 3 + cc]; /* (K S)[i,:] = (Sxz S^-1 S)[i,:] = Sxz[i,:] */
             Sxz[i * 3 + cc] = k3[cc];
             dl += k3[cc] * innov[cc];
         }
