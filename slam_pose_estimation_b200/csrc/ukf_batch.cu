@@ -63,6 +63,7 @@ struct ukfb_handle {
     double* state = nullptr;
     double* Q = nullptr; /* LP (broadcast) or B x LP */
     int q_per_filter = 0;
+    int q_diagonal = 0; /* the broadcast Q has no off-diagonal entry (StepParams::q_diagonal) */
     uint32_t* status = nullptr;
     long long* t_last = nullptr;
     unsigned long long* hist = nullptr;
@@ -530,6 +531,7 @@ static StepParams base_params(const ukfb_handle* h)
     p.state = h->state;
     p.Q = h->Q;
     p.q_stride = h->q_per_filter ? h->LP : 0;
+    p.q_diagonal = h->q_per_filter ? 0 : h->q_diagonal;
     p.B = h->B;
     p.status = h->status;
     p.t_last = h->t_last;
@@ -634,6 +636,7 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         }
         CUH(cudaMemcpyAsync(h->Q, q, sizeof(double) * h->LP, cudaMemcpyHostToDevice, h->stream));
         CUH(cudaStreamSynchronize(h->stream));
+        h->q_diagonal = 1; /* zero, or the PoseUKF default diagonal */
     }
     /* stored acceleration: NaN sentinel for PoseUKF (PoseUKF.cpp:109), identity covariance (Measurement.hpp:11) */
     fill_kernel<double><<<grid_for(B * 3), 256, 0, h->stream>>>(h->acc_mu, B * 3, filter_kind == UKFB_POSE ? double(NAN) : 0.0);
@@ -802,6 +805,13 @@ extern "C" int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_f
         cudaFree(h->Q);
         h->Q = nq;
         h->q_per_filter = per_filter ? 1 : 0;
+    }
+    h->q_diagonal = 0;
+    if (!per_filter) { /* the lower triangle is what pack_q_kernel keeps */
+        h->q_diagonal = 1;
+        for (int r = 0; r < h->n; ++r)
+            for (int c = 0; c < r; ++c)
+                if (Q[r * h->n + c] != 0.0) h->q_diagonal = 0;
     }
     CU(cudaMemcpyAsync(h->stage, Q, bytes, cudaMemcpyHostToDevice, h->stream));
     pack_q_kernel<<<grid_for(count * h->LP), 256, 0, h->stream>>>(h->Q, reinterpret_cast<const double*>(h->stage), count, h->n, h->LP);

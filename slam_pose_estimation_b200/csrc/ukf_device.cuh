@@ -150,6 +150,9 @@ struct StepParams {
      * per `prefetch_bytes` of the record */
     long long prefetch_tiles;
     int prefetch_bytes;
+    /* fast kernels: the broadcast Q is diagonal (the reference's own default, PoseUKF.cpp:103-107, and the usual
+     * configuration): only its diagonal is loaded */
+    int q_diagonal;
 };
 
 UKFB_HD int meas_dim(int kind)

@@ -266,7 +266,7 @@ UKFB_DNI OfLit of_literal_update(double* sig, int kind, const double* zm, const 
 
 /* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
 /* On success: m holds the new mean, the record holds the new covariance.  `a` (prior covariance) is destroyed. */
-UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const double* Qp, const ModelArgs& ma, OriMu& m,
+UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig, double* a, const double* Qp, const ModelArgs& ma, OriMu& m,
                        uint32_t& status, int& passes_out, bool& spd)
 {
     OriCtx cx;
@@ -447,8 +447,9 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
     }
     if (slow) return false;
 
-    /* ---- new covariance = 1/2 C + process noise dt^2 Q' (OrientationUKF.cpp:81-86), committed to the record */
-    {
+    /* ---- new covariance = 1/2 C + process noise dt^2 Q' (OrientationUKF.cpp:81-86), committed to the record.
+     * qv(i, k) = Q[i][k], i >= k: a load, or for a broadcast diagonal Q a load on the diagonal and a literal zero elsewhere */
+    auto commit = [&](auto qv) {
         const double scale = dt * dt;
         double nb[12]; /* the two rotated blocks of the noise; every other entry is scale * Q */
         UKFB_UNROLL
@@ -461,7 +462,7 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
                 for (int k = 0; k < 3; ++k) {
                     double s = 0.0;
                     UKFB_UNROLL
-                    for (int l = 0; l < 3; ++l) s += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
+                    for (int l = 0; l < 3; ++l) s += Rm[r * 3 + l] * (l >= k ? qv(off + l, off + k) : qv(off + k, off + l));
                     t[r * 3 + k] = s;
                 }
             }
@@ -483,7 +484,7 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
             for (int k = 0; k <= i; ++k) {
                 const int e = tri(i, k);
                 const double dk = k < 9 ? cg : (k < 12 ? ca : 1.0);
-                const double nz = (i < 6 && i / 3 == k / 3) ? nb[(i / 3) * 6 + tri(i % 3, k % 3)] : scale * UKFB_LDG(Qp + e);
+                const double nz = (i < 6 && i / 3 == k / 3) ? nb[(i / 3) * 6 + tri(i % 3, k % 3)] : scale * qv(i, k);
                 double s;
                 if (i < 6)
                     s = fma(0.5, C[e], nz);
@@ -494,7 +495,11 @@ UKFB_D bool of_predict(double* sm, int lane, double* sig, double* a, const doubl
                 sig[e * TILE] = s;
             }
         }
-    }
+    };
+    if (par.q_diagonal)
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; });
+    else
+        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); });
     m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
     m.v[0] = ref_v[0], m.v[1] = ref_v[1], m.v[2] = ref_v[2];
     UKFB_UNROLL
@@ -941,7 +946,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
             UKFB_UNROLL
             for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
             bool spd = true;
-            if (of_predict(sm, lane, sig, a, Qp, ma, m, status, passes_a, spd)) {
+            if (of_predict(p, sm, lane, sig, a, Qp, ma, m, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
                     do_upd = false; /* every later factorisation of this covariance fails too */

@@ -346,8 +346,8 @@ UKFB_DNI PfLit pf_literal_update(double* sig, int kind, const double* zm, const 
 /* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
 /* On success: m holds the new mean, the record and (when to_smem) slots 0..77 hold the new covariance.
  * `a` (the prior covariance, packed lower) is destroyed. */
-UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const double* Qp, const double* acov, const ModelArgs& ma,
-                       PoseMu& m, bool to_smem, uint32_t& status, int& passes_out, bool& spd)
+UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig, double* a, const double* Qp, const double* acov,
+                       const ModelArgs& ma, PoseMu& m, bool to_smem, uint32_t& status, int& passes_out, bool& spd)
 {
     const double dt = ma.dt;
     /* Cholesky of the covariance (a: loaded from the record by the caller), in registers; the factor goes to the
@@ -495,8 +495,10 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
     }
     if (slow) return false;
 
-    /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record */
-    {
+    /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record.  qv(i, k) = Q[i][k], i >= k:
+     * a load, or for a broadcast diagonal Q (the reference's default and the usual configuration) a load on the diagonal
+     * and a literal zero elsewhere, which leaves 12 loads of the 78 */
+    auto commit = [&](auto qv) {
         const double scale = ma.has_acc ? 1.0 : dt;
         /* the entries of the noise that are not plain scale * Q: the two rotated blocks, or 2 acc.cov */
         double nb[12], na[6];
@@ -515,7 +517,7 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
                     for (int k = 0; k < 3; ++k) {
                         double s = 0.0;
                         UKFB_UNROLL
-                        for (int l = 0; l < 3; ++l) s += Rm[r * 3 + l] * q_sym(Qp, off + l, off + k);
+                        for (int l = 0; l < 3; ++l) s += Rm[r * 3 + l] * (l >= k ? qv(off + l, off + k) : qv(off + k, off + l));
                         t[r * 3 + k] = s;
                     }
                 }
@@ -542,7 +544,7 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
             UKFB_UNROLL
             for (int k = 0; k <= i; ++k) {
                 const int e = tri(i, k);
-                double nz = scale * UKFB_LDG(Qp + e);
+                double nz = scale * qv(i, k);
                 if (i < 6 && i / 3 == k / 3) nz = ma.has_acc ? nz : nb[(i / 3) * 6 + tri(i % 3, k % 3)];
                 if (i >= 6 && i < 9 && k >= 6) nz = ma.has_acc ? na[tri(i - 6, k - 6)] : nz;
                 double s;
@@ -556,7 +558,11 @@ UKFB_D bool pf_predict(double* sm, int lane, double* sig, double* a, const doubl
                 if (to_smem) UKFB_PS(e) = s;
             }
         }
-    }
+    };
+    if (par.q_diagonal)
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; });
+    else
+        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); });
     m.p[0] = ref_p[0], m.p[1] = ref_p[1], m.p[2] = ref_p[2];
     m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
     m.v[0] = vm[0], m.v[1] = vm[1], m.v[2] = vm[2];
@@ -1076,7 +1082,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB
             ma.has_acc = (fabs(ma.acc[0]) <= big) && (fabs(ma.acc[1]) <= big) && (fabs(ma.acc[2]) <= big);
             bool spd = true;
             const bool want_smem = do_upd && kind != UKFB_MEAS_POSE_ORIENTATION;
-            if (pf_predict(sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
+            if (pf_predict(p, sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
                     do_upd = false; /* every later factorisation of this covariance fails too */

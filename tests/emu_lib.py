@@ -17,6 +17,9 @@ _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_emu")
 _LIB = None
 
 
+Q_DIAGONAL_FLAG = True  # tests flip this to run a diagonal Q through the general noise code
+
+
 class StepParams(C.Structure):
     _fields_ = [
         ("state", C.c_void_p), ("Q", C.c_void_p), ("q_stride", C.c_longlong), ("B", C.c_longlong),
@@ -31,7 +34,7 @@ class StepParams(C.Structure):
         ("r_kstride", C.c_longlong), ("kinds_kstride", C.c_longlong), ("mask_kstride", C.c_longlong),
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
         ("events", C.c_int), ("r_kind_stride", C.c_longlong), ("gate_d2", C.c_double),
-        ("ori_params", C.c_void_p), ("prefetch_tiles", C.c_longlong), ("prefetch_bytes", C.c_int),
+        ("ori_params", C.c_void_p), ("prefetch_tiles", C.c_longlong), ("prefetch_bytes", C.c_int), ("q_diagonal", C.c_int),
     ]
 
 
@@ -153,6 +156,10 @@ class EmuBatch:
         p.state = _ptr(self.state)
         self._Q = np.ascontiguousarray(self.Q)
         p.Q = _ptr(self._Q)
+        if self.q_stride == 0 and Q_DIAGONAL_FLAG:  # as the engine does for a broadcast Q without off-diagonal entries
+            full = np.zeros((self.n, self.n))
+            full[self.tril] = self._Q
+            p.q_diagonal = int(not np.any(full - np.diag(np.diag(full))))
         p.q_stride = self.q_stride
         p.B = self.B
         p.K = 1

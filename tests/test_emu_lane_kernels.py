@@ -307,3 +307,35 @@ def test_unnormalised_quaternions_take_the_literal_expressions(filt):
     P.assert_parity(0 if filt == "pose" else 1, e.get_state(), o.get_state(), tol=TOL, what=f"{filt} unnormalised q")
     fb = e.fallbacks() - before
     assert fb[0] >= 2 and fb.sum() < 3 * 4 * B, f"fallbacks {fb}"
+
+
+def test_diagonal_noise_path_equals_the_general_one(monkeypatch):
+    """A broadcast Q without off-diagonal entries (the reference's default) is read through 12 loads instead of 78
+    (StepParams::q_diagonal); the same run through the general noise code gives the same bits, and a dense Q does not
+    take the shortcut."""
+    import emu_lib
+
+    B = 33
+    out = []
+    for flag in (True, False):
+        monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", flag)
+        e = P.make_pose(EmuBatch, B, kernel="fast")
+        P.run_pose_c3(e, B, 6)
+        out.append(e.get_state())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    out = []
+    for flag in (True, False):
+        monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", flag)
+        e = P.make_ori(EmuBatch, B, kernel="fast")
+        P.run_ori_c1(e, B, 6, every=3)
+        out.append(e.get_state())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", True)
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(12, 12)) * 0.01
+    Q = A @ A.T
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel="fast")
+    for x in (o, e):
+        x.set_process_noise(Q)
+        P.run_pose_c3(x, B, 4)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what="dense broadcast Q")

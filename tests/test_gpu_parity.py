@@ -222,6 +222,25 @@ def test_process_noise_roundtrip_and_per_filter(Ukf):
     P.assert_parity(0, g.get_state(), o.get_state(), what="per-filter Q")
 
 
+@pytest.mark.parametrize("filt", [0, 1])
+def test_dense_and_diagonal_broadcast_process_noise(Ukf, filt):
+    """a broadcast Q without off-diagonal entries takes the 12/13-load path of the fast kernels, a dense one the general path"""
+    B = 40
+    n = 12 if filt == 0 else 13
+    rng = np.random.default_rng(11)
+    A = rng.normal(size=(n, n)) * 0.01
+    for Q in (A @ A.T, np.diag(rng.uniform(1e-6, 1e-3, n))):
+        g, o = both(Ukf, filt, B)
+        for x in (g, o):
+            x.set_process_noise(Q)
+            if filt == 0:
+                P.run_pose_c3(x, B, 8)
+            else:
+                P.run_ori_c1(x, B, 8, every=4)
+        assert np.array_equal(np.tril(g.get_process_noise()), np.tril(Q))  # the engine keeps the lower triangle
+        P.assert_parity(filt, g.get_state(), o.get_state(), what="broadcast Q")
+
+
 # ---- streams ---------------------------------------------------------------------------------------
 
 def test_pose_c3_200_steps(Ukf):
