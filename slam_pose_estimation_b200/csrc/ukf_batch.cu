@@ -636,7 +636,7 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         }
         CUH(cudaMemcpyAsync(h->Q, q, sizeof(double) * h->LP, cudaMemcpyHostToDevice, h->stream));
         CUH(cudaStreamSynchronize(h->stream));
-        h->q_diagonal = 1; /* zero, or the PoseUKF default diagonal */
+        h->q_diagonal = 2; /* zero, or the PoseUKF default diagonal (one value per 3 x 3 block) */
     }
     /* stored acceleration: NaN sentinel for PoseUKF (PoseUKF.cpp:109), identity covariance (Measurement.hpp:11) */
     fill_kernel<double><<<grid_for(B * 3), 256, 0, h->stream>>>(h->acc_mu, B * 3, filter_kind == UKFB_POSE ? double(NAN) : 0.0);
@@ -812,6 +812,9 @@ extern "C" int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_f
         for (int r = 0; r < h->n; ++r)
             for (int c = 0; c < r; ++c)
                 if (Q[r * h->n + c] != 0.0) h->q_diagonal = 0;
+        const int n = h->n;
+        if (h->q_diagonal && Q[0] == Q[n + 1] && Q[0] == Q[2 * n + 2] && Q[3 * n + 3] == Q[4 * n + 4] && Q[3 * n + 3] == Q[5 * n + 5])
+            h->q_diagonal = 2;
     }
     CU(cudaMemcpyAsync(h->stage, Q, bytes, cudaMemcpyHostToDevice, h->stream));
     pack_q_kernel<<<grid_for(count * h->LP), 256, 0, h->stream>>>(h->Q, reinterpret_cast<const double*>(h->stage), count, h->n, h->LP);

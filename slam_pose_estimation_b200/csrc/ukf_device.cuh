@@ -150,8 +150,9 @@ struct StepParams {
      * per `prefetch_bytes` of the record */
     long long prefetch_tiles;
     int prefetch_bytes;
-    /* fast kernels: the broadcast Q is diagonal (the reference's own default, PoseUKF.cpp:103-107, and the usual
-     * configuration): only its diagonal is loaded */
+    /* fast kernels: 1 = the broadcast Q is diagonal (the reference's own default, PoseUKF.cpp:103-107, and the usual
+     * configuration): only its diagonal is loaded; 2 = moreover entries 0..2 are equal and entries 3..5 are equal, so the
+     * two blocks the filters rotate into the navigation frame (R Q_blk R^T) are multiples of the identity and stay so */
     int q_diagonal;
 };
 

@@ -449,9 +449,16 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
 
     /* ---- new covariance = 1/2 C + process noise dt^2 Q' (OrientationUKF.cpp:81-86), committed to the record.
      * qv(i, k) = Q[i][k], i >= k: a load, or for a broadcast diagonal Q a load on the diagonal and a literal zero elsewhere */
-    auto commit = [&](auto qv) {
+    auto commit = [&](auto qv, auto iso) {
         const double scale = dt * dt;
         double nb[12]; /* the two rotated blocks of the noise; every other entry is scale * Q */
+        UKFB_UNROLL
+        for (int i = 0; i < 12; ++i) nb[i] = 0.0;
+        if (decltype(iso)::value) {
+            /* R (q I) R^T = q I for both rotated blocks: the rotation changes nothing */
+            nb[tri(0, 0)] = nb[tri(1, 1)] = nb[tri(2, 2)] = scale * qv(0, 0);
+            nb[6 + tri(0, 0)] = nb[6 + tri(1, 1)] = nb[6 + tri(2, 2)] = scale * qv(3, 3);
+        } else {
         UKFB_UNROLL
         for (int blk = 0; blk < 2; ++blk) {
             const int off = blk * 3;
@@ -477,6 +484,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
                 }
             }
         }
+        }
         UKFB_UNROLL
         for (int i = 0; i < 13; ++i) {
             const double di = i < 9 ? cg : (i < 12 ? ca : 1.0);
@@ -496,10 +504,12 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
             }
         }
     };
-    if (par.q_diagonal)
-        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; });
+    if (par.q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, TrueT());
+    else if (par.q_diagonal)
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, FalseT());
     else
-        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); });
+        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); }, FalseT());
     m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
     m.v[0] = ref_v[0], m.v[1] = ref_v[1], m.v[2] = ref_v[2];
     UKFB_UNROLL

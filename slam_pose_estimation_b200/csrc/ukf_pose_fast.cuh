@@ -145,6 +145,9 @@ UKFB_D bool pf_cholesky(double* a)
     return ok;
 }
 
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
+
 struct PoseMu {
     double p[3], q[4], v[3], w[3];
 };
@@ -498,7 +501,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
     /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record.  qv(i, k) = Q[i][k], i >= k:
      * a load, or for a broadcast diagonal Q (the reference's default and the usual configuration) a load on the diagonal
      * and a literal zero elsewhere, which leaves 12 loads of the 78 */
-    auto commit = [&](auto qv) {
+    auto commit = [&](auto qv, auto iso) {
         const double scale = ma.has_acc ? 1.0 : dt;
         /* the entries of the noise that are not plain scale * Q: the two rotated blocks, or 2 acc.cov */
         double nb[12], na[6];
@@ -506,7 +509,11 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         for (int i = 0; i < 12; ++i) nb[i] = 0.0;
         UKFB_UNROLL
         for (int i = 0; i < 6; ++i) na[i] = 0.0;
-        if (!ma.has_acc) {
+        if (!ma.has_acc && decltype(iso)::value) {
+            /* R (q I) R^T = q I for both rotated blocks (the reference's default Q: the rotation changes nothing) */
+            nb[tri(0, 0)] = nb[tri(1, 1)] = nb[tri(2, 2)] = scale * qv(0, 0);
+            nb[6 + tri(0, 0)] = nb[6 + tri(1, 1)] = nb[6 + tri(2, 2)] = scale * qv(3, 3);
+        } else if (!ma.has_acc) {
             UKFB_UNROLL
             for (int blk = 0; blk < 2; ++blk) {
                 const int off = blk * 3;
@@ -559,10 +566,12 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
             }
         }
     };
-    if (par.q_diagonal)
-        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; });
+    if (par.q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, TrueT());
+    else if (par.q_diagonal)
+        commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, FalseT());
     else
-        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); });
+        commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); }, FalseT());
     m.p[0] = ref_p[0], m.p[1] = ref_p[1], m.p[2] = ref_p[2];
     m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
     m.v[0] = vm[0], m.v[1] = vm[1], m.v[2] = vm[2];

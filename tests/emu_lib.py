@@ -17,7 +17,7 @@ _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_emu")
 _LIB = None
 
 
-Q_DIAGONAL_FLAG = True  # tests flip this to run a diagonal Q through the general noise code
+Q_DIAGONAL_FLAG = 2  # 2: as the engine sets StepParams::q_diagonal; 1: never the isotropic-block shortcut; 0: always the general code
 
 
 class StepParams(C.Structure):
@@ -159,7 +159,10 @@ class EmuBatch:
         if self.q_stride == 0 and Q_DIAGONAL_FLAG:  # as the engine does for a broadcast Q without off-diagonal entries
             full = np.zeros((self.n, self.n))
             full[self.tril] = self._Q
-            p.q_diagonal = int(not np.any(full - np.diag(np.diag(full))))
+            dg = np.diag(full)
+            p.q_diagonal = int(not np.any(full - np.diag(dg)))
+            if p.q_diagonal and Q_DIAGONAL_FLAG == 2 and dg[0] == dg[1] == dg[2] and dg[3] == dg[4] == dg[5]:
+                p.q_diagonal = 2
         p.q_stride = self.q_stride
         p.B = self.B
         p.K = 1

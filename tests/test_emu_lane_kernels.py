@@ -309,28 +309,23 @@ def test_unnormalised_quaternions_take_the_literal_expressions(filt):
     assert fb[0] >= 2 and fb.sum() < 3 * 4 * B, f"fallbacks {fb}"
 
 
-def test_diagonal_noise_path_equals_the_general_one(monkeypatch):
-    """A broadcast Q without off-diagonal entries (the reference's default) is read through 12 loads instead of 78
-    (StepParams::q_diagonal); the same run through the general noise code gives the same bits, and a dense Q does not
-    take the shortcut."""
+def test_diagonal_noise_paths_equal_the_general_one(monkeypatch):
+    """A broadcast Q without off-diagonal entries (the reference's default) is read through 12 / 13 loads instead of 78 / 91
+    (StepParams::q_diagonal = 1): the same bits as the general noise code.  With one value per rotated 3 x 3 block
+    (q_diagonal = 2) R (q I) R^T is taken as q I: equal to rounding.  A dense Q takes neither shortcut."""
     import emu_lib
 
     B = 33
-    out = []
-    for flag in (True, False):
-        monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", flag)
-        e = P.make_pose(EmuBatch, B, kernel="fast")
-        P.run_pose_c3(e, B, 6)
-        out.append(e.get_state())
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
-    out = []
-    for flag in (True, False):
-        monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", flag)
-        e = P.make_ori(EmuBatch, B, kernel="fast")
-        P.run_ori_c1(e, B, 6, every=3)
-        out.append(e.get_state())
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
-    monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", True)
+    for make, run, filt in ((P.make_pose, lambda e: P.run_pose_c3(e, B, 6), 0), (P.make_ori, lambda e: P.run_ori_c1(e, B, 6, every=3), 1)):
+        out = {}
+        for flag in (2, 1, 0):
+            monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", flag)
+            e = make(EmuBatch, B, kernel="fast")
+            run(e)
+            out[flag] = e.get_state()
+        assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+        P.assert_parity(filt, out[2], out[0], tol=1e-13, what="isotropic noise blocks")
+    monkeypatch.setattr(emu_lib, "Q_DIAGONAL_FLAG", 2)
     rng = np.random.default_rng(5)
     A = rng.normal(size=(12, 12)) * 0.01
     Q = A @ A.T
@@ -339,3 +334,9 @@ def test_diagonal_noise_path_equals_the_general_one(monkeypatch):
         x.set_process_noise(Q)
         P.run_pose_c3(x, B, 4)
     P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what="dense broadcast Q")
+    Qd = np.diag(np.linspace(1e-6, 1e-3, 12))  # diagonal, but not one value per block
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(EmuBatch, B, kernel="fast")
+    for x in (o, e):
+        x.set_process_noise(Qd)
+        P.run_pose_c3(x, B, 4)
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what="anisotropic diagonal Q")
