@@ -117,6 +117,9 @@ UKFB_CONSTANT double SO3_SINC5_C[6] = {0x1.0000000000000p+0, -0x1.5555555555554p
 /* 2 asin(s)/s as a function of y = s*s, y <= SO3_LOG_FAST_Y (the same angles as the atan kernel: tan^2 <= 0.09), degree 8:
  * 4e-17 from the function, and log(exp(v)) through pf_exp / pf_log within 7e-16 |v| of v (tests/test_so3_kernels.py) */
 constexpr double SO3_LOG_FAST_Y = 0.09 / 1.09;
+/* for a quaternion with | |q|^2 - 1 | <= 1e-7:  w >= SO3_LOG_FAST_W  implies  w > 0 and |vec|^2 <= SO3_LOG_FAST_Y
+ * (sqrt(1 - Y) (1 + 1e-6): W^2 = 0.917433027, so |vec|^2 <= 1.0000001 - W^2 = 0.0825671 < Y = 0.0825688) */
+constexpr double SO3_LOG_FAST_W = 0.957827243;
 UKFB_CONSTANT double SO3_ASIN_C[9] = {0x1.0000000000000p+1, 0x1.555555555503dp-2, 0x1.333333340075ap-3, 0x1.6db6daa72c4afp-4,
                                       0x1.f1c77c63fd8f8p-5, 0x1.6e7ea9f45b674p-5, 0x1.1d54d58e79ab9p-5, 0x1.b1cba0f288f34p-6,
                                       0x1.05955d9d4e360p-5};

@@ -81,7 +81,7 @@ UKFB_D void pf_log(const double* q, double* out, bool& slow)
     const double nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
     const double w = q[3];
     const double d = fma(w, w, nv2) - 1.0;
-    slow = slow || !(nv2 <= SO3_LOG_FAST_Y) || !(w > 0.0);
+    slow = slow || !(w >= SO3_LOG_FAST_W); /* one comparison: w > 0 and nv2 within the polynomial's range (|q| = 1 to 1e-7) */
     const double s0 = two_asin_over_s_poly(fma(-nv2, d, nv2));
     const double s = fma(s0, -0.5 * d, s0);
     out[0] = s * q[0];
