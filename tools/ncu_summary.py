@@ -22,7 +22,7 @@ try:
     ops = {k: val(f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") * cyc for k in ("dadd", "dmul", "dfma")}
     flops = ops["dadd"] + ops["dmul"] + 2 * ops["dfma"]
     inst = ops["dadd"] + ops["dmul"] + ops["dfma"]
-    ms = val("gpu__time_duration.sum")
+    ms = val("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].strip(), 1.0)
     print(f"  executed FP64 thread-instructions per filter: dadd {ops['dadd']/nf:.0f} dmul {ops['dmul']/nf:.0f} dfma {ops['dfma']/nf:.0f}"
           f"  = {inst/nf:.0f} instr, {flops/nf:.0f} flops (FMA = 2)")
     print(f"  executed FP64 rate: {flops/(ms*1e-3)/1e12:.2f} TFLOP/s; FP64 issue slots used: {100*inst/(cyc*148*64):.1f}% of 64 lanes/clk/SM")
