@@ -14,6 +14,9 @@
  * single reciprocal.  They evaluate the same functions as MTK's expressions
  * (cos x, sin x / x, 2 atan(|v|/w)/|v|) to within an ulp or two, well inside the
  * 1e-9 parity tolerance; outside that range the literal MTK expressions are used.
+ * The two structure-exploiting kernels (ukf_pose_fast.cuh, ukf_ori_fast.cuh) use a
+ * leaner pair on rotations of at most 0.58 rad: degree-5 cos / sinc and a log of a
+ * unit quaternion without the reciprocal (2 asin(s)/s in s^2, SO3_ASIN_C below).
  */
 #ifndef UKFB_SO3_CUH
 #define UKFB_SO3_CUH

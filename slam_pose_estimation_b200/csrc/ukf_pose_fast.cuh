@@ -28,7 +28,8 @@
  *     recomputed, from the 12 points of columns 0..5 (the others carry the orientation of X_0), and only the first
  *     six columns of the second Cholesky factor are needed.
  *
- * All SO(3) exp/log calls here are the branch-free polynomial kernels of so3.cuh; a lane whose argument leaves the
+ * All SO(3) exp/log calls here are branch-free polynomial kernels (pf_exp: degree-5 cos / sinc; pf_log: no reciprocal, for
+ * quaternions of unit norm, which pf_unit checks once per phase); a lane whose argument leaves the
  * polynomial range or that fails a guard falls back to the literal code of
  * ukf_thread.cuh (out of line, cold), which is also what UKFB_KERNEL=thread runs for every filter.
  * Covariance accumulators (57 / 33 doubles) and the state stay in registers, both Cholesky factorisations run in

@@ -1,7 +1,7 @@
 """The SO(3) exp / log kernels (csrc/so3.cuh: near-minimax polynomials inside their ranges, libm outside) and the
 Newton reciprocal / square root of csrc/simt.cuh against 50-digit mpmath values, over the whole range the filters can
 reach: rotation angles from 1e-12 to just below pi, across the polynomial boundaries (half angle 0.5 rad in exp, 33 degrees
-in log).  CPU: the host build of the same source; GPU: ukfb_selftest_so3."""
+in log), and the fast kernels' own pair (degree-5 exp, reciprocal-free log) on its range of 0.58 rad.  CPU: the host build of the same source; GPU: ukfb_selftest_so3."""
 from __future__ import annotations
 
 import ctypes as C
