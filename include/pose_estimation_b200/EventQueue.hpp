@@ -8,7 +8,9 @@
  * (UnscentedKalmanFilter.hpp:83-100, PoseUKF.cpp:112-178, OrientationUKF.cpp:53-72).  With many filters behind
  * one object that loop would cost one kernel launch per sample; this queue collects the callbacks of all filters
  * and flush() hands them to ukfb_run_events, which runs every queued sample of every filter -- in each filter's own
- * order -- in ONE launch.  The result is the same as making the calls one by one.
+ * order -- in ONE launch.  The result is the same as making the calls one by one with a try / catch around each
+ * callback: when predictionStep throws for a sample (negative or too large time step, UnscentedKalmanFilter.hpp:110-122)
+ * that callback ends, i.e. the sample is neither integrated nor stored, and the next sample is served normally.
  *
  * Exceptions: like the filter classes, flush() turns the status bits of the launch into the reference's
  * exceptions (first offending condition; all other samples have been integrated).

@@ -53,7 +53,13 @@ public:
     {
         check(ukfb_initialize(h, initial_state->v, state_cov->v));
     }
-    void initializeFilter(const State& initial_state, const Covariance& state_cov) { initializeFilter(&initial_state, &state_cov); }
+    /* the reference's signature: one filter.  On an object built with batch > 1 the C ABI would read `batch` states
+     * behind the single struct, so that is refused rather than left to overrun. */
+    void initializeFilter(const State& initial_state, const Covariance& state_cov)
+    {
+        single("initializeFilter(const State&, const Covariance&)");
+        initializeFilter(&initial_state, &state_cov);
+    }
 
     /* @returns false if the filter has not been initialized (:51-75) */
     bool getCurrentState(State* state, Covariance* state_cov) const
@@ -63,8 +69,16 @@ public:
         check(rc);
         return true;
     }
-    bool getCurrentState(State& state, Covariance& state_cov) const { return getCurrentState(&state, &state_cov); }
-    bool getCurrentState(State& state) const { return getCurrentState(&state, nullptr); }
+    bool getCurrentState(State& state, Covariance& state_cov) const
+    {
+        single("getCurrentState(State&, Covariance&)");
+        return getCurrentState(&state, &state_cov);
+    }
+    bool getCurrentState(State& state) const
+    {
+        single("getCurrentState(State&)");
+        return getCurrentState(&state, nullptr);
+    }
 
     /* :83-100; sample_time in microseconds (base::Time::microseconds) */
     void predictionStepFromSampleTime(int64_t sample_time_us)
@@ -113,6 +127,14 @@ public:
     void setMinTimeDelta(double min_time_delta) { check(ukfb_set_time_bounds(h, min_time_delta, getMaxTimeDelta())); }
 
 protected:
+    /* the by-reference overloads carry ONE state: batch objects must use the pointer (array) overloads */
+    void single(const char* what) const
+    {
+        if (batch_size != 1)
+            throw std::logic_error(std::string("ukf_batch: ") + what + " serves a single filter; this object holds " +
+                                   std::to_string(batch_size) + " -- pass arrays of `batch` entries to the pointer overload");
+    }
+
     /* a failed C ABI call is API misuse or a CUDA failure, never a filter condition */
     static void check(int rc)
     {

@@ -2,8 +2,9 @@
  * ukf_batch.h -- C ABI of the B200-native batched unscented Kalman filter engine.
  *
  * Drop-in boundary for the predict/update hot path of rock-slam/slam-pose_estimation.
- * One handle owns B independent filters of one kind (PoseUKF or OrientationUKF) on
- * ONE CUDA device; filter b of the batch behaves exactly like one instance of the
+ * One handle owns B independent filters of one kind (PoseUKF or OrientationUKF), on ONE
+ * CUDA device (ukfb_create) or split by filter index over several devices of one box
+ * (ukfb_create_sharded); filter b of the batch behaves exactly like one instance of the
  * reference class.  Every entry point below names the reference interface it
  * replaces (file:line relative to the reference tree).  The reference is a C++
  * class API with no FFI of its own; the headers under include/pose_estimation_b200/ re-create
@@ -29,7 +30,8 @@
  *     that filter exactly as the throw would have skipped it, and a sticky
  *     per-filter status bit UKFB_STATUS_* is set.  The C++ shim re-throws.
  *   - a handle is single-caller (the reference is not thread-safe either,
- *     UnscentedKalmanFilter.hpp:16); different handles are independent.
+ *     UnscentedKalmanFilter.hpp:16); different handles are independent and may be
+ *     driven from different host threads (a sharded handle does exactly that inside).
  *   - there is no CPU fallback: every entry point fails with UKFB_ERR_CUDA when no
  *     sm_100-class device is usable.
  */
@@ -99,6 +101,28 @@ const char* ukfb_last_error(void);
 int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_handle** out);
 int ukfb_destroy(ukfb_handle* h);
 
+/* The same B filters split by filter index over n_devices CUDA devices of one box.  Reference objects share nothing
+ * (each owns its mu, sigma, Q and timestamp: UnscentedKalmanFilter.hpp:150-154), so shard i holds the contiguous
+ * index range [first_i, first_i + count_i) with counts batch / n (+1 for the first batch % n shards), on devices[i],
+ * with its own CUDA streams and its own host worker thread; there is no inter-device traffic.
+ * EVERY host-pointer entry point of this header (blocking and _async) accepts the handle: the call fans out, each worker
+ * serves its range of the caller's arrays, and the call returns when all shards have (ukfb_get_state[_async] therefore
+ * lands all shards in the caller's single host buffer: the final gather).  Scalars and broadcast arguments
+ * (per_filter = 0) go to every shard.  Results per filter are bit-for-bit those of a one-device handle.
+ * `_dev` entry points take pointers of ONE device: on a sharded handle they return UKFB_ERR_INVALID; use them on the
+ * per-device handles ukfb_shard() hands out.  devices = NULL: devices 0 .. n_devices - 1.  A device may appear twice. */
+int ukfb_create_sharded(int filter_kind, int64_t batch, const int* devices, int n_devices, ukfb_handle** out);
+/* number of shards (1 for a ukfb_create handle) */
+int ukfb_shard_count(const ukfb_handle* h);
+/* shard i of a sharded handle: its one-device handle (owned by the parent: do not destroy), first filter and count.
+ * On a one-device handle, i = 0 returns the handle itself. */
+int ukfb_shard(ukfb_handle* h, int i, ukfb_handle** shard, int64_t* first, int64_t* count);
+
+/* Page-locked host memory visible to every device (cudaHostAllocPortable), for callers without the CUDA headers: the
+ * _async entry points only overlap copies with kernels when their host arrays are pinned. */
+int ukfb_host_alloc(void** ptr, uint64_t bytes);
+int ukfb_host_free(void* ptr);
+
 int64_t ukfb_batch(const ukfb_handle* h);
 int ukfb_dof(const ukfb_handle* h);     /* getStateSize(), UnscentedKalmanFilter.hpp:127 */
 int ukfb_mu_size(const ukfb_handle* h); /* 13 / 14 */
@@ -117,6 +141,13 @@ int ukfb_is_initialized(const ukfb_handle* h);
  * Returns UKFB_ERR_NOT_INITIALIZED where the reference returns false. */
 int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma);
 int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma);
+
+/* A contiguous range [mu_first, mu_first + mu_count) of the state vector only, out: B x mu_count.  What a consumer of
+ * toRigidBodyState's pose needs (BodyStateMeasurement.hpp:30-31: position and orientation = entries 0..6 of a POSE
+ * state) is 56 of the 104 bytes per filter of the full mean; on a link-bound host that is the difference. */
+int ukfb_get_mu_range(ukfb_handle* h, int mu_first, int mu_count, double* out);
+int ukfb_get_mu_range_dev(ukfb_handle* h, int mu_first, int mu_count, double* d_out);
+int ukfb_get_mu_range_async(ukfb_handle* h, int mu_first, int mu_count, double* out); /* rules of ukfb_get_state_async */
 
 /* BodyStateMeasurement (pose_with_velocity/BodyStateMeasurement.hpp:12-41), the format the reference's callers
  * exchange PoseUKF states in, for every filter of a POSE handle.  One base::samples::RigidBodyState is passed as
@@ -189,6 +220,8 @@ int ukfb_meas_dim(int meas_kind);
 /* Asynchronous mixed measurements (BASELINE.json config 5): kinds[b] is the kind
  * filter b integrates now (UKFB_MEAS_NONE = none).  mu: B x 3 and cov: B x 3 x 3,
  * the leading m / m x m block of each slot is used. */
+/* (a kind of the other filter class: UKFB_ERR_INVALID from the host-pointer call, which can read the array; ignored and
+ * flagged UKFB_STATUS_BAD_EVENT by the `_dev` call, whose kinds live on the device) */
 int ukfb_update_mixed(ukfb_handle* h, const int8_t* kinds, const double* mu3, const double* cov33);
 int ukfb_update_mixed_dev(ukfb_handle* h, const int8_t* d_kinds, const double* d_mu3, const double* d_cov33);
 
@@ -245,7 +278,9 @@ int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, c
  * (the leading m values are used).  Covariances: cov_mode 0 = one table cov[UKFB_EVENT_KIND_COUNT][3][3] indexed by
  * kind (a sensor's covariance, leading m x m block), 1 = one per event, cov[(k * B + b) * 9].
  * All K slots of all filters run in ONE kernel launch with the filter state resident on chip; time guards, the
- * first-call latch, finite checks and status bits behave per event as in the single calls.  A kind the filter class
+ * first-call latch, finite checks and status bits behave per event as in the single calls.  A sample whose time step is
+ * negative or above max_dt is flagged (UKFB_STATUS_NEG_DT / DT_TOO_LARGE) and NOT integrated or stored: the reference's
+ * callback leaves at the throw of predictionStep (:110-122), before its integrateMeasurement.  A kind the filter class
  * has no overload for is ignored and flagged UKFB_STATUS_BAD_EVENT. */
 int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us, const int8_t* d_kinds, const double* d_mu3,
                         const double* d_cov, int cov_mode);
@@ -270,8 +305,16 @@ int ukfb_clear_mean_iter_hist(ukfb_handle* h);
 /* ---- stream plumbing ------------------------------------------------------- */
 
 int ukfb_synchronize(ukfb_handle* h);
-/* the handle's cudaStream_t, as an opaque pointer */
+/* the handle's cudaStream_t, as an opaque pointer (NULL for a sharded handle: see ukfb_shard) */
 void* ukfb_stream(ukfb_handle* h);
+/* Ordering against the caller's own CUDA streams, for the `_dev` entry points (they enqueue on the handle's stream, a
+ * cudaStreamNonBlocking stream that does not synchronise with the legacy default stream either):
+ *   ukfb_wait_for_stream: work enqueued on the handle from now on starts after everything enqueued so far on
+ *     `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) -- call it after producing `_dev` inputs;
+ *   ukfb_stream_wait: work enqueued on `cuda_stream` from now on starts after everything enqueued so far on the
+ *     handle -- call it before consuming `_dev` outputs (ukfb_get_state_dev, ...). */
+int ukfb_wait_for_stream(ukfb_handle* h, void* cuda_stream);
+int ukfb_stream_wait(ukfb_handle* h, void* cuda_stream);
 /* CUDA events on the handle's stream, slots 0..15 */
 int ukfb_event_record(ukfb_handle* h, int slot);
 int ukfb_event_elapsed_ms(ukfb_handle* h, int slot_begin, int slot_end, float* ms);

@@ -365,7 +365,7 @@ int orc_set_rotation_rate(void* h, const double* mu, const double* cov, int cov_
 /* The reference's caller loop (one aggregator callback per sensor sample, in timestamp order):
  *     filter.predictionStepFromSampleTime(ts);  filter.integrateMeasurement(sample);
  * (UnscentedKalmanFilter.hpp:83-100, PoseUKF.cpp:112-178, OrientationUKF.cpp:53-72) run over the K queued samples of
- * every filter; same array shapes as ukfb_run_events.  Each of the two calls is guarded on its own. */
+ * every filter; same array shapes as ukfb_run_events. */
 int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const double* mu3, const double* cov, int cov_mode)
 {
     Batch* b = static_cast<Batch*>(h);
@@ -382,35 +382,36 @@ int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const
                 b->status[i] |= 32u;
                 continue;
             }
+            /* ONE guarded block per callback: a throw from predictionStep (negative / too large delta,
+             * UnscentedKalmanFilter.hpp:110-122) leaves the callback, so that sample's integrateMeasurement never runs */
             guarded(b, i, [&] {
                 if (pose)
                     b->pose[i]->predictionStepFromSampleTime(ts[e]);
                 else
                     b->ori[i]->predictionStepFromSampleTime(ts[e]);
-            });
-            if (kind < 0) continue;
-            const double* c33 = cov + (cov_mode ? e * 9 : int64_t(kind) * 9);
-            const double* z = mu3 + e * 3;
-            if (kind >= 10) {
-                guarded(b, i, [&] {
+                if (kind < 0) return;
+                const double* c33 = cov + (cov_mode ? e * 9 : int64_t(kind) * 9);
+                const double* z = mu3 + e * 3;
+                if (kind >= 10) {
                     if (pose)
                         b->pose[i]->setAcceleration(z, c33);
                     else if (kind == 11)
                         b->ori[i]->setRotationRate(z, c33);
                     else
                         b->ori[i]->setAcceleration(z, c33);
-                });
-                continue;
-            }
-            const int m = meas_dim(kind);
-            double zc[9];
-            for (int a = 0; a < m; ++a)
-                for (int c = 0; c < m; ++c) zc[a * m + c] = c33[a * 3 + c];
-            guarded(b, i, [&] {
-                if (pose)
-                    { b->pose[i]->integrateMeasurement(kind, z, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
-                else
-                    { b->ori[i]->integrateVelocity(z, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
+                    return;
+                }
+                const int m = meas_dim(kind);
+                double zc[9];
+                for (int a = 0; a < m; ++a)
+                    for (int c = 0; c < m; ++c) zc[a * m + c] = c33[a * 3 + c];
+                if (pose) {
+                    b->pose[i]->integrateMeasurement(kind, z, zc);
+                    if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u;
+                } else {
+                    b->ori[i]->integrateVelocity(z, zc);
+                    if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u;
+                }
             });
         }
     }

@@ -17,6 +17,11 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
 
 #include "ukf_device.cuh"
 #include "ukf_thread.cuh"
@@ -83,6 +88,17 @@ struct ukfb_handle {
     long long* summary = nullptr; /* 2 words */
     cudaEvent_t ev[16] = {};
     long long launches = 0;
+    /* launch configuration of the two fast-kernel instances this handle can run (index = template flag), filled on first
+     * use by the handle's single caller: nothing about a launch is shared between handles, so one host thread per handle
+     * (the workers of a sharded handle) needs no lock */
+    struct FastCfg {
+        bool attr_set = false;
+        long long prefetch_tiles = -1; /* -1 = not computed yet */
+    } fast_cfg[2];
+    /* sharded parent (ukfb_create_sharded): owns no device memory itself; shard i = filters first[i] .. first[i + 1] */
+    std::vector<ukfb_handle*> shards;
+    std::vector<long long> first;
+    struct ShardPool* pool = nullptr;
     /* pipelined host-pointer calls (ukfb_step_async / ukfb_get_state_async): copy-in and copy-out streams beside the
      * compute stream, two staging slots each, events ordering slot reuse */
     struct Pipe {
@@ -130,6 +146,100 @@ struct Bind { /* sets the device for the duration of a call */
     if (!(h)) return fail(UKFB_ERR_INVALID, "%s: null handle", __func__); \
     Bind bind_(h);                                                      \
     if (!bind_.ok) return fail(UKFB_ERR_CUDA, "%s: cudaSetDevice(%d) failed", __func__, (h)->device)
+
+/* ---- sharded handles: one worker thread per shard ---------------------------------------------------------------- */
+/* Filters share nothing (UnscentedKalmanFilter.hpp:150-154), so a sharded parent is just a list of one-device handles
+ * over contiguous index ranges.  Every host-pointer entry point starts with UKFB_FAN: on a parent it hands the SAME
+ * call, with the caller's arrays advanced to the shard's first filter, to each shard's worker and waits for all of them
+ * (copies to / from the devices and the final synchronisations of the shards then run concurrently). */
+struct ShardPool {
+    struct Worker {
+        std::thread th;
+        int rc = 0;
+        std::string err;
+    };
+    std::vector<Worker> w;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(int)> job;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool quit = false;
+
+    explicit ShardPool(int n) : w(size_t(n))
+    {
+        for (int i = 0; i < n; ++i) w[size_t(i)].th = std::thread([this, i] { loop(i); });
+    }
+    ~ShardPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            quit = true;
+        }
+        cv_job.notify_all();
+        for (auto& x : w)
+            if (x.th.joinable()) x.th.join();
+    }
+    void loop(int i)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::function<int(int)> fn;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv_job.wait(lock, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+                fn = job;
+            }
+            const int rc = fn(i);
+            std::string err = rc ? std::string(ukfb_last_error()) : std::string();
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                w[size_t(i)].rc = rc;
+                w[size_t(i)].err.swap(err);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    /* runs fn(i) on every worker; returns the first non-zero result (its text in *err) */
+    int run(const std::function<int(int)>& fn, std::string* err, int* who)
+    {
+        std::unique_lock<std::mutex> lock(mu);
+        job = fn;
+        pending = int(w.size());
+        ++generation;
+        cv_job.notify_all();
+        cv_done.wait(lock, [&] { return pending == 0; });
+        for (size_t i = 0; i < w.size(); ++i)
+            if (w[i].rc) {
+                *err = w[i].err;
+                *who = int(i);
+                return w[i].rc;
+            }
+        return 0;
+    }
+};
+
+static inline bool is_sharded(const ukfb_handle* h) { return h && !h->shards.empty(); }
+
+/* fn(shard handle, first filter of the shard, number of filters) on every shard, concurrently */
+template <class Fn>
+static int fan_out(ukfb_handle* h, Fn fn)
+{
+    std::string err;
+    int who = -1;
+    const int rc = h->pool->run([&](int i) { return fn(h->shards[size_t(i)], h->first[size_t(i)], h->first[size_t(i) + 1] - h->first[size_t(i)]); },
+                                &err, &who);
+    if (rc) return fail(rc, "shard %d (device %d): %s", who, h->shards[size_t(who)]->device, err.c_str());
+    return UKFB_OK;
+}
+
+#define UKFB_FAN(h, call)                                                                                   \
+    if (is_sharded(h)) return fan_out(h, [&](ukfb_handle* s_, long long f_, long long c_) -> int { (void)f_; (void)c_; return (call); })
+/* `_dev` entry points take pointers of one device */
+#define UKFB_NOT_SHARDED(h)                                                                                   \
+    if (is_sharded(h)) return fail(UKFB_ERR_INVALID, "%s: device pointers belong to one device -- use the per-device handles of ukfb_shard()", __func__)
 
 /* ---- small kernels ------------------------------------------------------------------------- */
 
@@ -377,16 +487,50 @@ static inline int grid_for(long long count, int block = 256)
 }
 
 /* ---- step launch ------------------------------------------------------------------------------ */
+/* process-wide tuning knobs from the environment, read once (thread-safe: function-local static initialisation) */
+struct EnvKnobs {
+    int fast_wpb;              /* UKFB_FAST_WPB: warps per block of the two fast kernels, 1 | 2 | 4 */
+    long smem_pad_kb;          /* UKFB_SMEM_PAD_KB: unused dynamic shared memory per block (occupancy experiments) */
+    int prefetch_bytes;        /* UKFB_PREFETCH_BYTES: request granularity of the next-wave prefetch (one L2 line) */
+    long long prefetch_tiles;  /* UKFB_PREFETCH_TILES: forced prefetch distance, -1 = from the occupancy API, 0 = off */
+    EnvKnobs()
+    {
+        const char* e = getenv("UKFB_FAST_WPB");
+        const int v = e ? atoi(e) : UKFB_DEFAULT_WPB;
+        fast_wpb = (v == 1 || v == 2 || v == 4) ? v : UKFB_DEFAULT_WPB;
+        e = getenv("UKFB_SMEM_PAD_KB");
+        smem_pad_kb = e ? atol(e) : 0;
+        e = getenv("UKFB_PREFETCH_BYTES");
+        prefetch_bytes = e && atoi(e) >= 8 ? atoi(e) : UKFB_DEFAULT_PREFETCH_BYTES;
+        e = getenv("UKFB_PREFETCH_TILES");
+        prefetch_tiles = e ? atoll(e) : -1;
+    }
+};
+static const EnvKnobs& knobs()
+{
+    static const EnvKnobs k;
+    return k;
+}
+
+/* cudaFuncSetAttribute is per (function, device): remembered per device under a lock (cold: literal / warp kernels) */
+static std::mutex g_attr_mu;
+template <class K>
+static cudaError_t ensure_smem_attr(K kernel, int device, size_t smem)
+{
+    static bool done[64] = {}; /* one array per kernel instantiation */
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (done[device & 63]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) done[device & 63] = true;
+    return e;
+}
+
 template <class F, int G, int WPB, int MINB>
 static cudaError_t launch_step_t(const ukfb_handle* h, const StepParams& p)
 {
-    static bool attr_set[64] = {};
     const size_t smem = sizeof(double) * WPB * Smem<F, G>::TOTAL;
-    if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(ukf_step_kernel<F, G, WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        attr_set[h->device & 63] = true;
-    }
+    cudaError_t e = ensure_smem_attr(ukf_step_kernel<F, G, WPB, MINB>, h->device, smem);
+    if (e != cudaSuccess) return e;
     const long long per_block = (long long)WPB * G;
     const long long grid = (p.B + per_block - 1) / per_block;
     ukf_step_kernel<F, G, WPB, MINB><<<unsigned(grid), WPB * 32, smem, h->stream>>>(p);
@@ -411,97 +555,58 @@ static cudaError_t launch_step_f(const ukfb_handle* h, const StepParams& p)
 template <class F>
 static cudaError_t launch_thread_f(const ukfb_handle* h, const StepParams& p)
 {
-    static bool attr_set[64] = {};
     const size_t smem = sizeof(double) * TSmem<F>::TOTAL;
-    if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(ukf_thread_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        attr_set[h->device & 63] = true;
-    }
+    cudaError_t e = ensure_smem_attr(ukf_thread_kernel<F>, h->device, smem);
+    if (e != cudaSuccess) return e;
     const long long grid = (p.B + TILE - 1) / TILE;
     ukf_thread_kernel<F><<<unsigned(grid), TILE, smem, h->stream>>>(p);
     return cudaGetLastError();
 }
 
-/* warps per block of the two fast kernels: UKFB_WPB = 1, 2 or 4 (read once) */
-static int fast_wpb()
-{
-    static int wpb = 0;
-    if (!wpb) {
-        const char* e = getenv("UKFB_WPB");
-        const int v = e ? atoi(e) : UKFB_DEFAULT_WPB;
-        wpb = (v == 1 || v == 2 || v == 4) ? v : UKFB_DEFAULT_WPB;
-    }
-    return wpb;
-}
-
 template <class K>
-static cudaError_t launch_fast(K kernel, int per_lane, const ukfb_handle* h, const StepParams& p, bool* attr_set)
+static cudaError_t launch_fast(K kernel, int per_lane, ukfb_handle* h, const StepParams& p, ukfb_handle::FastCfg& cfg)
 {
-    const int wpb = fast_wpb();
-    size_t smem = sizeof(double) * per_lane * TILE * wpb;
-    {   /* occupancy experiments: UKFB_SMEM_PAD_KB adds unused dynamic shared memory per block (fewer resident warps) */
-        static long pad = -1;
-        if (pad < 0) {
-            const char* e = getenv("UKFB_SMEM_PAD_KB");
-            pad = e ? atol(e) : 0;
-        }
-        smem += size_t(pad) * 1024;
-    }
-    if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const EnvKnobs& kn = knobs();
+    const int wpb = kn.fast_wpb;
+    const size_t smem = sizeof(double) * per_lane * TILE * wpb + size_t(kn.smem_pad_kb) * 1024;
+    if (!cfg.attr_set) {
+        cudaError_t e = ensure_smem_attr(kernel, h->device, smem);
         if (e != cudaSuccess) return e;
-        attr_set[h->device & 63] = true;
+        cfg.attr_set = true;
     }
     const long long tiles = (p.B + TILE - 1) / TILE;
     const long long grid = (tiles + wpb - 1) / wpb; /* warps past the last tile return at once */
     StepParams q = p;
-    {   /* prefetch distance = a quarter of the resident warps of this kernel on the device (measured on B200, pose C4:
-         * flat optimum from 32 to 444 tiles with 1184 resident warps, -2 % at 888, no gain from 1184 on;
-         * UKFB_PREFETCH_TILES overrides, 0 = off), request granularity UKFB_PREFETCH_BYTES (one L2 line).
-         * All instances share K's type: cached per (kernel, device). */
-        static struct { const void* k; int dev; long long r; } cache[32];
-        static int ncache = 0, gran = 0;
-        static long long forced = -2;
-        if (!gran) {
-            const char* e = getenv("UKFB_PREFETCH_BYTES");
-            gran = e && atoi(e) >= 8 ? atoi(e) : UKFB_DEFAULT_PREFETCH_BYTES;
-            const char* t = getenv("UKFB_PREFETCH_TILES");
-            forced = t ? atoll(t) : -1;
-        }
-        long long r = forced;
+    /* prefetch distance = a quarter of the resident warps of this kernel on the device (measured on B200, pose C4:
+     * flat optimum from 32 to 444 tiles with 1184 resident warps, -2 % at 888, no gain from 1184 on;
+     * UKFB_PREFETCH_TILES overrides, 0 = off), request granularity UKFB_PREFETCH_BYTES (one L2 line) */
+    if (cfg.prefetch_tiles < 0) {
+        long long r = kn.prefetch_tiles;
         if (r < 0) {
-            int i = 0;
-            while (i < ncache && !(cache[i].k == (const void*)kernel && cache[i].dev == h->device)) ++i;
-            if (i == ncache && ncache < 32) {
-                int per_sm = 0, sms = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE * wpb, smem) != cudaSuccess) per_sm = 0;
-                if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) sms = 0;
-                cache[ncache].k = (const void*)kernel, cache[ncache].dev = h->device, cache[ncache].r = (long long)per_sm * wpb * sms / 4;
-                if (cache[ncache].r < 32 && per_sm > 0) cache[ncache].r = 32;
-                ++ncache;
-            }
-            r = i < ncache ? cache[i].r : 0;
+            int per_sm = 0, sms = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE * wpb, smem) != cudaSuccess) per_sm = 0;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) sms = 0;
+            r = (long long)per_sm * wpb * sms / 4;
+            if (r < 32 && per_sm > 0) r = 32;
         }
-        q.prefetch_tiles = r > 0 ? r : 0;
-        q.prefetch_bytes = gran;
+        cfg.prefetch_tiles = r > 0 ? r : 0;
     }
+    q.prefetch_tiles = cfg.prefetch_tiles;
+    q.prefetch_bytes = kn.prefetch_bytes;
     kernel<<<unsigned(grid), TILE * wpb, smem, h->stream>>>(q);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_pose_fast(const ukfb_handle* h, const StepParams& p, bool may_have_orientation_meas)
+static cudaError_t launch_pose_fast(ukfb_handle* h, const StepParams& p, bool may_have_orientation_meas)
 {
-    static bool attr_set[2][64] = {};
-    if (may_have_orientation_meas) return launch_fast(ukf_pose_fast_kernel<true>, PF_PER_LANE, h, p, attr_set[1]);
-    return launch_fast(ukf_pose_fast_kernel<false>, PF_PER_LANE, h, p, attr_set[0]);
+    if (may_have_orientation_meas) return launch_fast(ukf_pose_fast_kernel<true>, PF_PER_LANE, h, p, h->fast_cfg[1]);
+    return launch_fast(ukf_pose_fast_kernel<false>, PF_PER_LANE, h, p, h->fast_cfg[0]);
 }
 
-static cudaError_t launch_ori_fast(const ukfb_handle* h, const StepParams& p)
+static cudaError_t launch_ori_fast(ukfb_handle* h, const StepParams& p)
 {
-    static bool attr_set[2][64] = {};
-    if (p.ori_params) return launch_fast(ukf_ori_fast_kernel<true>, OF_PER_LANE, h, p, attr_set[1]);
-    return launch_fast(ukf_ori_fast_kernel<false>, OF_PER_LANE, h, p, attr_set[0]);
+    if (p.ori_params) return launch_fast(ukf_ori_fast_kernel<true>, OF_PER_LANE, h, p, h->fast_cfg[1]);
+    return launch_fast(ukf_ori_fast_kernel<false>, OF_PER_LANE, h, p, h->fast_cfg[0]);
 }
 
 static int launch_step(ukfb_handle* h, const StepParams& p)
@@ -593,7 +698,7 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
         h->tiled = strcmp(g, "warp") != 0;
         if (strcmp(g, "thread") == 0) h->fast = 0;
     }
-    if (const char* g = getenv("UKFB_WPB")) h->WPB = atoi(g);
+    if (const char* g = getenv("UKFB_WARP_WPB")) h->WPB = atoi(g); /* warp-per-group kernel only; the fast kernels: UKFB_FAST_WPB */
     if (const char* g = getenv("UKFB_MINB")) h->MINB = atoi(g);
     Bind bind_(h);
     if (!bind_.ok) {
@@ -649,9 +754,85 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
     return UKFB_OK;
 }
 
+extern "C" int ukfb_create_sharded(int filter_kind, int64_t batch, const int* devices, int n_devices, ukfb_handle** out)
+{
+    if (!out) return fail(UKFB_ERR_INVALID, "ukfb_create_sharded: out is null");
+    *out = nullptr;
+    if (filter_kind != UKFB_POSE && filter_kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_create_sharded: bad filter kind %d", filter_kind);
+    if (n_devices < 1 || n_devices > 64) return fail(UKFB_ERR_INVALID, "ukfb_create_sharded: n_devices must be 1..64");
+    if (batch < n_devices) return fail(UKFB_ERR_INVALID, "ukfb_create_sharded: batch must be >= n_devices (every shard holds at least one filter)");
+    ukfb_handle* h = new (std::nothrow) ukfb_handle;
+    if (!h) return fail(UKFB_ERR_NOMEM, "ukfb_create_sharded: out of host memory");
+    h->kind = filter_kind;
+    h->B = batch;
+    if (filter_kind == UKFB_POSE)
+        h->n = PoseF::N, h->MU = PoseF::MU, h->LP = PoseF::LP, h->REC = PoseF::REC;
+    else
+        h->n = OriF::N, h->MU = OriF::MU, h->LP = OriF::LP, h->REC = OriF::REC;
+    /* contiguous ranges, the first batch % n shards one filter longer (shard_range of the Python side) */
+    const long long base = batch / n_devices, extra = batch % n_devices;
+    h->first.assign(size_t(n_devices) + 1, 0);
+    for (int i = 0; i < n_devices; ++i) h->first[size_t(i) + 1] = h->first[size_t(i)] + base + (i < extra ? 1 : 0);
+    for (int i = 0; i < n_devices; ++i) {
+        ukfb_handle* sh = nullptr;
+        const int rc = ukfb_create(filter_kind, h->first[size_t(i) + 1] - h->first[size_t(i)], devices ? devices[i] : i, &sh);
+        if (rc) {
+            for (ukfb_handle* made : h->shards) ukfb_destroy(made);
+            delete h;
+            return rc; /* the text of ukfb_create stands */
+        }
+        h->shards.push_back(sh);
+    }
+    h->device = h->shards[0]->device;
+    h->tiled = h->shards[0]->tiled, h->fast = h->shards[0]->fast;
+    h->pool = new (std::nothrow) ShardPool(n_devices);
+    if (!h->pool) {
+        for (ukfb_handle* made : h->shards) ukfb_destroy(made);
+        delete h;
+        return fail(UKFB_ERR_NOMEM, "ukfb_create_sharded: out of host memory");
+    }
+    *out = h;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_shard_count(const ukfb_handle* h) { return !h ? 0 : (is_sharded(h) ? int(h->shards.size()) : 1); }
+
+extern "C" int ukfb_shard(ukfb_handle* h, int i, ukfb_handle** shard, int64_t* first, int64_t* count)
+{
+    if (!h) return fail(UKFB_ERR_INVALID, "ukfb_shard: null handle");
+    const int n = ukfb_shard_count(h);
+    if (i < 0 || i >= n) return fail(UKFB_ERR_INVALID, "ukfb_shard: shard %d out of range (%d shards)", i, n);
+    if (shard) *shard = is_sharded(h) ? h->shards[size_t(i)] : h;
+    if (first) *first = is_sharded(h) ? h->first[size_t(i)] : 0;
+    if (count) *count = is_sharded(h) ? h->first[size_t(i) + 1] - h->first[size_t(i)] : h->B;
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_host_alloc(void** ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return fail(UKFB_ERR_INVALID, "ukfb_host_alloc: bad argument");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, size_t(bytes), cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? UKFB_ERR_NOMEM : UKFB_ERR_CUDA, "ukfb_host_alloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_host_free(void* ptr)
+{
+    if (!ptr) return UKFB_OK;
+    CU(cudaFreeHost(ptr));
+    return UKFB_OK;
+}
+
 extern "C" int ukfb_destroy(ukfb_handle* h)
 {
     if (!h) return UKFB_OK;
+    if (is_sharded(h)) {
+        delete h->pool; /* joins the workers (none is mid-call: the handle is single-caller) */
+        for (ukfb_handle* s : h->shards) ukfb_destroy(s);
+        delete h;
+        return UKFB_OK;
+    }
     Bind bind_(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist);
@@ -676,7 +857,7 @@ extern "C" int64_t ukfb_batch(const ukfb_handle* h) { return h ? h->B : 0; }
 extern "C" int ukfb_dof(const ukfb_handle* h) { return h ? h->n : 0; }
 extern "C" int ukfb_mu_size(const ukfb_handle* h) { return h ? h->MU : 0; }
 extern "C" int ukfb_device(const ukfb_handle* h) { return h ? h->device : -1; }
-extern "C" int ukfb_is_initialized(const ukfb_handle* h) { return h && h->initialized ? 1 : 0; }
+extern "C" int ukfb_is_initialized(const ukfb_handle* h) { return h && h->initialized ? 1 : 0; } /* a sharded parent mirrors its shards */
 
 static int initialize_dev(ukfb_handle* h, const double* d_mu, const double* d_sigma)
 {
@@ -696,6 +877,11 @@ extern "C" int ukfb_initialize(ukfb_handle* h, const double* mu, const double* s
 {
     CHECK_H(h);
     if (!mu || !sigma) return fail(UKFB_ERR_INVALID, "ukfb_initialize: null argument");
+    if (is_sharded(h)) {
+        const int rc = fan_out(h, [&](ukfb_handle* s_, long long f_, long long) { return ukfb_initialize(s_, mu + f_ * s_->MU, sigma + f_ * s_->n * s_->n); });
+        if (rc == UKFB_OK) h->initialized = true;
+        return rc;
+    }
     const size_t bm = align256(sizeof(double) * h->B * h->MU), bs = sizeof(double) * h->B * h->n * h->n;
     int rc = stage_reserve(h, bm + bs);
     if (rc) return rc;
@@ -712,6 +898,7 @@ extern "C" int ukfb_initialize(ukfb_handle* h, const double* mu, const double* s
 extern "C" int ukfb_initialize_from_body_states_dev(ukfb_handle* h, const double* d_rbs)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     if (h->kind != UKFB_POSE) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: BodyStateMeasurement belongs to PoseUKF");
     if (!d_rbs) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: null argument");
     pack_rbs_kernel<<<grid_for(h->B * h->REC), 256, 0, h->stream>>>(h->state, d_rbs, h->B, h->tiled);
@@ -726,6 +913,12 @@ extern "C" int ukfb_initialize_from_body_states(ukfb_handle* h, const double* rb
 {
     CHECK_H(h);
     if (!rbs) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: null argument");
+    if (is_sharded(h)) {
+        if (h->kind != UKFB_POSE) return fail(UKFB_ERR_INVALID, "ukfb_initialize_from_body_states: BodyStateMeasurement belongs to PoseUKF");
+        const int rc = fan_out(h, [&](ukfb_handle* s_, long long f_, long long) { return ukfb_initialize_from_body_states(s_, rbs + f_ * UKFB_RBS_DOUBLES); });
+        if (rc == UKFB_OK) h->initialized = true;
+        return rc;
+    }
     const size_t bytes = sizeof(double) * h->B * UKFB_RBS_DOUBLES;
     int rc = stage_reserve(h, bytes);
     if (rc) return rc;
@@ -739,6 +932,7 @@ extern "C" int ukfb_initialize_from_body_states(ukfb_handle* h, const double* rb
 extern "C" int ukfb_get_body_states_dev(ukfb_handle* h, double* d_rbs)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     if (h->kind != UKFB_POSE) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: BodyStateMeasurement belongs to PoseUKF");
     NEED_INIT(h);
     if (!d_rbs) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: null argument");
@@ -752,6 +946,7 @@ extern "C" int ukfb_get_body_states(ukfb_handle* h, double* rbs)
     CHECK_H(h);
     NEED_INIT(h);
     if (!rbs) return fail(UKFB_ERR_INVALID, "ukfb_get_body_states: null argument");
+    UKFB_FAN(h, ukfb_get_body_states(s_, rbs + f_ * UKFB_RBS_DOUBLES));
     const size_t bytes = sizeof(double) * h->B * UKFB_RBS_DOUBLES;
     int rc = stage_reserve(h, bytes);
     if (rc) return rc;
@@ -765,6 +960,7 @@ extern "C" int ukfb_get_body_states(ukfb_handle* h, double* rbs)
 extern "C" int ukfb_get_state_dev(ukfb_handle* h, double* d_mu, double* d_sigma)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (d_mu) unpack_mu_kernel<<<grid_for(h->B * h->MU), 256, 0, h->stream>>>(h->state, d_mu, h->B, h->MU, h->REC, h->tiled);
     if (d_sigma) unpack_sigma_kernel<<<grid_for(h->B * h->n * h->n), 256, 0, h->stream>>>(h->state, d_sigma, h->B, h->n, h->MU, h->REC, h->tiled);
@@ -776,6 +972,8 @@ extern "C" int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma)
 {
     CHECK_H(h);
     NEED_INIT(h);
+    /* sharded: every shard lands in its range of the caller's single buffer -- the final gather of the estimates */
+    UKFB_FAN(h, ukfb_get_state(s_, mu ? mu + f_ * s_->MU : nullptr, sigma ? sigma + f_ * s_->n * s_->n : nullptr));
     const size_t bm = align256(sizeof(double) * h->B * h->MU), bs = sizeof(double) * h->B * h->n * h->n;
     int rc = stage_reserve(h, bm + (sigma ? bs : 0));
     if (rc) return rc;
@@ -789,10 +987,59 @@ extern "C" int ukfb_get_state(ukfb_handle* h, double* mu, double* sigma)
     return UKFB_OK;
 }
 
+/* mu entries [first, first + count) of every filter, dense B x count */
+__global__ void unpack_mu_range_kernel(const double* __restrict__ state, double* __restrict__ out, long long B, int first, int count, int REC, int tiled)
+{
+    const long long total = B * count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / count;
+        const int k = int(i - b * count);
+        out[i] = state[rec_index(tiled, b, first + k, REC)];
+    }
+}
+
+static int mu_range_ok(const ukfb_handle* h, int mu_first, int mu_count, const void* out, const char* who)
+{
+    if (!out) return fail(UKFB_ERR_INVALID, "%s: null argument", who);
+    if (mu_first < 0 || mu_count < 1 || mu_first + mu_count > h->MU)
+        return fail(UKFB_ERR_INVALID, "%s: entries [%d, %d) are outside the %d-entry state", who, mu_first, mu_first + mu_count, h->MU);
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_mu_range_dev(ukfb_handle* h, int mu_first, int mu_count, double* d_out)
+{
+    CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
+    NEED_INIT(h);
+    const int rc = mu_range_ok(h, mu_first, mu_count, d_out, "ukfb_get_mu_range_dev");
+    if (rc) return rc;
+    unpack_mu_range_kernel<<<grid_for(h->B * mu_count), 256, 0, h->stream>>>(h->state, d_out, h->B, mu_first, mu_count, h->REC, h->tiled);
+    CU(cudaGetLastError());
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_get_mu_range(ukfb_handle* h, int mu_first, int mu_count, double* out)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    int rc = mu_range_ok(h, mu_first, mu_count, out, "ukfb_get_mu_range");
+    if (rc) return rc;
+    UKFB_FAN(h, ukfb_get_mu_range(s_, mu_first, mu_count, out + f_ * mu_count));
+    const size_t bytes = sizeof(double) * h->B * mu_count;
+    rc = stage_reserve(h, bytes);
+    if (rc) return rc;
+    rc = ukfb_get_mu_range_dev(h, mu_first, mu_count, reinterpret_cast<double*>(h->stage));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
 extern "C" int ukfb_set_process_noise(ukfb_handle* h, const double* Q, int per_filter)
 {
     CHECK_H(h);
     if (!Q) return fail(UKFB_ERR_INVALID, "ukfb_set_process_noise: null argument");
+    UKFB_FAN(h, ukfb_set_process_noise(s_, Q + (per_filter ? f_ * s_->n * s_->n : 0), per_filter));
     const long long count = per_filter ? h->B : 1;
     const size_t bytes = sizeof(double) * count * h->n * h->n;
     int rc = stage_reserve(h, bytes);
@@ -827,6 +1074,7 @@ extern "C" int ukfb_get_process_noise(ukfb_handle* h, double* Q, int per_filter)
 {
     CHECK_H(h);
     if (!Q) return fail(UKFB_ERR_INVALID, "ukfb_get_process_noise: null argument");
+    UKFB_FAN(h, (per_filter || f_ == 0) ? ukfb_get_process_noise(s_, Q + (per_filter ? f_ * s_->n * s_->n : 0), per_filter) : UKFB_OK);
     const long long count = per_filter ? h->B : 1;
     const size_t bytes = sizeof(double) * count * h->n * h->n;
     int rc = stage_reserve(h, bytes);
@@ -842,6 +1090,7 @@ extern "C" int ukfb_get_process_noise(ukfb_handle* h, double* Q, int per_filter)
 extern "C" int ukfb_set_time_bounds(ukfb_handle* h, double min_dt, double max_dt)
 {
     if (!h) return fail(UKFB_ERR_INVALID, "ukfb_set_time_bounds: null handle");
+    for (ukfb_handle* s : h->shards) s->min_dt = min_dt, s->max_dt = max_dt; /* host-side fields; the parent keeps a copy */
     h->min_dt = min_dt;
     h->max_dt = max_dt;
     return UKFB_OK;
@@ -859,6 +1108,7 @@ extern "C" int ukfb_set_last_time(ukfb_handle* h, const int64_t* ts_us, int per_
 {
     CHECK_H(h);
     if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_set_last_time: null argument");
+    UKFB_FAN(h, ukfb_set_last_time(s_, ts_us + (per_filter ? f_ : 0), per_filter));
     if (per_filter) {
         CU(cudaMemcpyAsync(h->t_last, ts_us, sizeof(long long) * h->B, cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -873,6 +1123,7 @@ extern "C" int ukfb_get_last_time(ukfb_handle* h, int64_t* ts_us)
 {
     CHECK_H(h);
     if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_get_last_time: null argument");
+    UKFB_FAN(h, ukfb_get_last_time(s_, ts_us + f_));
     CU(cudaMemcpyAsync(ts_us, h->t_last, sizeof(long long) * h->B, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
@@ -882,6 +1133,7 @@ extern "C" int ukfb_set_mahalanobis_gate(ukfb_handle* h, double max_d2)
 {
     CHECK_H(h);
     if (!(max_d2 > 0.0)) return fail(UKFB_ERR_INVALID, "ukfb_set_mahalanobis_gate: the threshold must be positive (+inf accepts everything)");
+    for (ukfb_handle* s : h->shards) s->gate_d2 = max_d2;
     h->gate_d2 = max_d2;
     return UKFB_OK;
 }
@@ -897,6 +1149,10 @@ extern "C" int ukfb_set_orientation_params(ukfb_handle* h, double gyro_bias_tau,
 {
     if (!h) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params: null handle");
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params: not an ORIENTATION handle");
+    for (ukfb_handle* s : h->shards) {
+        const int rc = ukfb_set_orientation_params(s, gyro_bias_tau, acc_bias_tau, latitude);
+        if (rc) return rc;
+    }
     h->tau_g = gyro_bias_tau;
     h->tau_a = acc_bias_tau;
     h->latitude = latitude;
@@ -918,6 +1174,7 @@ extern "C" int ukfb_set_orientation_params_per_filter(ukfb_handle* h, const doub
     CHECK_H(h);
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: not an ORIENTATION handle");
     if (!gyro_bias_tau || !acc_bias_tau || !latitude) return fail(UKFB_ERR_INVALID, "ukfb_set_orientation_params_per_filter: null argument");
+    UKFB_FAN(h, ukfb_set_orientation_params_per_filter(s_, gyro_bias_tau + f_, acc_bias_tau + f_, latitude + f_));
     std::vector<double> packed(size_t(h->B) * 5);
     for (long long b = 0; b < h->B; ++b) {
         packed[b * 5] = -1.0 / gyro_bias_tau[b];
@@ -939,6 +1196,7 @@ extern "C" int ukfb_set_orientation_params_per_filter(ukfb_handle* h, const doub
 extern "C" int ukfb_predict_dt_dev(ukfb_handle* h, const double* d_dt, int per_filter)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_predict_dt: null argument");
     StepParams p = base_params(h);
@@ -954,6 +1212,7 @@ extern "C" int ukfb_predict_dt(ukfb_handle* h, const double* dt, int per_filter)
     CHECK_H(h);
     NEED_INIT(h);
     if (!dt) return fail(UKFB_ERR_INVALID, "ukfb_predict_dt: null argument");
+    UKFB_FAN(h, ukfb_predict_dt(s_, dt + (per_filter ? f_ : 0), per_filter));
     const size_t bytes = sizeof(double) * (per_filter ? h->B : 1);
     int rc = stage_reserve(h, bytes);
     if (rc) return rc;
@@ -967,6 +1226,7 @@ extern "C" int ukfb_predict_dt(ukfb_handle* h, const double* dt, int per_filter)
 extern "C" int ukfb_predict_time_dev(ukfb_handle* h, const int64_t* d_ts_us, int per_filter)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (!d_ts_us) return fail(UKFB_ERR_INVALID, "ukfb_predict_time: null argument");
     StepParams p = base_params(h);
@@ -982,6 +1242,7 @@ extern "C" int ukfb_predict_time(ukfb_handle* h, const int64_t* ts_us, int per_f
     CHECK_H(h);
     NEED_INIT(h);
     if (!ts_us) return fail(UKFB_ERR_INVALID, "ukfb_predict_time: null argument");
+    UKFB_FAN(h, ukfb_predict_time(s_, ts_us + (per_filter ? f_ : 0), per_filter));
     const size_t bytes = sizeof(int64_t) * (per_filter ? h->B : 1);
     int rc = stage_reserve(h, bytes);
     if (rc) return rc;
@@ -1016,6 +1277,7 @@ extern "C" int ukfb_update_dev(ukfb_handle* h, int meas_kind, const double* d_mu
                                const uint8_t* d_mask)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_update: measurement kind %d does not belong to this filter kind", meas_kind);
     if (!d_mu || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
@@ -1064,6 +1326,7 @@ extern "C" int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, cons
     if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_update: measurement kind %d does not belong to this filter kind", meas_kind);
     if (!mu || !cov) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
     const int m = meas_dim(meas_kind);
+    UKFB_FAN(h, ukfb_update(s_, meas_kind, mu + f_ * m, cov + (cov_per_filter ? f_ * m * m : 0), cov_per_filter, mask ? mask + f_ : nullptr));
     const double *d_mu, *d_cov;
     const uint8_t* d_mask;
     int rc = stage_meas(h, 0, m, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
@@ -1077,6 +1340,7 @@ extern "C" int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, cons
 extern "C" int ukfb_update_mixed_dev(ukfb_handle* h, const int8_t* d_kinds, const double* d_mu3, const double* d_cov33)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (!d_kinds || !d_mu3 || !d_cov33) return fail(UKFB_ERR_INVALID, "ukfb_update_mixed: null argument");
     StepParams p = base_params(h);
@@ -1100,6 +1364,7 @@ extern "C" int ukfb_update_mixed(ukfb_handle* h, const int8_t* kinds, const doub
     for (long long b = 0; b < h->B; ++b)
         if (kinds[b] != UKFB_MEAS_NONE && !kind_ok(h, kinds[b]))
             return fail(UKFB_ERR_INVALID, "ukfb_update_mixed: kinds[%lld] = %d does not belong to this filter kind", b, int(kinds[b]));
+    UKFB_FAN(h, ukfb_update_mixed(s_, kinds + f_, mu3 + f_ * 3, cov33 + f_ * 9));
     const size_t bk = align256(size_t(h->B)), bm = align256(sizeof(double) * h->B * 3), bc = sizeof(double) * h->B * 9;
     int rc = stage_reserve(h, bk + bm + bc);
     if (rc) return rc;
@@ -1124,6 +1389,7 @@ static int store_vec3_dev(ukfb_handle* h, double* dst_mu, double* dst_cov, const
 extern "C" int ukfb_set_acceleration_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter, const uint8_t* d_mask)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     if (!d_mu) return fail(UKFB_ERR_INVALID, "ukfb_set_acceleration: null argument");
     /* PoseUKF stores unchecked (PoseUKF.cpp:175-178); OrientationUKF checks (OrientationUKF.cpp:61) */
     return store_vec3_dev(h, h->acc_mu, h->acc_cov, d_mu, d_cov, cov_per_filter, d_mask, h->kind == UKFB_ORIENTATION);
@@ -1133,6 +1399,7 @@ extern "C" int ukfb_set_acceleration(ukfb_handle* h, const double* mu, const dou
 {
     CHECK_H(h);
     if (!mu) return fail(UKFB_ERR_INVALID, "ukfb_set_acceleration: null argument");
+    UKFB_FAN(h, ukfb_set_acceleration(s_, mu + f_ * 3, cov ? cov + (cov_per_filter ? f_ * 9 : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
     const double *d_mu, *d_cov;
     const uint8_t* d_mask;
     int rc = stage_meas(h, 0, 3, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
@@ -1146,6 +1413,7 @@ extern "C" int ukfb_set_acceleration(ukfb_handle* h, const double* mu, const dou
 extern "C" int ukfb_set_rotation_rate_dev(ukfb_handle* h, const double* d_mu, const double* d_cov, int cov_per_filter, const uint8_t* d_mask)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: not an ORIENTATION handle");
     if (!d_mu) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: null argument");
     /* the rotation-rate covariance is never read by the reference (OrientationUKF.cpp:88 passes .mu only) but
@@ -1158,6 +1426,7 @@ extern "C" int ukfb_set_rotation_rate(ukfb_handle* h, const double* mu, const do
     CHECK_H(h);
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: not an ORIENTATION handle");
     if (!mu) return fail(UKFB_ERR_INVALID, "ukfb_set_rotation_rate: null argument");
+    UKFB_FAN(h, ukfb_set_rotation_rate(s_, mu + f_ * 3, cov ? cov + (cov_per_filter ? f_ * 9 : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
     const double *d_mu, *d_cov;
     const uint8_t* d_mask;
     int rc = stage_meas(h, 0, 3, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
@@ -1174,6 +1443,7 @@ extern "C" int ukfb_get_rotation_rate(ukfb_handle* h, double* out)
     NEED_INIT(h);
     if (h->kind != UKFB_ORIENTATION) return fail(UKFB_ERR_INVALID, "ukfb_get_rotation_rate: not an ORIENTATION handle");
     if (!out) return fail(UKFB_ERR_INVALID, "ukfb_get_rotation_rate: null argument");
+    UKFB_FAN(h, ukfb_get_rotation_rate(s_, out + f_ * 3));
     int rc = stage_reserve(h, sizeof(double) * h->B * 3);
     if (rc) return rc;
     rotation_rate_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->state, h->gyro_mu, h->earth[0], h->earth[1], h->earth[2], h->ori_params,
@@ -1189,6 +1459,7 @@ extern "C" int ukfb_step_dev(ukfb_handle* h, const double* d_dt, int dt_per_filt
                              int cov_per_filter, const uint8_t* d_mask)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_step: null dt");
     StepParams p = base_params(h);
@@ -1214,6 +1485,8 @@ extern "C" int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, in
     if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step: measurement kind %d does not belong to this filter kind", meas_kind);
     if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step: null measurement");
     const int m = upd ? meas_dim(meas_kind) : 0;
+    UKFB_FAN(h, ukfb_step(s_, dt + (dt_per_filter ? f_ : 0), dt_per_filter, meas_kind, mu ? mu + f_ * m : nullptr,
+                          cov ? cov + (cov_per_filter ? f_ * m * m : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
     int rc = stage_reserve(h, bd + (upd ? meas_bytes(h, m, true, cov_per_filter, mask != nullptr) : 0));
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->stage, dt, sizeof(double) * (dt_per_filter ? h->B : 1), cudaMemcpyHostToDevice, h->stream));
@@ -1273,10 +1546,12 @@ extern "C" int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filt
     const bool upd = meas_kind != UKFB_MEAS_NONE;
     if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: measurement kind %d does not belong to this filter kind", meas_kind);
     if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null measurement");
+    const int m = upd ? meas_dim(meas_kind) : 0;
+    UKFB_FAN(h, ukfb_step_async(s_, dt + (dt_per_filter ? f_ : 0), dt_per_filter, meas_kind, mu ? mu + f_ * m : nullptr,
+                                cov ? cov + (cov_per_filter ? f_ * m * m : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
     int rc = pipe_make(h);
     if (rc) return rc;
     const int slot = int(h->pipe.n_in & 1);
-    const int m = upd ? meas_dim(meas_kind) : 0;
     const size_t bd = align256(sizeof(double) * (dt_per_filter ? h->B : 1));
     const size_t bm = upd ? align256(sizeof(double) * h->B * m) : 0;
     const size_t bc = upd ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0;
@@ -1315,6 +1590,7 @@ extern "C" int ukfb_get_state_async(ukfb_handle* h, double* mu, double* sigma)
 {
     CHECK_H(h);
     NEED_INIT(h);
+    UKFB_FAN(h, ukfb_get_state_async(s_, mu ? mu + f_ * s_->MU : nullptr, sigma ? sigma + f_ * s_->n * s_->n : nullptr));
     int rc = pipe_make(h);
     if (rc) return rc;
     const int slot = int(h->pipe.n_out & 1);
@@ -1336,10 +1612,37 @@ extern "C" int ukfb_get_state_async(ukfb_handle* h, double* mu, double* sigma)
     return UKFB_OK;
 }
 
+extern "C" int ukfb_get_mu_range_async(ukfb_handle* h, int mu_first, int mu_count, double* out)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    int rc = mu_range_ok(h, mu_first, mu_count, out, "ukfb_get_mu_range_async");
+    if (rc) return rc;
+    UKFB_FAN(h, ukfb_get_mu_range_async(s_, mu_first, mu_count, out + f_ * mu_count));
+    rc = pipe_make(h);
+    if (rc) return rc;
+    const int slot = int(h->pipe.n_out & 1);
+    const size_t bytes = sizeof(double) * h->B * mu_count;
+    rc = pipe_reserve(h, &h->pipe.out[slot], &h->pipe.out_bytes[slot], bytes);
+    if (rc) return rc;
+    double* d_out = reinterpret_cast<double*>(h->pipe.out[slot]);
+    if (h->pipe.n_out >= 2) CU(cudaStreamWaitEvent(h->stream, h->pipe.out_drained[slot], 0)); /* the copy that read this slot is done */
+    rc = ukfb_get_mu_range_dev(h, mu_first, mu_count, d_out);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->pipe.out_ready[slot], h->stream));
+    cudaStream_t so = h->pipe.s_out;
+    CU(cudaStreamWaitEvent(so, h->pipe.out_ready[slot], 0));
+    CU(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, so));
+    CU(cudaEventRecord(h->pipe.out_drained[slot], so));
+    h->pipe.n_out++;
+    return UKFB_OK;
+}
+
 extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_per_filter, const int8_t* kinds_host, const double* d_mu3,
                             const double* d_cov33, int cov_per_filter, const double* d_imu)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run: K must be >= 1");
     if (!d_dt) return fail(UKFB_ERR_INVALID, "ukfb_run: null dt");
@@ -1385,6 +1688,7 @@ extern "C" int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us
                                    const double* d_cov, int cov_mode)
 {
     CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
     NEED_INIT(h);
     if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: K must be >= 1");
     if (!d_ts_us || !d_kinds || !d_mu3 || !d_cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events: null argument");
@@ -1412,29 +1716,82 @@ extern "C" int ukfb_run_events_dev(ukfb_handle* h, int K, const int64_t* d_ts_us
     return launch_step(h, p);
 }
 
-extern "C" int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3, const double* cov,
-                               int cov_mode)
+/* K rows of `cols` elements each, host -> device; the host rows are `src_cols` elements apart (a shard's slice of the
+ * caller's slot-major K x B arrays), the device rows dense */
+static cudaError_t copy_rows_h2d(void* dst, const void* src, size_t elem, long long cols, long long src_cols, int rows, cudaStream_t st)
+{
+    if (cols == src_cols) return cudaMemcpyAsync(dst, src, elem * size_t(cols) * size_t(rows), cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, elem * size_t(cols), src, elem * size_t(src_cols), elem * size_t(cols), size_t(rows), cudaMemcpyHostToDevice, st);
+}
+
+/* ukfb_run_events / ukfb_run_events_async on one device.  The arrays point at this handle's first filter in slot 0 and
+ * their slots are src_B filters apart (src_B = h->B for a one-device handle, the parent's batch for a shard). */
+static int run_events_host(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3, const double* cov,
+                           int cov_mode, long long src_B, bool async)
 {
     CHECK_H(h);
     NEED_INIT(h);
-    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: K must be >= 1");
-    if (!ts_us || !kinds || !mu3 || !cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events: null argument");
-    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events: cov_mode must be 0 (per-kind table) or 1 (per event)");
     const size_t n = size_t(K) * size_t(h->B);
     const size_t bt = align256(sizeof(int64_t) * n), bk = align256(n), bm = align256(sizeof(double) * n * 3);
     const size_t bc = sizeof(double) * (cov_mode ? n * 9 : size_t(UKFB_EVENT_KIND_COUNT) * 9);
-    int rc = stage_reserve(h, bt + bk + bm + bc);
+    char* base;
+    cudaStream_t si;
+    int slot = 0;
+    int rc;
+    if (async) {
+        rc = pipe_make(h);
+        if (rc) return rc;
+        slot = int(h->pipe.n_in & 1);
+        rc = pipe_reserve(h, &h->pipe.in[slot], &h->pipe.in_bytes[slot], bt + bk + bm + bc);
+        if (rc) return rc;
+        base = h->pipe.in[slot];
+        si = h->pipe.s_in;
+        if (h->pipe.n_in >= 2) CU(cudaStreamWaitEvent(si, h->pipe.in_consumed[slot], 0)); /* the launch that read this slot is done */
+    } else {
+        rc = stage_reserve(h, bt + bk + bm + bc);
+        if (rc) return rc;
+        base = h->stage;
+        si = h->stream;
+    }
+    CU(copy_rows_h2d(base, ts_us, sizeof(int64_t), h->B, src_B, K, si));
+    CU(copy_rows_h2d(base + bt, kinds, 1, h->B, src_B, K, si));
+    CU(copy_rows_h2d(base + bt + bk, mu3, sizeof(double) * 3, h->B, src_B, K, si));
+    if (cov_mode)
+        CU(copy_rows_h2d(base + bt + bk + bm, cov, sizeof(double) * 9, h->B, src_B, K, si));
+    else
+        CU(cudaMemcpyAsync(base + bt + bk + bm, cov, bc, cudaMemcpyHostToDevice, si));
+    if (async) {
+        CU(cudaEventRecord(h->pipe.in_ready[slot], si));
+        CU(cudaStreamWaitEvent(h->stream, h->pipe.in_ready[slot], 0));
+    }
+    rc = ukfb_run_events_dev(h, K, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const int8_t*>(base + bt),
+                             reinterpret_cast<const double*>(base + bt + bk), reinterpret_cast<const double*>(base + bt + bk + bm), cov_mode);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h->stage, ts_us, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->stage + bt, kinds, n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->stage + bt + bk, mu3, sizeof(double) * n * 3, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->stage + bt + bk + bm, cov, bc, cudaMemcpyHostToDevice, h->stream));
-    rc = ukfb_run_events_dev(h, K, reinterpret_cast<const int64_t*>(h->stage), reinterpret_cast<const int8_t*>(h->stage + bt),
-                             reinterpret_cast<const double*>(h->stage + bt + bk), reinterpret_cast<const double*>(h->stage + bt + bk + bm),
-                             cov_mode);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));
+    if (async) {
+        CU(cudaEventRecord(h->pipe.in_consumed[slot], h->stream));
+        h->pipe.n_in++;
+    } else
+        CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
+}
+
+static int run_events_any(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3, const double* cov,
+                          int cov_mode, bool async, const char* who)
+{
+    CHECK_H(h);
+    NEED_INIT(h);
+    if (K < 1) return fail(UKFB_ERR_INVALID, "%s: K must be >= 1", who);
+    if (!ts_us || !kinds || !mu3 || !cov) return fail(UKFB_ERR_INVALID, "%s: null argument", who);
+    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "%s: cov_mode must be 0 (per-kind table) or 1 (per event)", who);
+    const long long B = h->B;
+    UKFB_FAN(h, run_events_host(s_, K, ts_us + f_, kinds + f_, mu3 + f_ * 3, cov_mode ? cov + f_ * 9 : cov, cov_mode, B, async));
+    return run_events_host(h, K, ts_us, kinds, mu3, cov, cov_mode, B, async);
+}
+
+extern "C" int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3, const double* cov,
+                               int cov_mode)
+{
+    return run_events_any(h, K, ts_us, kinds, mu3, cov, cov_mode, false, "ukfb_run_events");
 }
 
 /* ukfb_run_events without the final synchronisation: the queues travel on the copy-in stream into one of the two
@@ -1442,34 +1799,7 @@ extern "C" int ukfb_run_events(ukfb_handle* h, int K, const int64_t* ts_us, cons
 extern "C" int ukfb_run_events_async(ukfb_handle* h, int K, const int64_t* ts_us, const int8_t* kinds, const double* mu3,
                                      const double* cov, int cov_mode)
 {
-    CHECK_H(h);
-    NEED_INIT(h);
-    if (K < 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: K must be >= 1");
-    if (!ts_us || !kinds || !mu3 || !cov) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: null argument");
-    if (cov_mode != 0 && cov_mode != 1) return fail(UKFB_ERR_INVALID, "ukfb_run_events_async: cov_mode must be 0 (per-kind table) or 1 (per event)");
-    int rc = pipe_make(h);
-    if (rc) return rc;
-    const int slot = int(h->pipe.n_in & 1);
-    const size_t n = size_t(K) * size_t(h->B);
-    const size_t bt = align256(sizeof(int64_t) * n), bk = align256(n), bm = align256(sizeof(double) * n * 3);
-    const size_t bc = sizeof(double) * (cov_mode ? n * 9 : size_t(UKFB_EVENT_KIND_COUNT) * 9);
-    rc = pipe_reserve(h, &h->pipe.in[slot], &h->pipe.in_bytes[slot], bt + bk + bm + bc);
-    if (rc) return rc;
-    char* base = h->pipe.in[slot];
-    cudaStream_t si = h->pipe.s_in;
-    if (h->pipe.n_in >= 2) CU(cudaStreamWaitEvent(si, h->pipe.in_consumed[slot], 0)); /* the launch that read this slot is done */
-    CU(cudaMemcpyAsync(base, ts_us, sizeof(int64_t) * n, cudaMemcpyHostToDevice, si));
-    CU(cudaMemcpyAsync(base + bt, kinds, n, cudaMemcpyHostToDevice, si));
-    CU(cudaMemcpyAsync(base + bt + bk, mu3, sizeof(double) * n * 3, cudaMemcpyHostToDevice, si));
-    CU(cudaMemcpyAsync(base + bt + bk + bm, cov, bc, cudaMemcpyHostToDevice, si));
-    CU(cudaEventRecord(h->pipe.in_ready[slot], si));
-    CU(cudaStreamWaitEvent(h->stream, h->pipe.in_ready[slot], 0));
-    rc = ukfb_run_events_dev(h, K, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const int8_t*>(base + bt),
-                             reinterpret_cast<const double*>(base + bt + bk), reinterpret_cast<const double*>(base + bt + bk + bm), cov_mode);
-    if (rc) return rc;
-    CU(cudaEventRecord(h->pipe.in_consumed[slot], h->stream));
-    h->pipe.n_in++;
-    return UKFB_OK;
+    return run_events_any(h, K, ts_us, kinds, mu3, cov, cov_mode, true, "ukfb_run_events_async");
 }
 
 /* ---- status ------------------------------------------------------------------------------------------------ */
@@ -1477,6 +1807,7 @@ extern "C" int ukfb_get_status(ukfb_handle* h, uint32_t* flags)
 {
     CHECK_H(h);
     if (!flags) return fail(UKFB_ERR_INVALID, "ukfb_get_status: null argument");
+    UKFB_FAN(h, ukfb_get_status(s_, flags + f_));
     CU(cudaMemcpyAsync(flags, h->status, sizeof(uint32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
@@ -1485,6 +1816,7 @@ extern "C" int ukfb_get_status(ukfb_handle* h, uint32_t* flags)
 extern "C" int ukfb_clear_status(ukfb_handle* h)
 {
     CHECK_H(h);
+    UKFB_FAN(h, ukfb_clear_status(s_));
     CU(cudaMemsetAsync(h->status, 0, sizeof(uint32_t) * h->B, h->stream));
     return UKFB_OK;
 }
@@ -1492,6 +1824,22 @@ extern "C" int ukfb_clear_status(ukfb_handle* h)
 extern "C" int ukfb_status_summary(ukfb_handle* h, int64_t* n_flagged, uint32_t* any_bits)
 {
     CHECK_H(h);
+    if (is_sharded(h)) {
+        std::vector<int64_t> n(h->shards.size(), 0);
+        std::vector<uint32_t> bits(h->shards.size(), 0u);
+        const int rc = fan_out(h, [&](ukfb_handle* s_, long long f_, long long) {
+            size_t i = 0;
+            while (h->first[i] != f_) ++i; /* the shard whose range starts at f_ (every shard holds >= 1 filter) */
+            return ukfb_status_summary(s_, &n[i], &bits[i]);
+        });
+        if (rc) return rc;
+        int64_t nt = 0;
+        uint32_t bt = 0;
+        for (size_t i = 0; i < n.size(); ++i) nt += n[i], bt |= bits[i];
+        if (n_flagged) *n_flagged = nt;
+        if (any_bits) *any_bits = bt;
+        return UKFB_OK;
+    }
     CU(cudaMemsetAsync(h->summary, 0, sizeof(long long) * 2, h->stream));
     status_summary_kernel<<<grid_for(h->B), 256, 0, h->stream>>>(h->status, h->B, h->summary);
     CU(cudaGetLastError());
@@ -1507,6 +1855,16 @@ extern "C" int ukfb_get_mean_iter_hist(ukfb_handle* h, uint64_t hist[8])
 {
     CHECK_H(h);
     if (!hist) return fail(UKFB_ERR_INVALID, "ukfb_get_mean_iter_hist: null argument");
+    if (is_sharded(h)) {
+        for (int k = 0; k < 8; ++k) hist[k] = 0;
+        for (ukfb_handle* s : h->shards) {
+            uint64_t one[8];
+            const int rc = ukfb_get_mean_iter_hist(s, one);
+            if (rc) return rc;
+            for (int k = 0; k < 8; ++k) hist[k] += one[k];
+        }
+        return UKFB_OK;
+    }
     unsigned long long tmp[HIST_SLOTS * 8];
     CU(cudaMemcpyAsync(tmp, h->hist, sizeof(tmp), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1519,6 +1877,7 @@ extern "C" int ukfb_get_mean_iter_hist(ukfb_handle* h, uint64_t hist[8])
 extern "C" int ukfb_clear_mean_iter_hist(ukfb_handle* h)
 {
     CHECK_H(h);
+    UKFB_FAN(h, ukfb_clear_mean_iter_hist(s_));
     CU(cudaMemsetAsync(h->hist, 0, sizeof(unsigned long long) * HIST_SLOTS * 8, h->stream));
     return UKFB_OK;
 }
@@ -1527,6 +1886,7 @@ extern "C" int ukfb_clear_mean_iter_hist(ukfb_handle* h)
 extern "C" int ukfb_synchronize(ukfb_handle* h)
 {
     CHECK_H(h);
+    UKFB_FAN(h, ukfb_synchronize(s_));
     CU(cudaStreamSynchronize(h->stream));
     if (h->pipe.made) {
         CU(cudaStreamSynchronize(h->pipe.s_in));
@@ -1535,12 +1895,39 @@ extern "C" int ukfb_synchronize(ukfb_handle* h)
     return UKFB_OK;
 }
 
-extern "C" void* ukfb_stream(ukfb_handle* h) { return h ? reinterpret_cast<void*>(h->stream) : nullptr; }
+extern "C" void* ukfb_stream(ukfb_handle* h) { return h ? reinterpret_cast<void*>(h->stream) : nullptr; } /* sharded parent: null */
+
+extern "C" int ukfb_wait_for_stream(ukfb_handle* h, void* cuda_stream)
+{
+    CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t rc = cudaEventRecord(e, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (rc == cudaSuccess) rc = cudaStreamWaitEvent(h->stream, e, 0);
+    cudaEventDestroy(e); /* released once the recorded work has completed */
+    if (rc != cudaSuccess) return fail(UKFB_ERR_CUDA, "ukfb_wait_for_stream: %s", cudaGetErrorString(rc));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_stream_wait(ukfb_handle* h, void* cuda_stream)
+{
+    CHECK_H(h);
+    UKFB_NOT_SHARDED(h);
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t rc = cudaEventRecord(e, h->stream);
+    if (rc == cudaSuccess) rc = cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), e, 0);
+    cudaEventDestroy(e);
+    if (rc != cudaSuccess) return fail(UKFB_ERR_CUDA, "ukfb_stream_wait: %s", cudaGetErrorString(rc));
+    return UKFB_OK;
+}
 
 extern "C" int ukfb_event_record(ukfb_handle* h, int slot)
 {
     CHECK_H(h);
     if (slot < 0 || slot >= 16) return fail(UKFB_ERR_INVALID, "ukfb_event_record: slot out of range");
+    UKFB_FAN(h, ukfb_event_record(s_, slot)); /* every shard records on its own stream */
     CU(cudaEventRecord(h->ev[slot], h->stream));
     return UKFB_OK;
 }
@@ -1549,12 +1936,28 @@ extern "C" int ukfb_event_elapsed_ms(ukfb_handle* h, int slot_begin, int slot_en
 {
     CHECK_H(h);
     if (slot_begin < 0 || slot_begin >= 16 || slot_end < 0 || slot_end >= 16 || !ms) return fail(UKFB_ERR_INVALID, "ukfb_event_elapsed_ms: bad argument");
+    if (is_sharded(h)) { /* the slowest shard: device-timed, max over devices */
+        *ms = 0.f;
+        for (ukfb_handle* s : h->shards) {
+            float one = 0.f;
+            const int rc = ukfb_event_elapsed_ms(s, slot_begin, slot_end, &one);
+            if (rc) return rc;
+            if (one > *ms) *ms = one;
+        }
+        return UKFB_OK;
+    }
     CU(cudaEventSynchronize(h->ev[slot_end]));
     CU(cudaEventElapsedTime(ms, h->ev[slot_begin], h->ev[slot_end]));
     return UKFB_OK;
 }
 
-extern "C" int64_t ukfb_launch_count(const ukfb_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t ukfb_launch_count(const ukfb_handle* h)
+{
+    if (!h) return 0;
+    long long n = h->launches;
+    for (const ukfb_handle* s : h->shards) n += s->launches;
+    return n;
+}
 
 /* self-test of the device SO(3) kernels (so3.cuh): q = exp(v), w = log(q), rc = 1 / x, (sq, rs) = sqrt / rsqrt of x */
 __global__ void so3_selftest_kernel(const double* __restrict__ v, const double* __restrict__ x, double* __restrict__ out, long long n)
@@ -1580,6 +1983,7 @@ extern "C" int ukfb_selftest_so3(ukfb_handle* h, int64_t n, const double* v, con
 {
     CHECK_H(h);
     if (n < 1 || !v || !x || !out) return fail(UKFB_ERR_INVALID, "ukfb_selftest_so3: bad argument");
+    if (is_sharded(h)) return ukfb_selftest_so3(h->shards[0], n, v, x, out);
     const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * 14;
     int rc = stage_reserve(h, bv + bx + bo);
     if (rc) return rc;
@@ -1597,6 +2001,7 @@ extern "C" int ukfb_measure_fp64_peak(ukfb_handle* h, double* flops_per_s)
 {
     CHECK_H(h);
     if (!flops_per_s) return fail(UKFB_ERR_INVALID, "ukfb_measure_fp64_peak: null argument");
+    if (is_sharded(h)) return ukfb_measure_fp64_peak(h->shards[0], flops_per_s);
     int rc = stage_reserve(h, 256);
     if (rc) return rc;
     cudaDeviceProp prop;

@@ -165,6 +165,13 @@ UKFB_HD int meas_dim(int kind)
     }
 }
 
+/* does filter class F (F::KIND) have an integrateMeasurement overload that calls ukf->update for `kind`? */
+template <class F>
+UKFB_HD bool meas_kind_of_class(int kind)
+{
+    return F::KIND == 0 ? (kind >= 0 && kind <= UKFB_MEAS_POSE_ANGULAR_VELOCITY) : kind == UKFB_MEAS_ORI_VELOCITY;
+}
+
 /* ---- manifold operations on a lane's state x[MU] --------------------------------- */
 
 template <class F>
@@ -912,12 +919,15 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                         dt = p.dt[tick * p.dt_kstride + b * p.dt_stride];
                     }
                     if (have_dt) {
-                        if (dt < 0.0)
+                        if (dt < 0.0) {
                             st |= UKFB_STATUS_NEG_DT;
-                        else if (dt <= p.min_dt) {
+                            if (p.events) kind = -1, store = -1; /* the reference's callback leaves here (the throw): this sample is neither integrated nor stored */
+                        } else if (dt <= p.min_dt) {
                             /* delta time is zero or close to zero: no-op */
-                        } else if (dt > p.max_dt)
+                        } else if (dt > p.max_dt) {
                             st |= UKFB_STATUS_DT_TOO_LARGE;
+                            if (p.events) kind = -1, store = -1;
+                        }
                         else {
                             flags |= CF_PRED;
                             fr[SM::OFF_DT] = dt;
@@ -928,6 +938,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(WPB * 32, MINB) ukf_step_kernel(const UKFB_G
                     if (!p.events) {
                         kind = p.tick_kinds ? int(p.tick_kinds[tick])
                                             : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                        if (p.kind == -2 && !p.tick_kinds && kind != UKFB_MEAS_NONE && !meas_kind_of_class<F>(kind)) {
+                            st |= UKFB_STATUS_BAD_EVENT; /* per-filter kinds on the device: a kind of the other filter class is ignored */
+                            kind = -1;
+                        }
                         if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
                     }
                     if (kind >= 0 || store >= 0) {

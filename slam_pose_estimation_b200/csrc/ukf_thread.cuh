@@ -514,12 +514,15 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
                     dt = p.dt[tick * p.dt_kstride + b * p.dt_stride];
                 }
                 if (have_dt) {
-                    if (dt < 0.0)
+                    if (dt < 0.0) {
                         status |= UKFB_STATUS_NEG_DT;
-                    else if (dt <= p.min_dt) {
+                        if (p.events) kind = -1, store = -1; /* the reference's callback leaves here (the throw): this sample is neither integrated nor stored */
+                    } else if (dt <= p.min_dt) {
                         /* delta time is zero or close to zero: no-op */
-                    } else if (dt > p.max_dt)
+                    } else if (dt > p.max_dt) {
                         status |= UKFB_STATUS_DT_TOO_LARGE;
+                        if (p.events) kind = -1, store = -1;
+                    }
                     else {
                         do_pred = true;
                         ma.dt = dt;
@@ -529,6 +532,10 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(TILE, 1) ukf_thread_kernel(const UKFB_GRID_C
             if (p.do_update && !idle) {
                 if (!p.events) {
                     kind = p.tick_kinds ? int(p.tick_kinds[tick]) : (p.kind == -2 ? int(p.kinds[tick * p.kinds_kstride + b]) : p.kind);
+                    if (p.kind == -2 && !p.tick_kinds && kind != UKFB_MEAS_NONE && !meas_kind_of_class<F>(kind)) {
+                        status |= UKFB_STATUS_BAD_EVENT; /* per-filter kinds on the device: a kind of the other filter class is ignored */
+                        kind = -1;
+                    }
                     if (p.mask && !p.mask[tick * p.mask_kstride + b]) kind = -1;
                 }
                 if (kind >= 0) {
