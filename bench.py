@@ -107,16 +107,31 @@ def bind_to_gpu_numa_node(index: int):
     return None
 
 
+R_SCALES = (0.25, 1.0, 4.0)  # BASELINE config 4 / SURVEY 8(d) "C4": measurement-covariance scale swept over the filters
+
+
+def r_scale_of(idx: np.ndarray) -> np.ndarray:
+    return np.asarray(R_SCALES)[np.asarray(idx) % len(R_SCALES)]
+
+
 def make_workload(B: int, first: int, pool: int):
-    """initial state (perturbed per filter) and `pool` distinct measurement sets for filters first..first+B"""
+    """initial state (perturbed per filter), `pool` distinct measurement sets and the per-filter measurement covariance
+    (sigma_gyro^2 I scaled by 0.25 / 1 / 4 along the sweep) for filters first..first+B"""
     from slam_pose_estimation_b200 import synthetic as syn
 
     mu, sg = syn.pose_initial(B, perturb=True, first=first)
     zs = np.empty((pool, B, 3))
     for j in range(pool):
         zs[j] = syn.pose_measurement(8, B, j + 1, first=first)[0]
-    R = np.eye(3) * syn.SIGMA_GYRO**2
-    return mu, sg, zs, R
+    R = (np.eye(3) * syn.SIGMA_GYRO**2)[None] * r_scale_of(np.arange(first, first + B))[:, None, None]
+    return mu, sg, zs, np.ascontiguousarray(R)
+
+
+def make_workload_of(indices, pool: int):
+    """the same as make_workload for an arbitrary list of global filter indices (the parity sample)"""
+    parts = [make_workload(1, int(i), pool) for i in indices]
+    return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]),
+            np.concatenate([p[2] for p in parts], axis=1), np.concatenate([p[3] for p in parts]))
 
 
 def time_oracle(B: int, steps: int, warmup: int, threads: int | None = None):
@@ -134,6 +149,25 @@ def time_oracle(B: int, steps: int, warmup: int, threads: int | None = None):
         o.step(syn.DT, 8, zs[k % 4], R)
     dt = time.perf_counter() - t0
     return B * steps / dt, o.max_threads(), dt
+
+
+def parity_sample(applied, indices, mu_gpu, sg_gpu, pool: int):
+    """replays the steps the engine has applied (`applied`: the measurement-set index of every step so far) on the CPU
+    oracle for the sampled filters and returns the parity figures of tests/parity.py"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity as P
+    from oracle.oracle_lib import OracleBatch
+    from slam_pose_estimation_b200 import synthetic as syn
+
+    mu0, sg0, zs, R = make_workload_of(indices, pool)
+    o = OracleBatch(0, len(indices))
+    o.initialize(mu0, sg0)
+    for j in applied:
+        o.step(syn.DT, 8, zs[j], R)
+    mu_ref, sg_ref = o.get_state()
+    return {"filters": len(indices), "steps_replayed": len(applied), "checker": "CPU oracle (oracle/), same inputs",
+            "max_mu_err": float(P.mu_error(0, mu_gpu, mu_ref).max()), "max_sigma_err": float(P.sigma_error(sg_gpu, sg_ref).max()),
+            "tolerance": 1e-9}
 
 
 def run_reference(args, rank, world):
@@ -171,6 +205,20 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def timed_steps(f, step, steps, warmup, barrier, max_over_ranks):
+    """`warmup` untimed then `steps` timed calls of step(k) on handle f: device-timed with CUDA events on the engine's
+    stream, barrier + synchronize on both sides, max over ranks.  Returns ms for the `steps` calls."""
+    for k in range(warmup):
+        step(k)
+    barrier()
+    f.event_record(0)
+    for k in range(steps):
+        step(warmup + k)
+    f.event_record(1)
+    barrier()
+    return max_over_ranks(f.event_elapsed_ms(0, 1))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +232,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-literal", action="store_true", help="skip the secondary measurement of the literal kernel")
     ap.add_argument("--no-orientation", action="store_true", help="skip the secondary OrientationUKF (C2) figure")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (1 Mi filters in total) at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -206,20 +255,24 @@ def main():
 
     from slam_pose_estimation_b200 import _build, synthetic as syn
     from slam_pose_estimation_b200.batch import UkfBatch
+    from slam_pose_estimation_b200.shard import gather_estimates
 
     if not os.path.exists(_build.LIB):
         raise RuntimeError("lib/libukfb.so missing -- run __graft_entry__.build()")
 
     B = args.filters
+    pool = args.pool
     first = rank * B  # contiguous shard [rank*B, (rank+1)*B) of a world*B Monte-Carlo sweep
-    mu0, sg0, zs, R = make_workload(B, first, args.pool)
+    mu0, sg0, zs, R = make_workload(B, first, pool)
     f = UkfBatch(0, B, device=local)
     f.initialize(mu0, sg0)
+    f.set_measurement_cov(8, R)  # the sensor covariances stay on the device: a streaming caller sends z only
     dev = torch.device("cuda", local)
     d_dt = torch.full((1,), syn.DT, dtype=torch.float64, device=dev)
     d_R = torch.from_numpy(R).to(dev)
-    d_z = [torch.from_numpy(zs[j]).to(dev) for j in range(args.pool)]
+    d_z = [torch.from_numpy(zs[j]).to(dev) for j in range(pool)]
     torch.cuda.synchronize()
+    applied = []  # measurement-set index of every step handle f has taken (the parity sample replays them)
 
     def barrier():
         f.synchronize()
@@ -235,8 +288,12 @@ def main():
         return float(t.item())
 
     # ---- device-timed: inputs resident in HBM --------------------------------------------------
+    def dev_step(k):
+        applied.append(k % pool)
+        f.step_dev(d_dt, False, 8, d_z[k % pool], d_R, True)
+
     for k in range(args.warmup):
-        f.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
+        dev_step(k)
     f.clear_mean_iter_hist()
     barrier()
     sampler = ClockSampler(local)
@@ -244,60 +301,150 @@ def main():
     launches0 = f.launch_count()
     f.event_record(0)
     for k in range(args.steps):
-        f.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
+        dev_step(args.warmup + k)
     f.event_record(1)
     barrier()
     ms = max_over_ranks(f.event_elapsed_ms(0, 1))
     launches = f.launch_count() - launches0
-    clocks_dev = sampler.rows[:]
     hist = f.get_mean_iter_hist()
     n_flag, bits = f.status_summary()
 
     # ---- end to end through the host-pointer C ABI ----------------------------------------------
-    # Every step: H2D of that step's measurements from pinned host memory, the fused kernel, D2H of the B x 13
-    # estimates into pinned host memory.  `e2e` uses the streaming calls (ukfb_step_async / ukfb_get_state_async:
-    # copy-in, compute and copy-out streams, two staging slots each, so step k+1's input copy and kernel overlap
-    # step k's output copy); `e2e_blocking` the blocking calls (each returns after its own copies).
+    # Every step: H2D of that step's measurements from pinned host memory, the fused kernel, D2H of the estimates into
+    # pinned host memory.  `e2e` uses the streaming calls (ukfb_step_async / ukfb_get_state_async: copy-in, compute and
+    # copy-out streams, two staging slots each, so step k+1's input copy and kernel overlap step k's output copy) and
+    # reads back the whole B x 13 mean; `pose_only` reads back position + orientation (7 of the 13 entries, what a
+    # consumer of BodyStateMeasurement's pose needs); `blocking` uses the blocking calls.
     e2e = None
     if not args.no_e2e:
-        z_pin = [torch.from_numpy(zs[j]).pin_memory() for j in range(args.pool)]
+        z_pin = [torch.from_numpy(zs[j]).pin_memory() for j in range(pool)]
         z_np = [t.numpy() for t in z_pin]
-        R_pin = torch.from_numpy(R.copy()).pin_memory()
         dt_pin = torch.full((1,), syn.DT, dtype=torch.float64).pin_memory()
         mu_pin = [torch.empty((B, 13), dtype=torch.float64).pin_memory() for _ in range(2)]
         mu_np = [t.numpy() for t in mu_pin]
-        for k in range(2):
-            f.step(syn.DT, 8, z_np[k % args.pool], R)
-            f.get_state_into(mu_np[0])
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            f.step(syn.DT, 8, z_np[k % args.pool], R)  # H2D of z (B x 3) and R inside the call
-            f.get_state_into(mu_np[0])                  # D2H of the B x 13 estimates
-        f.synchronize()
-        blk_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        for k in range(3):
-            f.step_async(dt_pin.numpy(), 8, z_np[k % args.pool], R_pin.numpy())
-            f.get_state_async(mu_np[k & 1])
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            f.step_async(dt_pin.numpy(), 8, z_np[k % args.pool], R_pin.numpy())
-            f.get_state_async(mu_np[k & 1])
-        f.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
+        pose_np = [torch.empty((B, 7), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+
+        def e2e_loop(step, read, n):
+            for k in range(n):
+                applied.append(k % pool)
+                step(k)
+                read(k)
+            f.synchronize()
+
+        blk = (lambda k: f.step(syn.DT, 8, z_np[k % pool], None), lambda k: f.get_state_into(mu_np[0]))
+        full = (lambda k: f.step_async(dt_pin.numpy(), 8, z_np[k % pool], None), lambda k: f.get_state_async(mu_np[k & 1]))
+        pose = (lambda k: f.step_async(dt_pin.numpy(), 8, z_np[k % pool], None), lambda k: f.get_mu_range_async(0, 7, pose_np[k & 1]))
+        res = {}
+        for name, (step, read) in (("blocking", blk), ("full", full), ("pose_only", pose)):
+            e2e_loop(step, read, 3)
+            barrier()
+            t0 = time.perf_counter()
+            e2e_loop(step, read, args.steps)
+            res[name] = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+        e2e_s = res["full"]
         e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(B * 3 * 8 + 9 * 8 + 8), "d2h_bytes_per_step": int(B * 13 * 8),
+               "h2d_bytes_per_step": int(B * 3 * 8 + 8), "d2h_bytes_per_step": int(B * 13 * 8),
                "ms_per_step": e2e_s / args.steps * 1e3,
-               "api": "ukfb_step_async(host z, R) + ukfb_get_state_async(host mu) per step, pinned host buffers, "
-                      "one ukfb_synchronize at the end; copies of step k overlap the kernel of step k+1",
-               "blocking": {"value": world * B * args.steps / blk_s, "ms_per_step": blk_s / args.steps * 1e3,
+               "api": "ukfb_step_async(host z; per-filter R kept on the device by ukfb_set_measurement_cov) + "
+                      "ukfb_get_state_async(host mu) per step, pinned host buffers, one ukfb_synchronize at the end; copies "
+                      "of step k overlap the kernel of step k+1",
+               "pose_only": {"value": world * B * args.steps / res["pose_only"], "ms_per_step": res["pose_only"] / args.steps * 1e3,
+                             "d2h_bytes_per_step": int(B * 7 * 8),
+                             "api": "the same with ukfb_get_mu_range_async(0, 7): position + orientation only"},
+               "blocking": {"value": world * B * args.steps / res["blocking"], "ms_per_step": res["blocking"] / args.steps * 1e3,
                             "api": "ukfb_step + ukfb_get_state, each returning after its own copies"}}
         assert np.isfinite(mu_np[0]).all() and np.isfinite(mu_np[1]).all()
+        assert np.array_equal(pose_np[(args.steps - 1) & 1], f.get_mu_range(0, 7))
     sampler.stop()
     clocks = sampler.summary()
+
+    # ---- the final gather of the estimates and a parity sample against the CPU oracle ----------------------------------
+    # N > 1: every rank's B x 13 means travel to rank 0 (one torch.distributed gather over NCCL, then one D2H): the only
+    # cross-GPU traffic of the job.  The sample: S filters per rank at a stride through the shard, mean AND covariance,
+    # compared with the oracle replaying the very steps applied above.
+    S = 8
+    loc = (np.arange(S) * (B // S)).astype(np.int64)
+    d_mu = torch.empty((B, 13), dtype=torch.float64, device=dev)
+    d_sg = torch.empty((B, 12, 12), dtype=torch.float64, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    f.get_state_dev(d_mu, d_sg)
+    f.synchronize()
+    gathered = None
+    if world > 1:
+        gathered = gather_estimates(d_mu, world * B)
+        if rank == 0:
+            gathered = gathered.cpu()
+    else:
+        gathered = d_mu.cpu()
+    torch.cuda.synchronize()
+    gather_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    smp_mu, smp_sg = d_mu[torch.from_numpy(loc).to(dev)], d_sg[torch.from_numpy(loc).to(dev)]
+    if world > 1:
+        mus = [torch.empty_like(smp_mu) for _ in range(world)]
+        sgs = [torch.empty_like(smp_sg) for _ in range(world)]
+        dist.all_gather(mus, smp_mu)
+        dist.all_gather(sgs, smp_sg)
+        smp_mu, smp_sg = torch.cat(mus), torch.cat(sgs)
+    del d_sg
+    gather = None
+    if rank == 0:
+        gidx = np.concatenate([r * B + loc for r in range(world)])
+        assert np.array_equal(gathered.numpy()[gidx], smp_mu.cpu().numpy())  # the gathered buffer is in filter order
+        gather = {"ms": gather_ms, "bytes": int(world * B * 13 * 8),
+                  "api": "ukfb_get_state_dev per rank + one torch.distributed.gather (NCCL) + D2H on rank 0" if world > 1
+                         else "ukfb_get_state_dev + D2H",
+                  "parity_sample": parity_sample(applied, gidx, smp_mu.cpu().numpy(), smp_sg.cpu().numpy(), pool)}
+    del gathered, d_mu
+
+    # ---- strong scaling: BASELINE config 4 proper, ONE batch of 1 Mi filters sharded over the N GPUs ---------------------
+    strong = None
+    if world > 1 and not args.no_strong:
+        total = 1 << 20
+        Bs = total // world
+        mu_s, sg_s, zs_s, R_s = make_workload(Bs, rank * Bs, pool)
+        fs = UkfBatch(0, Bs, device=local)
+        fs.initialize(mu_s, sg_s)
+        fs.set_measurement_cov(8, R_s)
+        ds_R = torch.from_numpy(R_s).to(dev)
+        ds_z = [torch.from_numpy(zs_s[j]).to(dev) for j in range(pool)]
+        torch.cuda.synchronize()
+
+        def sbarrier():
+            fs.synchronize()
+            torch.cuda.synchronize()
+            dist.barrier()
+
+        reps = max(args.steps, 20) * 4  # short launches: more of them for a stable figure
+        s_ms = timed_steps(fs, lambda k: fs.step_dev(d_dt, False, 8, ds_z[k % pool], ds_R, True), reps, args.warmup, sbarrier, max_over_ranks)
+        per_step = s_ms / reps
+        tiles = (Bs + 31) // 32
+        resident = 148 * 8
+        strong = {"filters_total": total, "filters_per_gpu": Bs, "value": total / (per_step * 1e-3), "unit": UNIT,
+                  "ms_per_step": per_step, "steps": reps,
+                  "efficiency_vs_one_gpu_launch": (ms / args.steps) / (world * per_step),
+                  "note": "efficiency = time of the 1 Mi-filter launch on one GPU (the weak leg above, same kernel) / (N x this "
+                          "leg's time per step)",
+                  "warps_per_gpu": tiles, "resident_warps_per_gpu": resident, "waves": tiles / resident}
+        if not args.no_e2e:
+            zs_pin = [torch.from_numpy(zs_s[j]).pin_memory().numpy() for j in range(pool)]
+            dts_pin = torch.full((1,), syn.DT, dtype=torch.float64).pin_memory().numpy()
+            mus_pin = [torch.empty((Bs, 13), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+            for k in range(3):
+                fs.step_async(dts_pin, 8, zs_pin[k % pool], None)
+                fs.get_state_async(mus_pin[k & 1])
+            sbarrier()
+            t0 = time.perf_counter()
+            for k in range(reps):
+                fs.step_async(dts_pin, 8, zs_pin[k % pool], None)
+                fs.get_state_async(mus_pin[k & 1])
+            fs.synchronize()
+            se = max_over_ranks(time.perf_counter() - t0)
+            sbarrier()
+            strong["e2e"] = {"value": total * reps / se, "ms_per_step": se / reps * 1e3,
+                             "h2d_bytes_per_step": int(Bs * 3 * 8 + 8), "d2h_bytes_per_step": int(Bs * 13 * 8)}
+        fs.close()
 
     # ---- the literal kernel on the same workload (secondary figure) -----------------------------------
     # UKFB_KERNEL=thread selects ukf_thread.cuh at ukfb_create: every sigma point of every pass is pushed through
@@ -310,15 +457,14 @@ def main():
         g = UkfBatch(0, B, device=local)
         os.environ.pop("UKFB_KERNEL")
         g.initialize(mu0, sg0)
-        for k in range(args.warmup):
-            g.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
-        g.synchronize()
-        g.event_record(0)
-        for k in range(args.steps):
-            g.step_dev(d_dt, False, 8, d_z[k % args.pool], d_R, False)
-        g.event_record(1)
-        g.synchronize()
-        lit_ms = max_over_ranks(g.event_elapsed_ms(0, 1))
+
+        def gbarrier():
+            g.synchronize()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+
+        lit_ms = timed_steps(g, lambda k: g.step_dev(d_dt, False, 8, d_z[k % pool], d_R, True), args.steps, args.warmup, gbarrier, max_over_ranks)
         literal = {"kernel": "ukf_thread_kernel<PoseF>", "value": world * B * args.steps / (lit_ms * 1e-3), "unit": UNIT,
                    "ms_per_step": lit_ms / args.steps}
         fp64_peak = g.measure_fp64_peak() if rank == 0 else 0.0
@@ -347,6 +493,7 @@ def main():
         d_zo = torch.from_numpy(syn.orientation_velocity(Bo, 1)[0]).to(dev)[None].expand(Ko, Bo, 3).contiguous()
         d_Ro = torch.from_numpy(np.tile(np.eye(3) * syn.SIGMA_DVL**2, (Ko, 1, 1))).to(dev)
         d_dto = torch.full((Ko,), syn.DT, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()  # the inputs above were produced on torch's stream (run_dev also orders itself after it)
         for _ in range(2):
             g.run_dev(Ko, d_dto, False, kinds_o, d_zo, d_Ro, False, d_imu)
         g.synchronize()
@@ -380,17 +527,22 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # ncu figures of the dominant kernel (one `ncu --set full` capture, profiles/): only reported when the capture was
+    # taken from the kernel sources this library is built from
     prof = {}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    traffic = prof.get("dram_bytes_per_launch") if B == (1 << 20) else None
+    prof_current = bool(prof) and prof.get("source_sha16") == _build.source_hash()
+    traffic = prof.get("dram_bytes_per_launch") if (prof_current and B == (1 << 20)) else None
     executed = None
-    if prof.get("executed_fp64_flops_per_step") and fp64_peak:
+    if prof_current and prof.get("executed_fp64_flops_per_step") and fp64_peak:
         ex = float(prof["executed_fp64_flops_per_step"]) * B / launch_s
         executed = {"flops_per_step": prof["executed_fp64_flops_per_step"], "achieved": ex / 1e12, "frac": ex / fp64_peak,
-                    "source": "ncu op counts of this kernel on this workload (profiles/traffic.json) / this run's launch time"}
+                    "fp64_pipe_active_pct_ncu": prof.get("fp64_pipe_active_pct"),
+                    "source": "ncu op counts of this kernel on this workload (profiles/traffic.json, same source hash as the "
+                              "loaded library) / this run's launch time"}
     if orientation and fp64_peak:
         orientation["roofline_frac"] = orientation["achieved_tflops"] * 1e12 / fp64_peak
     if literal and fp64_peak:
@@ -401,15 +553,18 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4: PoseUKF Monte-Carlo sweep sharded by filter index; step = predictionStep(1 ms) + "
+        "config": {"workload": "C4: PoseUKF Monte-Carlo sweep (initial states drawn per filter, measurement covariance scaled "
+                               "x0.25 / x1 / x4 along the sweep) sharded by filter index; step = predictionStep(1 ms) + "
                                "AngularVelocityMeasurement update (m=3), one fused launch",
                    "filters_per_gpu": B, "filters_total": world * B, "parallelism": f"filter-shard x{world}, no collective on the step path",
                    "l2": "state records 805 MB per GPU >> 126 MB L2 (inputs larger than L2)" if B * 768 > 3 * 126e6 else "inputs smaller than L2",
-                   "mean_passes_avg": passes, "status_flagged": int(n_flag), "rank0_cpu_affinity": numa},
+                   "mean_passes_avg": passes, "status_flagged": int(n_flag), "rank0_cpu_affinity": numa,
+                   "kernel_source_sha16": _build.source_hash()},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved_flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                      "frac": (achieved_flops / fp64_peak) if fp64_peak else None, "traffic": traffic,
+                     "traffic_note": None if prof_current else "profiles/traffic.json was captured from other kernel sources: not reported",
                      "peak_source": "measured in this run: independent-DFMA microkernel (MEASURED_PEAKS.json holds no FP64 figure)",
                      "flops_per_step": flops_step, "flops_per_step_contract_k3": FLOPS_PER_STEP_K3,
                      "flops_basis": "SURVEY.md 8(d): algorithmic flops of the reference's sigma-point sequence per step; the "
@@ -422,6 +577,10 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if gather:
+        line["gather"] = gather
+    if strong:
+        line["strong_1M"] = strong
     if orientation:
         line["orientation_c2"] = orientation
     if rank == 0 and not args.no_cpu_baseline and world == 1:

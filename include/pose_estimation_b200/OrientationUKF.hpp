@@ -44,6 +44,14 @@ public:
         initializeFilter(initial_state, state_cov);
     }
 
+    OrientationUKF(int64_t batch, const State* initial_state, const Covariance* state_cov, double gyro_bias_tau, double acc_bias_tau,
+                   const LocationConfiguration& location, const std::vector<int>& devices)
+        : UnscentedKalmanFilter(batch, devices)
+    {
+        check(ukfb_set_orientation_params(h, gyro_bias_tau, acc_bias_tau, location.latitude));
+        initializeFilter(initial_state, state_cov);
+    }
+
     /* OrientationUKF.cpp:53-57: finite check, then store */
     void integrateMeasurement(const RotationRate& m)
     {

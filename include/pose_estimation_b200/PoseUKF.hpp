@@ -39,6 +39,13 @@ public:
         initializeFilter(initial_state, state_cov);
     }
 
+    /* `batch` filters split by filter index over the listed GPUs (one object, one host thread per device inside) */
+    PoseUKF(int64_t batch, const State* initial_state, const Covariance* state_cov, const std::vector<int>& devices)
+        : UnscentedKalmanFilter(batch, devices)
+    {
+        initializeFilter(initial_state, state_cov);
+    }
+
     /* PoseUKF.cpp:112-173.  The measurement is applied to every filter of the batch (batch = 1: the
      * reference call); integrateMeasurements takes one measurement per filter. */
     void integrateMeasurement(const PositionMeasurement& m) { update(UKFB_MEAS_POSE_POSITION, &m, false); }

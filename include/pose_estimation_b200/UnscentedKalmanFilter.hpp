@@ -5,7 +5,8 @@
  * Same member names, argument meaning and error behaviour as the reference class, minus its Eigen / MTK /
  * base-types dependencies (absent from this image): states and covariances are plain arrays, base::Time is an
  * int64 microsecond count.  One object drives `batch` independent filters (batch = 1 gives exactly the
- * reference's single-filter object); every method applies to all of them.  The arithmetic runs in the CUDA
+ * reference's single-filter object), on one GPU or -- constructed with a device list -- split by filter index over
+ * several GPUs of the box; every method applies to all of them.  The arithmetic runs in the CUDA
  * engine -- there is no host implementation behind this class.
  *
  * Error behaviour: the reference throws std::runtime_error from predictionStep / checkMeasurment.  The engine
@@ -40,6 +41,13 @@ public:
     explicit UnscentedKalmanFilter(int64_t batch = 1, int device = 0) : h(nullptr), batch_size(batch)
     {
         check(ukfb_create(FILTER_KIND, batch, device, &h));
+    }
+    /* the same `batch` filters split by filter index over several GPUs of the box behind one object (ukfb_create_sharded:
+     * contiguous shards, one host worker and one set of streams per device, no inter-device traffic); every method below
+     * then serves all devices at once and getCurrentState gathers all shards into the caller's arrays */
+    UnscentedKalmanFilter(int64_t batch, const std::vector<int>& devices) : h(nullptr), batch_size(batch)
+    {
+        check(ukfb_create_sharded(FILTER_KIND, batch, devices.data(), int(devices.size()), &h));
     }
     virtual ~UnscentedKalmanFilter() { ukfb_destroy(h); }
     UnscentedKalmanFilter(const UnscentedKalmanFilter&) = delete; /* boost::noncopyable, :16 */

@@ -213,6 +213,11 @@ int ukfb_predict_time_dev(ukfb_handle* h, const int64_t* d_ts_us, int per_filter
  * or NULL for all.  m = ukfb_meas_dim(kind). */
 int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, const double* cov, int cov_per_filter,
                 const uint8_t* mask);
+/* A sensor's covariance rarely changes between samples.  ukfb_set_measurement_cov keeps one covariance for
+ * `meas_kind` on the device (m x m, or B x m x m when per_filter = 1); afterwards the host-pointer calls ukfb_update,
+ * ukfb_step and ukfb_step_async accept cov = NULL for that kind and use the kept one (cov_per_filter is then ignored),
+ * so a streaming caller only sends the measurement vectors.  Same results as passing the covariance every time. */
+int ukfb_set_measurement_cov(ukfb_handle* h, int meas_kind, const double* cov, int per_filter);
 int ukfb_update_dev(ukfb_handle* h, int meas_kind, const double* d_mu, const double* d_cov, int cov_per_filter,
                     const uint8_t* d_mask);
 int ukfb_meas_dim(int meas_kind);

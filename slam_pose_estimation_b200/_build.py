@@ -29,6 +29,18 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found: the engine is CUDA-only and cannot be built without the CUDA toolkit")
 
 
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) of the kernel sources the library is built from: profiles/traffic.json is stamped
+    with it, so that ncu figures of an older kernel are not reported for a newer one"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in sorted(x for x in DEPS if x.endswith((".cu", ".cuh"))):
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True

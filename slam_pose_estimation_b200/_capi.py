@@ -18,6 +18,16 @@ SIGNATURES = {
     "ukfb_last_error": (C.c_char_p, []),
     "ukfb_create": (I, [I, L, I, C.POINTER(P)]),
     "ukfb_destroy": (I, [P]),
+    "ukfb_create_sharded": (I, [I, L, P, I, C.POINTER(P)]),
+    "ukfb_shard_count": (I, [P]),
+    "ukfb_shard": (I, [P, I, C.POINTER(P), C.POINTER(L), C.POINTER(L)]),
+    "ukfb_host_alloc": (I, [C.POINTER(P), C.c_uint64]),
+    "ukfb_host_free": (I, [P]),
+    "ukfb_get_mu_range": (I, [P, I, I, P]),
+    "ukfb_get_mu_range_dev": (I, [P, I, I, P]),
+    "ukfb_get_mu_range_async": (I, [P, I, I, P]),
+    "ukfb_wait_for_stream": (I, [P, P]),
+    "ukfb_stream_wait": (I, [P, P]),
     "ukfb_batch": (L, [P]),
     "ukfb_dof": (I, [P]),
     "ukfb_mu_size": (I, [P]),
@@ -46,6 +56,7 @@ SIGNATURES = {
     "ukfb_predict_time_dev": (I, [P, P, I]),
     "ukfb_update": (I, [P, I, P, P, I, P]),
     "ukfb_update_dev": (I, [P, I, P, P, I, P]),
+    "ukfb_set_measurement_cov": (I, [P, I, P, I]),
     "ukfb_meas_dim": (I, [I]),
     "ukfb_update_mixed": (I, [P, P, P, P]),
     "ukfb_update_mixed_dev": (I, [P, P, P, P]),

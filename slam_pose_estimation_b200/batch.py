@@ -1,10 +1,14 @@
 """UkfBatch -- thin Python driver over the C ABI (include/ukf_batch.h).
 
-One UkfBatch is B independent PoseUKF / OrientationUKF filters on one B200.  Method names
+One UkfBatch is B independent PoseUKF / OrientationUKF filters on one B200, or -- with `devices=[...]` -- split by
+filter index over several B200s of the box behind ONE handle (ukfb_create_sharded).  Method names
 and argument meaning follow the ABI, which in turn follows the reference classes
 (UnscentedKalmanFilter.hpp:27-137, PoseUKF.hpp:32-86, OrientationUKF.hpp:28-48).  Host
 (NumPy) arguments are copied by the library inside the call; `*_dev` methods take device
-pointers (torch CUDA tensors or raw ints) and only enqueue work on the handle's stream.
+pointers (torch CUDA tensors or raw ints) and only enqueue work on the handle's stream: for
+torch tensors the handle's stream is first made to wait for the torch stream that is current
+on the tensor's device (ukfb_wait_for_stream), so that a kernel never reads inputs that torch
+is still writing; outputs of `*_dev` getters are ordered the other way round (ukfb_stream_wait).
 PyTorch is used for device memory only -- all filter arithmetic is in lib/libukfb.so.
 """
 from __future__ import annotations
@@ -56,21 +60,69 @@ def _dev(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _torch_stream_of(*tensors):
+    """the raw cudaStream_t torch has current on the device of the first torch tensor among the arguments (None if
+    there is none: raw device pointers are the caller's own business)"""
+    for t in tensors:
+        if t is not None and not isinstance(t, int):
+            import torch
+
+            return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
 class UkfBatch:
-    def __init__(self, kind: int, B: int, device: int = 0):
+    def __init__(self, kind: int, B: int, device: int = 0, devices=None, _borrowed=None):
+        """devices = [d0, d1, ...]: one handle whose filters are split by index over those devices (contiguous shards,
+        one host worker thread and one set of CUDA streams per device, no inter-device traffic)."""
         self.lib = _capi.load()
-        self.kind, self.B, self.device = int(kind), int(B), int(device)
-        h = C.c_void_p()
-        self._chk(self.lib.ukfb_create(self.kind, self.B, self.device, C.byref(h)))
-        self.h = h
+        self.kind, self.B = int(kind), int(B)
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self.h = _borrowed
+            self.device = self.lib.ukfb_device(self.h)
+        else:
+            h = C.c_void_p()
+            if devices is not None:
+                arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+                self._chk(self.lib.ukfb_create_sharded(self.kind, self.B, arr, len(devices), C.byref(h)))
+                self.device = int(devices[0])
+            else:
+                self.device = int(device)
+                self._chk(self.lib.ukfb_create(self.kind, self.B, self.device, C.byref(h)))
+            self.h = h
+        h = self.h
         self.n = self.lib.ukfb_dof(h)
         self.MU = self.lib.ukfb_mu_size(h)
         self._inflight = []  # host arrays referenced by enqueued *_async calls
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.ukfb_destroy(self.h)
+            if self._owned:
+                self.lib.ukfb_destroy(self.h)
             self.h = None
+
+    def shard_count(self) -> int:
+        return int(self.lib.ukfb_shard_count(self.h))
+
+    def shard(self, i: int):
+        """(UkfBatch over shard i's one-device handle -- owned by this object --, first filter, count): the `_dev`
+        entry points of a sharded handle live here"""
+        sh, first, count = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._chk(self.lib.ukfb_shard(self.h, int(i), C.byref(sh), C.byref(first), C.byref(count)))
+        return UkfBatch(self.kind, count.value, _borrowed=sh), first.value, count.value
+
+    def _after_torch(self, *tensors):
+        """the handle's stream waits for the torch stream that produced these device inputs"""
+        st = _torch_stream_of(*tensors)
+        if st is not None:
+            self._chk(self.lib.ukfb_wait_for_stream(self.h, st))
+
+    def _before_torch(self, *tensors):
+        """the torch stream that will read these device outputs waits for the handle's stream"""
+        st = _torch_stream_of(*tensors)
+        if st is not None:
+            self._chk(self.lib.ukfb_stream_wait(self.h, st))
 
     def __del__(self):
         try:
@@ -106,7 +158,24 @@ class UkfBatch:
                                           sigma.ctypes.data_as(C.c_void_p) if sigma is not None else None))
 
     def get_state_dev(self, d_mu, d_sigma=None):
+        self._after_torch(d_mu, d_sigma)  # torch may still be using the output buffers
         self._chk(self.lib.ukfb_get_state_dev(self.h, _dev(d_mu), _dev(d_sigma)))
+        self._before_torch(d_mu, d_sigma)
+
+    def get_mu_range(self, first: int, count: int, out: np.ndarray | None = None):
+        """entries [first, first + count) of every filter's state, B x count (PoseUKF pose = (0, 7))"""
+        out = np.empty((self.B, count)) if out is None else out
+        self._chk(self.lib.ukfb_get_mu_range(self.h, int(first), int(count), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_mu_range_async(self, first: int, count: int, out: np.ndarray):
+        self._inflight.append((out,))
+        self._chk(self.lib.ukfb_get_mu_range_async(self.h, int(first), int(count), out.ctypes.data_as(C.c_void_p)))
+
+    def get_mu_range_dev(self, first: int, count: int, d_out):
+        self._after_torch(d_out)
+        self._chk(self.lib.ukfb_get_mu_range_dev(self.h, int(first), int(count), _dev(d_out)))
+        self._before_torch(d_out)
 
     def initialize_from_body_states(self, rbs):
         """BodyStateMeasurement::fromRigidBodyState + initializeFilter; rbs: B x 49 (include/ukf_batch.h)"""
@@ -172,6 +241,7 @@ class UkfBatch:
         self._chk(self.lib.ukfb_predict_dt(self.h, pd, per))
 
     def predict_dt_dev(self, d_dt, per_filter: bool):
+        self._after_torch(d_dt)
         self._chk(self.lib.ukfb_predict_dt_dev(self.h, _dev(d_dt), int(per_filter)))
 
     def predict_time(self, ts):
@@ -181,6 +251,7 @@ class UkfBatch:
         self._chk(self.lib.ukfb_predict_time(self.h, pt, per))
 
     def predict_time_dev(self, d_ts, per_filter: bool):
+        self._after_torch(d_ts)
         self._chk(self.lib.ukfb_predict_time_dev(self.h, _dev(d_ts), int(per_filter)))
 
     # ---- measurements -------------------------------------------------------------------------
@@ -193,11 +264,17 @@ class UkfBatch:
         cov, pc = _host(cov, np.float64)
         if mu.size != self.B * m:
             raise ValueError(f"update: mu must be B x {m}")
-        per = 1 if cov.ndim == 3 else 0
+        per = 1 if (cov is not None and cov.ndim == 3) else 0
         mask, pk = _host(mask, np.uint8)
         self._chk(self.lib.ukfb_update(self.h, kind, pm, pc, per, pk))
 
+    def set_measurement_cov(self, kind: int, cov):
+        """keep a covariance for `kind` on the device (m x m or B x m x m); update / step / step_async then take cov=None"""
+        cov, pc = _host(cov, np.float64)
+        self._chk(self.lib.ukfb_set_measurement_cov(self.h, kind, pc, 1 if cov.ndim == 3 else 0))
+
     def update_dev(self, kind: int, d_mu, d_cov, cov_per_filter: bool, d_mask=None):
+        self._after_torch(d_mu, d_cov, d_mask)
         self._chk(self.lib.ukfb_update_dev(self.h, kind, _dev(d_mu), _dev(d_cov), int(cov_per_filter), _dev(d_mask)))
 
     def update_mixed(self, kinds, mu3, cov33):
@@ -209,6 +286,7 @@ class UkfBatch:
         self._chk(self.lib.ukfb_update_mixed(self.h, pk, pm, pc))
 
     def update_mixed_dev(self, d_kinds, d_mu3, d_cov33):
+        self._after_torch(d_kinds, d_mu3, d_cov33)
         self._chk(self.lib.ukfb_update_mixed_dev(self.h, _dev(d_kinds), _dev(d_mu3), _dev(d_cov33)))
 
     def set_acceleration(self, mu, cov=None, mask=None):
@@ -261,6 +339,7 @@ class UkfBatch:
                                                 sigma.ctypes.data_as(C.c_void_p) if sigma is not None else None))
 
     def step_dev(self, d_dt, dt_per_filter: bool, kind: int, d_mu=None, d_cov=None, cov_per_filter: bool = False, d_mask=None):
+        self._after_torch(d_dt, d_mu, d_cov, d_mask)
         self._chk(self.lib.ukfb_step_dev(self.h, _dev(d_dt), int(dt_per_filter), kind, _dev(d_mu), _dev(d_cov),
                                          int(cov_per_filter), _dev(d_mask)))
 
@@ -269,6 +348,7 @@ class UkfBatch:
         kinds_arr, pk = _host(kinds, np.int8)
         if kinds_arr is not None and kinds_arr.size != K:
             raise ValueError("run_dev: kinds must hold K entries")
+        self._after_torch(d_dt, d_mu3, d_cov33, d_imu)
         self._chk(self.lib.ukfb_run_dev(self.h, K, _dev(d_dt), int(dt_per_filter), pk, _dev(d_mu3), _dev(d_cov33),
                                         int(cov_per_filter), _dev(d_imu)))
 
@@ -298,6 +378,7 @@ class UkfBatch:
         self._chk(self.lib.ukfb_run_events_async(self.h, K, pt, pk, pm, pc, 1 if per_event else 0))
 
     def run_events_dev(self, K: int, d_ts, d_kinds, d_mu3, d_cov, per_event: bool):
+        self._after_torch(d_ts, d_kinds, d_mu3, d_cov)
         self._chk(self.lib.ukfb_run_events_dev(self.h, int(K), _dev(d_ts), _dev(d_kinds), _dev(d_mu3), _dev(d_cov),
                                                1 if per_event else 0))
 

@@ -78,6 +78,9 @@ struct ukfb_handle {
     double* ori_params = nullptr; /* B x 5 per-filter (-1/tau_g, -1/tau_a, earth xyz), or null: the scalars above */
     bool tick_kinds_have_orientation = false; /* set by ukfb_run_dev from its host-side kinds */
     double* gyro_mu = nullptr;
+    /* ukfb_set_measurement_cov: a kept covariance per measurement kind (m x m, or B x m x m) for calls that pass cov = NULL */
+    double* meas_cov[UKFB_MEAS_KIND_COUNT] = {};
+    int meas_cov_per_filter[UKFB_MEAS_KIND_COUNT] = {};
     bool initialized = false, first_init = true;
     double min_dt = UKFB_DEFAULT_MIN_DT, max_dt = DBL_MAX;
     double tau_g = INFINITY, tau_a = INFINITY, latitude = 0.0;
@@ -837,6 +840,7 @@ extern "C" int ukfb_destroy(ukfb_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist);
     cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary), cudaFree(h->ori_params);
+    for (int k = 0; k < UKFB_MEAS_KIND_COUNT; ++k) cudaFree(h->meas_cov[k]);
     for (int i = 0; i < 16; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->pipe.made) {
@@ -1324,15 +1328,40 @@ extern "C" int ukfb_update(ukfb_handle* h, int meas_kind, const double* mu, cons
     CHECK_H(h);
     NEED_INIT(h);
     if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_update: measurement kind %d does not belong to this filter kind", meas_kind);
-    if (!mu || !cov) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
+    if (!mu) return fail(UKFB_ERR_INVALID, "ukfb_update: null argument");
+    if (!cov && !h->meas_cov_per_filter[meas_kind]) return fail(UKFB_ERR_INVALID, "ukfb_update: null covariance and none kept by ukfb_set_measurement_cov for kind %d", meas_kind);
     const int m = meas_dim(meas_kind);
-    UKFB_FAN(h, ukfb_update(s_, meas_kind, mu + f_ * m, cov + (cov_per_filter ? f_ * m * m : 0), cov_per_filter, mask ? mask + f_ : nullptr));
+    UKFB_FAN(h, ukfb_update(s_, meas_kind, mu + f_ * m, cov ? cov + (cov_per_filter ? f_ * m * m : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
     const double *d_mu, *d_cov;
     const uint8_t* d_mask;
     int rc = stage_meas(h, 0, m, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
     if (rc) return rc;
+    if (!cov) d_cov = h->meas_cov[meas_kind], cov_per_filter = h->meas_cov_per_filter[meas_kind] == 2;
     rc = ukfb_update_dev(h, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return UKFB_OK;
+}
+
+extern "C" int ukfb_set_measurement_cov(ukfb_handle* h, int meas_kind, const double* cov, int per_filter)
+{
+    CHECK_H(h);
+    if (!kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_set_measurement_cov: measurement kind %d does not belong to this filter kind", meas_kind);
+    if (!cov) return fail(UKFB_ERR_INVALID, "ukfb_set_measurement_cov: null argument");
+    const int m = meas_dim(meas_kind);
+    if (is_sharded(h)) {
+        const int rc = fan_out(h, [&](ukfb_handle* s_, long long f_, long long) { return ukfb_set_measurement_cov(s_, meas_kind, cov + (per_filter ? f_ * m * m : 0), per_filter); });
+        if (rc == UKFB_OK) h->meas_cov_per_filter[meas_kind] = per_filter ? 2 : 1; /* the parent only remembers that one is kept */
+        return rc;
+    }
+    const size_t bytes = sizeof(double) * size_t(per_filter ? h->B : 1) * m * m;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->meas_cov[meas_kind]) CU(cudaFree(h->meas_cov[meas_kind]));
+    h->meas_cov[meas_kind] = nullptr;
+    cudaError_t e = cudaMalloc(&h->meas_cov[meas_kind], bytes);
+    if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "ukfb_set_measurement_cov: %s", cudaGetErrorString(e));
+    h->meas_cov_per_filter[meas_kind] = per_filter ? 2 : 1;
+    CU(cudaMemcpyAsync(h->meas_cov[meas_kind], cov, bytes, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return UKFB_OK;
 }
@@ -1483,11 +1512,12 @@ extern "C" int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, in
     const size_t bd = align256(sizeof(double) * (dt_per_filter ? h->B : 1));
     const bool upd = meas_kind != UKFB_MEAS_NONE;
     if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step: measurement kind %d does not belong to this filter kind", meas_kind);
-    if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step: null measurement");
+    if (upd && !mu) return fail(UKFB_ERR_INVALID, "ukfb_step: null measurement");
+    if (upd && !cov && !h->meas_cov_per_filter[meas_kind]) return fail(UKFB_ERR_INVALID, "ukfb_step: null covariance and none kept by ukfb_set_measurement_cov for kind %d", meas_kind);
     const int m = upd ? meas_dim(meas_kind) : 0;
     UKFB_FAN(h, ukfb_step(s_, dt + (dt_per_filter ? f_ : 0), dt_per_filter, meas_kind, mu ? mu + f_ * m : nullptr,
                           cov ? cov + (cov_per_filter ? f_ * m * m : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
-    int rc = stage_reserve(h, bd + (upd ? meas_bytes(h, m, true, cov_per_filter, mask != nullptr) : 0));
+    int rc = stage_reserve(h, bd + (upd ? meas_bytes(h, m, cov != nullptr, cov_per_filter, mask != nullptr) : 0));
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->stage, dt, sizeof(double) * (dt_per_filter ? h->B : 1), cudaMemcpyHostToDevice, h->stream));
     const double *d_mu = nullptr, *d_cov = nullptr;
@@ -1495,6 +1525,7 @@ extern "C" int ukfb_step(ukfb_handle* h, const double* dt, int dt_per_filter, in
     if (upd) {
         rc = stage_meas(h, bd, m, mu, cov, cov_per_filter, mask, &d_mu, &d_cov, &d_mask, nullptr);
         if (rc) return rc;
+        if (!cov) d_cov = h->meas_cov[meas_kind], cov_per_filter = h->meas_cov_per_filter[meas_kind] == 2;
     }
     rc = ukfb_step_dev(h, reinterpret_cast<const double*>(h->stage), dt_per_filter, meas_kind, d_mu, d_cov, cov_per_filter, d_mask);
     if (rc) return rc;
@@ -1545,7 +1576,8 @@ extern "C" int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filt
     if (!dt) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null dt");
     const bool upd = meas_kind != UKFB_MEAS_NONE;
     if (upd && !kind_ok(h, meas_kind)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: measurement kind %d does not belong to this filter kind", meas_kind);
-    if (upd && (!mu || !cov)) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null measurement");
+    if (upd && !mu) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null measurement");
+    if (upd && !cov && !h->meas_cov_per_filter[meas_kind]) return fail(UKFB_ERR_INVALID, "ukfb_step_async: null covariance and none kept by ukfb_set_measurement_cov for kind %d", meas_kind);
     const int m = upd ? meas_dim(meas_kind) : 0;
     UKFB_FAN(h, ukfb_step_async(s_, dt + (dt_per_filter ? f_ : 0), dt_per_filter, meas_kind, mu ? mu + f_ * m : nullptr,
                                 cov ? cov + (cov_per_filter ? f_ * m * m : 0) : nullptr, cov_per_filter, mask ? mask + f_ : nullptr));
@@ -1554,7 +1586,7 @@ extern "C" int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filt
     const int slot = int(h->pipe.n_in & 1);
     const size_t bd = align256(sizeof(double) * (dt_per_filter ? h->B : 1));
     const size_t bm = upd ? align256(sizeof(double) * h->B * m) : 0;
-    const size_t bc = upd ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0;
+    const size_t bc = (upd && cov) ? align256(sizeof(double) * (cov_per_filter ? h->B : 1) * m * m) : 0;
     const size_t bk = (upd && mask) ? align256(size_t(h->B)) : 0;
     rc = pipe_reserve(h, &h->pipe.in[slot], &h->pipe.in_bytes[slot], bd + bm + bc + bk);
     if (rc) return rc;
@@ -1566,9 +1598,12 @@ extern "C" int ukfb_step_async(ukfb_handle* h, const double* dt, int dt_per_filt
     const uint8_t* d_mask = nullptr;
     if (upd) {
         CU(cudaMemcpyAsync(base + bd, mu, sizeof(double) * h->B * m, cudaMemcpyHostToDevice, si));
-        CU(cudaMemcpyAsync(base + bd + bm, cov, sizeof(double) * (cov_per_filter ? h->B : 1) * m * m, cudaMemcpyHostToDevice, si));
         d_mu = reinterpret_cast<const double*>(base + bd);
-        d_cov = reinterpret_cast<const double*>(base + bd + bm);
+        if (cov) {
+            CU(cudaMemcpyAsync(base + bd + bm, cov, sizeof(double) * (cov_per_filter ? h->B : 1) * m * m, cudaMemcpyHostToDevice, si));
+            d_cov = reinterpret_cast<const double*>(base + bd + bm);
+        } else
+            d_cov = h->meas_cov[meas_kind], cov_per_filter = h->meas_cov_per_filter[meas_kind] == 2;
         if (mask) {
             CU(cudaMemcpyAsync(base + bd + bm + bc, mask, size_t(h->B), cudaMemcpyHostToDevice, si));
             d_mask = reinterpret_cast<const uint8_t*>(base + bd + bm + bc);
