@@ -134,13 +134,25 @@ def make_workload_of(indices, pool: int):
             np.concatenate([p[2] for p in parts], axis=1), np.concatenate([p[3] for p in parts]))
 
 
+def cpu_arm():
+    """which CPU implementation the baseline legs time: oracle/_ref (the reference's own PoseUKF.cpp /
+    UnscentedKalmanFilter.hpp compiled unmodified against oracle/ref_shim, over the restated ukfom / MTK engine) when it
+    was built in the build container, else the oracle port.  Returns (variant, kind, description)."""
+    from oracle import oracle_lib as O
+
+    if os.path.exists(O.REF_LIB):
+        return "ref", "reference", ("oracle/_ref: the reference's own wrapper sources (PoseUKF.cpp, UnscentedKalmanFilter.hpp) compiled "
+                                    "unmodified; ukfom / MTK / Eigen underneath are the oracle's restatement (slam/mtk is not vendored)")
+    return "left", "port", "oracle port (the reference could not be compiled here)"
+
+
 def time_oracle(B: int, steps: int, warmup: int, threads: int | None = None):
-    """the CPU oracle (port of the reference's Eigen/MTK path) on the same workload; returns steps/s, threads"""
+    """the reference's CPU path (cpu_arm) on the same workload, OpenMP over filters; returns steps/s, threads, seconds"""
     from oracle.oracle_lib import OracleBatch
     from slam_pose_estimation_b200 import synthetic as syn
 
     mu, sg, zs, R = make_workload(B, 0, 4)
-    o = OracleBatch(0, B, threads=threads)
+    o = OracleBatch(0, B, variant=cpu_arm()[0], threads=threads)
     o.initialize(mu, sg)
     for k in range(warmup):
         o.step(syn.DT, 8, zs[k % 4], R)
@@ -171,9 +183,8 @@ def parity_sample(applied, indices, mu_gpu, sg_gpu, pool: int):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path.  The reference itself cannot be built here (Rock CMake
-    macros, Eigen, Boost, base-types, slam/mtk absent -- DESIGN.md), so this is the oracle port, OpenMP over
-    filters on all host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU path (cpu_arm: oracle/_ref, else the oracle port), OpenMP over filters on
+    all host cores.  Rank 0 only."""
     if rank != 0:
         return
     B = args.ref_filters
@@ -195,10 +206,10 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C4: PoseUKF Monte-Carlo sweep sharded by filter index; step = predictionStep(1 ms) + "
                                "AngularVelocityMeasurement update (m=3)",
-                   "sample": f"{B} filters of the sweep per step on the host cores (the reference's CPU path: oracle port, "
-                             "OpenMP over filters)", "filters": B},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{B} filters x {args.steps} steps, OpenMP over filters"},
+                   "sample": f"{B} filters of the sweep per step on the host cores ({cpu_arm()[2]}; OpenMP over filters)",
+                   "filters": B},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu_arm()[1],
+                         "sample": f"{B} filters x {args.steps} steps, OpenMP over filters; {cpu_arm()[2]}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -588,9 +599,9 @@ def main():
         v, threads, dt = time_oracle(args.ref_filters, 2, 1, threads=len(all_cpus))  # calibrate, then ~10 s of CPU work
         nsteps = int(min(20000, max(4, 12.0 / (dt / 2))))  # about 12 s of CPU work
         v, threads, dt = time_oracle(args.ref_filters, nsteps, 1, threads=len(all_cpus))
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{args.ref_filters} filters x {nsteps} steps of the same workload, oracle port, "
-                                          f"OpenMP over filters, {dt:.1f} s"}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": cpu_arm()[1],
+                                "sample": f"{args.ref_filters} filters x {nsteps} steps of the same workload, OpenMP over filters, "
+                                          f"{dt:.1f} s; {cpu_arm()[2]}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

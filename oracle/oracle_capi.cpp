@@ -19,6 +19,35 @@
 
 using namespace orc;
 
+/* The filter objects behind the batch.  Default: the oracle's own restatement of the reference classes.  oracle/ref_capi.cpp
+ * defines ORC_CUSTOM_IMPL, adapters over the REFERENCE'S OWN classes (compiled unmodified from /root/reference against
+ * oracle/ref_shim) with the same member functions, and includes this file: the same batch interface then drives them. */
+#ifndef ORC_CUSTOM_IMPL
+typedef PoseFilter<double> PoseImpl;
+typedef OrientationFilter<double> OriImpl;
+namespace ax { /* access to what the reference keeps in protected members / inside ukfom::ukf */
+template <class F> void store_mu(const F& f, double* mu) { f.ukf.mu.store(mu); }
+template <class F> void copy_sigma(const F& f, double* sigma) { std::memcpy(sigma, f.ukf.sigma, sizeof(f.ukf.sigma)); }
+template <class F> void set_q(F& f, int k, double v) { f.process_noise_cov[k] = v; }
+template <class F> void set_dt_bounds(F& f, double lo, double hi) { f.min_time_delta = lo, f.max_time_delta = hi; }
+template <class F> void set_gate(F& f, double d2) { f.ukf.accept_max_d2 = d2; }
+template <class F> bool rejected(const F& f) { return f.ukf.last_update_rejected; }
+template <class F> void set_last_time(F& f, int64_t t) { f.last_measurement_time_us = t; }
+template <class F> int64_t last_time(const F& f) { return f.last_measurement_time_us; }
+template <class F> uint32_t status(const F& f) { return f.ukf.status; }
+template <class F> void clear_status(F& f) { f.ukf.status = 0; }
+template <class F> uint64_t mean_iters(const F& f, int k) { return f.ukf.mean_iters[k]; }
+inline void set_ori_params(OriImpl& f, double tau_g, double tau_a, double latitude)
+{
+    f.gyro_bias_tau = tau_g;
+    f.acc_bias_tau = tau_a;
+    f.earth_rotation[0] = UKFB_EARTHW * std::cos(latitude);
+    f.earth_rotation[1] = 0.;
+    f.earth_rotation[2] = UKFB_EARTHW * std::sin(latitude);
+}
+} /* namespace ax */
+#endif
+
 namespace {
 
 struct Batch {
@@ -27,8 +56,8 @@ struct Batch {
     int n, MU;
     bool initialized = false;
     bool constructed = false; /* filter objects exist */
-    std::vector<std::unique_ptr<PoseFilter<double>>> pose;
-    std::vector<std::unique_ptr<OrientationFilter<double>>> ori;
+    std::vector<std::unique_ptr<PoseImpl>> pose;
+    std::vector<std::unique_ptr<OriImpl>> ori;
     std::vector<uint32_t> status;
     /* parameters applied at construction / kept across re-initialisation */
     std::vector<double> Q; /* n*n or B*n*n */
@@ -47,10 +76,9 @@ void apply_common(Batch* b, F& f, int64_t i)
     const int nn = b->n * b->n;
     if (b->q_set) {
         const double* q = b->Q.data() + (b->q_per_filter ? i * nn : 0);
-        for (int k = 0; k < nn; ++k) f.process_noise_cov[k] = q[k];
+        for (int k = 0; k < nn; ++k) ax::set_q(f, k, q[k]);
     }
-    f.min_time_delta = b->min_dt;
-    f.max_time_delta = b->max_dt;
+    ax::set_dt_bounds(f, b->min_dt, b->max_dt);
 }
 
 template <class Fn>
@@ -109,7 +137,7 @@ int orc_initialize(void* h, const double* mu, const double* sigma)
             PoseState<double> s;
             s.load(mu + i * b->MU);
             if (!b->constructed) {
-                b->pose[i].reset(new PoseFilter<double>(s, sigma + i * nn));
+                b->pose[i].reset(new PoseImpl(s, sigma + i * nn));
                 apply_common(b, *b->pose[i], i);
             } else
                 b->pose[i]->initializeFilter(s, sigma + i * nn);
@@ -117,7 +145,7 @@ int orc_initialize(void* h, const double* mu, const double* sigma)
             OrientationState<double> s;
             s.load(mu + i * b->MU);
             if (!b->constructed) {
-                b->ori[i].reset(new OrientationFilter<double>(s, sigma + i * nn, b->tau_g, b->tau_a, b->latitude));
+                b->ori[i].reset(new OriImpl(s, sigma + i * nn, b->tau_g, b->tau_a, b->latitude));
                 apply_common(b, *b->ori[i], i);
             } else
                 b->ori[i]->initializeFilter(s, sigma + i * nn);
@@ -136,11 +164,11 @@ int orc_get_state(void* h, double* mu, double* sigma)
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < b->B; ++i) {
         if (b->kind == 0) {
-            b->pose[i]->ukf.mu.store(mu + i * b->MU);
-            if (sigma) std::memcpy(sigma + i * nn, b->pose[i]->ukf.sigma, nn * sizeof(double));
+            ax::store_mu(*b->pose[i], mu + i * b->MU);
+            if (sigma) ax::copy_sigma(*b->pose[i], sigma + i * nn);
         } else {
-            b->ori[i]->ukf.mu.store(mu + i * b->MU);
-            if (sigma) std::memcpy(sigma + i * nn, b->ori[i]->ukf.sigma, nn * sizeof(double));
+            ax::store_mu(*b->ori[i], mu + i * b->MU);
+            if (sigma) ax::copy_sigma(*b->ori[i], sigma + i * nn);
         }
     }
     return 0;
@@ -172,9 +200,9 @@ int orc_set_time_bounds(void* h, double min_dt, double max_dt)
     if (b->constructed)
         for (int64_t i = 0; i < b->B; ++i) {
             if (b->kind == 0)
-                b->pose[i]->min_time_delta = min_dt, b->pose[i]->max_time_delta = max_dt;
+                ax::set_dt_bounds(*b->pose[i], min_dt, max_dt);
             else
-                b->ori[i]->min_time_delta = min_dt, b->ori[i]->max_time_delta = max_dt;
+                ax::set_dt_bounds(*b->ori[i], min_dt, max_dt);
         }
     return 0;
 }
@@ -186,9 +214,9 @@ int orc_set_mahalanobis_gate(void* h, double max_d2)
     if (!b->constructed) return -2;
     for (int64_t i = 0; i < b->B; ++i) {
         if (b->kind == 0)
-            b->pose[i]->ukf.accept_max_d2 = max_d2;
+            ax::set_gate(*b->pose[i], max_d2);
         else
-            b->ori[i]->ukf.accept_max_d2 = max_d2;
+            ax::set_gate(*b->ori[i], max_d2);
     }
     return 0;
 }
@@ -199,13 +227,7 @@ int orc_set_orientation_params(void* h, double tau_g, double tau_a, double latit
     if (b->kind != 1) return -1;
     b->tau_g = tau_g, b->tau_a = tau_a, b->latitude = latitude;
     if (b->constructed)
-        for (int64_t i = 0; i < b->B; ++i) {
-            b->ori[i]->gyro_bias_tau = tau_g;
-            b->ori[i]->acc_bias_tau = tau_a;
-            b->ori[i]->earth_rotation[0] = UKFB_EARTHW * std::cos(latitude);
-            b->ori[i]->earth_rotation[1] = 0.;
-            b->ori[i]->earth_rotation[2] = UKFB_EARTHW * std::sin(latitude);
-        }
+        for (int64_t i = 0; i < b->B; ++i) ax::set_ori_params(*b->ori[i], tau_g, tau_a, latitude);
     return 0;
 }
 
@@ -214,13 +236,7 @@ int orc_set_orientation_params_per_filter(void* h, const double* tau_g, const do
     Batch* b = static_cast<Batch*>(h);
     if (b->kind != 1) return -1;
     if (!b->constructed) return -2; /* the oracle's objects exist after the first initialize */
-    for (int64_t i = 0; i < b->B; ++i) {
-        b->ori[i]->gyro_bias_tau = tau_g[i];
-        b->ori[i]->acc_bias_tau = tau_a[i];
-        b->ori[i]->earth_rotation[0] = UKFB_EARTHW * std::cos(latitude[i]);
-        b->ori[i]->earth_rotation[1] = 0.;
-        b->ori[i]->earth_rotation[2] = UKFB_EARTHW * std::sin(latitude[i]);
-    }
+    for (int64_t i = 0; i < b->B; ++i) ax::set_ori_params(*b->ori[i], tau_g[i], tau_a[i], latitude[i]);
     return 0;
 }
 
@@ -231,9 +247,9 @@ int orc_set_last_time(void* h, const int64_t* ts, int per_filter)
     for (int64_t i = 0; i < b->B; ++i) {
         const int64_t t = ts[per_filter ? i : 0];
         if (b->kind == 0)
-            b->pose[i]->last_measurement_time_us = t;
+            ax::set_last_time(*b->pose[i], t);
         else
-            b->ori[i]->last_measurement_time_us = t;
+            ax::set_last_time(*b->ori[i], t);
     }
     return 0;
 }
@@ -243,7 +259,7 @@ int orc_get_last_time(void* h, int64_t* ts)
     Batch* b = static_cast<Batch*>(h);
     if (!b->constructed) return -2;
     for (int64_t i = 0; i < b->B; ++i)
-        ts[i] = b->kind == 0 ? b->pose[i]->last_measurement_time_us : b->ori[i]->last_measurement_time_us;
+        ts[i] = b->kind == 0 ? ax::last_time(*b->pose[i]) : ax::last_time(*b->ori[i]);
     return 0;
 }
 
@@ -297,9 +313,9 @@ int orc_update(void* h, int meas_kind, const double* mu, const double* cov, int 
         const double* zc = cov + (cov_per_filter ? i * m * m : 0);
         guarded(b, i, [&] {
             if (b->kind == 0)
-                { b->pose[i]->integrateMeasurement(meas_kind, zm, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
+                { b->pose[i]->integrateMeasurement(meas_kind, zm, zc); if (ax::rejected(*b->pose[i])) b->status[i] |= 64u; }
             else
-                { b->ori[i]->integrateVelocity(zm, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
+                { b->ori[i]->integrateVelocity(zm, zc); if (ax::rejected(*b->ori[i])) b->status[i] |= 64u; }
         });
     }
     return 0;
@@ -320,9 +336,9 @@ int orc_update_mixed(void* h, const int8_t* kinds, const double* mu3, const doub
             for (int c = 0; c < m; ++c) zc[a * m + c] = cov33[i * 9 + a * 3 + c];
         guarded(b, i, [&] {
             if (b->kind == 0)
-                { b->pose[i]->integrateMeasurement(k, zm, zc); if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
+                { b->pose[i]->integrateMeasurement(k, zm, zc); if (ax::rejected(*b->pose[i])) b->status[i] |= 64u; }
             else
-                { b->ori[i]->integrateVelocity(zm, zc); if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u; }
+                { b->ori[i]->integrateVelocity(zm, zc); if (ax::rejected(*b->ori[i])) b->status[i] |= 64u; }
         });
     }
     return 0;
@@ -407,10 +423,10 @@ int orc_run_events(void* h, int K, const int64_t* ts, const int8_t* kinds, const
                     for (int c = 0; c < m; ++c) zc[a * m + c] = c33[a * 3 + c];
                 if (pose) {
                     b->pose[i]->integrateMeasurement(kind, z, zc);
-                    if (b->pose[i]->ukf.last_update_rejected) b->status[i] |= 64u;
+                    if (ax::rejected(*b->pose[i])) b->status[i] |= 64u;
                 } else {
                     b->ori[i]->integrateVelocity(z, zc);
-                    if (b->ori[i]->ukf.last_update_rejected) b->status[i] |= 64u;
+                    if (ax::rejected(*b->ori[i])) b->status[i] |= 64u;
                 }
             });
         }
@@ -471,7 +487,7 @@ int orc_get_status(void* h, uint32_t* flags)
     Batch* b = static_cast<Batch*>(h);
     for (int64_t i = 0; i < b->B; ++i) {
         uint32_t s = b->status[i];
-        if (b->constructed) s |= b->kind == 0 ? b->pose[i]->ukf.status : b->ori[i]->ukf.status;
+        if (b->constructed) s |= b->kind == 0 ? ax::status(*b->pose[i]) : ax::status(*b->ori[i]);
         flags[i] = s;
     }
     return 0;
@@ -484,9 +500,9 @@ int orc_clear_status(void* h)
         b->status[i] = 0;
         if (b->constructed) {
             if (b->kind == 0)
-                b->pose[i]->ukf.status = 0;
+                ax::clear_status(*b->pose[i]);
             else
-                b->ori[i]->ukf.status = 0;
+                ax::clear_status(*b->ori[i]);
         }
     }
     return 0;
@@ -499,7 +515,7 @@ int orc_get_mean_iter_hist(void* h, uint64_t hist[8])
     if (!b->constructed) return 0;
     for (int64_t i = 0; i < b->B; ++i)
         for (int k = 0; k < 8; ++k)
-            hist[k] += b->kind == 0 ? b->pose[i]->ukf.mean_iters[k] : b->ori[i]->ukf.mean_iters[k];
+            hist[k] += b->kind == 0 ? ax::mean_iters(*b->pose[i], k) : ax::mean_iters(*b->ori[i], k);
     return 0;
 }
 

@@ -23,14 +23,34 @@ def build(quiet: bool = True) -> None:
     subprocess.run(["make", "-C", _DIR], check=True, stdout=subprocess.DEVNULL if quiet else None)
 
 
+REF_LIB = os.path.join(_DIR, "_ref", "libref.so")
+REF_ROOT = "/root/reference"
+
+
+def build_ref(quiet: bool = True) -> bool:
+    """oracle/_ref/libref.so: the reference's own UKF sources compiled unmodified against oracle/ref_shim
+    (oracle/ref_recipe.mk).  Needs /root/reference, which exists in the build container only: elsewhere the file built
+    there is used as it is.  Returns whether the library exists afterwards."""
+    if os.path.isdir(os.path.join(REF_ROOT, "src")):
+        subprocess.run(["make", "-f", os.path.join("oracle", "ref_recipe.mk")], check=True, cwd=os.path.dirname(_DIR),
+                       stdout=subprocess.DEVNULL if quiet else None)
+    return os.path.exists(REF_LIB)
+
+
 def load(variant: str = "left") -> C.CDLL:
-    """variant: 'left' (default SO(3) convention) or 'right' (upstream body-frame)."""
+    """variant: 'left' (default SO(3) convention), 'right' (upstream body-frame) or 'ref' (the reference's own wrapper
+    sources over the oracle's engine, oracle/_ref)."""
     if variant in _LIBS:
         return _LIBS[variant]
-    name = "liboracle.so" if variant == "left" else "liboracle_right.so"
-    path = os.path.join(_DIR, "build", name)
-    if not os.path.exists(path):
-        build()
+    if variant == "ref":
+        if not build_ref():
+            raise RuntimeError("oracle/_ref/libref.so is missing and /root/reference is not here to build it")
+        path = REF_LIB
+    else:
+        name = "liboracle.so" if variant == "left" else "liboracle_right.so"
+        path = os.path.join(_DIR, "build", name)
+        if not os.path.exists(path):
+            build()
     lib = C.CDLL(path)
     lib.orc_create.restype = C.c_void_p
     lib.orc_create.argtypes = [C.c_int, C.c_int64]

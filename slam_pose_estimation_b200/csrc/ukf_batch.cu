@@ -22,6 +22,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 
 #include "ukf_device.cuh"
 #include "ukf_thread.cuh"
@@ -515,16 +516,19 @@ static const EnvKnobs& knobs()
     return k;
 }
 
-/* cudaFuncSetAttribute is per (function, device): remembered per device under a lock (cold: literal / warp kernels) */
+/* cudaFuncSetAttribute is per (function, device): remembered under a lock, keyed by the kernel's address (all step
+ * kernels share one function-pointer type, so a per-type static would be shared between them) */
 static std::mutex g_attr_mu;
 template <class K>
 static cudaError_t ensure_smem_attr(K kernel, int device, size_t smem)
 {
-    static bool done[64] = {}; /* one array per kernel instantiation */
+    static std::vector<std::pair<const void*, int>> done;
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), device);
     std::lock_guard<std::mutex> lock(g_attr_mu);
-    if (done[device & 63]) return cudaSuccess;
+    for (const auto& d : done)
+        if (d == key) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e == cudaSuccess) done[device & 63] = true;
+    if (e == cudaSuccess) done.push_back(key);
     return e;
 }
 

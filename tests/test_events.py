@@ -254,3 +254,67 @@ def test_gpu_event_queue_streaming_calls():
         b.run_events(t, k, m, tab)
         assert np.array_equal(outs[i], b.get_state()[0])
     assert np.array_equal(a.get_state()[1], b.get_state()[1])
+
+
+def _gps_fixes_through_the_projection(mu3, kinds, tmp_path):
+    """XYMeasurement samples as the reference's callers make them: the GPS fix is a (lat, lon) pair that
+    GeographicProjection::worldToNav (GeographicProjection.cpp:29-37) turns into nav-plane x, y.  The synthetic stream
+    holds noisy nav-plane positions; they become GPS fixes through navToWorld (:39-44) and come back through worldToNav,
+    the host-side feeder path (the C++ mirror under include/pose_estimation_b200/)."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libgeo.so")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "geo_capi.cpp"), "-o", so], check=True)
+    geo = C.CDLL(so)
+    sel = kinds == 1
+    x, y = np.ascontiguousarray(mu3[sel][:, 0]), np.ascontiguousarray(mu3[sel][:, 1])
+    n = x.size
+    lat, lon, x2, y2 = np.empty(n), np.empty(n), np.empty(n), np.empty(n)
+    pd = lambda a: a.ctypes.data_as(C.c_void_p)
+    lat0, lon0 = C.c_double(syn.LATITUDE_BREMEN), C.c_double(0.154595663)
+    assert geo.geo_nav_to_world(lat0, lon0, C.c_long(n), pd(x), pd(y), pd(lat), pd(lon)) == 0
+    assert geo.geo_world_to_nav(lat0, lon0, C.c_long(n), pd(lat), pd(lon), pd(x2), pd(y2)) == 0
+    assert np.abs(x2 - x).max() < 1e-6 and np.abs(y2 - y).max() < 1e-6 and n > 0  # the projection round trip
+    out = mu3.copy()
+    xy = out[sel]
+    xy[:, 0], xy[:, 1] = x2, y2
+    out[sel] = xy
+    return out, n
+
+
+@pytest.mark.gpu
+def test_gpu_10k_ticks_of_the_mixed_imu_dvl_gps_stream(tmp_path):
+    """north star: 1e-9 after 10 000 steps on the asynchronous IMU / DVL / GPS stream (BASELINE config 5).  64 PoseUKF
+    filters, 10 000 IMU ticks at 1 kHz (AngularVelocityMeasurement, PoseUKF.cpp:168-173), DVL at 10 Hz
+    (VelocityMeasurement, :140-145) and GPS at 1 Hz (XYMeasurement, :119-124, coordinates through the GeographicProjection
+    mirror), per-filter phases, queue windows of 337 slots through ukfb_run_events_async; the oracle runs the reference's
+    callback loop over the same queues."""
+    import torch
+    from slam_pose_estimation_b200 import UkfBatch
+
+    B, ticks, W = 64, 10_000, 337
+    ts, kinds, mu3 = syn.pose_c5_events(B, 1, ticks)
+    mu3, n_gps = _gps_fixes_through_the_projection(mu3, kinds, tmp_path)
+    K = ts.shape[0]
+    assert (kinds == 8).sum() == B * ticks and (kinds == 4).sum() >= B * (ticks // 100 - 1) and n_gps >= B * (ticks // 1000 - 1)
+    tab = syn.sensor_cov_table()
+    g, o = P.make_pose(UkfBatch, B), P.make_pose(OracleBatch, B)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    tabp = pin(tab)
+    keep = []
+    for lo in range(0, K, W):
+        part = (pin(ts[lo:lo + W]), pin(kinds[lo:lo + W]), pin(mu3[lo:lo + W]))
+        keep.append(part)
+        g.run_events_async(*part, tabp)
+    g.synchronize()
+    o.run_events(ts, kinds, mu3, tab)
+    em, es = P.assert_parity(0, g.get_state(), o.get_state(), tol=1e-9, what="10 000 ticks of the mixed stream")
+    assert np.array_equal(g.get_status(), o.get_status()) and not g.get_status().any()
+    assert np.array_equal(g.get_last_time(), o.get_last_time())
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+    assert P.spd_ok(g.get_state()[1])
+    print(f"10k mixed stream: mu err {em:.2e}, sigma err {es:.2e}, {K} slots, {n_gps} GPS fixes")
