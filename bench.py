@@ -378,6 +378,8 @@ def main():
     loc = (np.arange(S) * (B // S)).astype(np.int64)
     d_mu = torch.empty((B, 13), dtype=torch.float64, device=dev)
     d_sg = torch.empty((B, 12, 12), dtype=torch.float64, device=dev)
+    if world > 1:  # NCCL sets its gather channels up on first use: not part of the transfer being timed
+        gather_estimates(torch.zeros((world, 13), dtype=torch.float64, device=dev)[rank:rank + 1], world)
     barrier()
     t0 = time.perf_counter()
     f.get_state_dev(d_mu, d_sg)
