@@ -45,6 +45,27 @@ namespace ukfb {
 
 #define UKFB_PS(e) sm[(e) * TILE + lane]
 
+/* tuning knobs of the sigma-point loops (column pairs in flight per iteration) and of the register budget; the defaults
+ * are what measured best on B200 (profiles/r02_kernel_experiments.txt) */
+#ifndef UKFB_PF_MEAN_UNROLL
+#define UKFB_PF_MEAN_UNROLL 1
+#endif
+#ifndef UKFB_PF_COV_UNROLL
+#define UKFB_PF_COV_UNROLL 1
+#endif
+#ifndef UKFB_PF_MIN_BLOCKS
+#define UKFB_PF_MIN_BLOCKS 2 /* x 128 threads: 255 registers per thread */
+#endif
+#ifndef UKFB_PF_MAX_THREADS
+#define UKFB_PF_MAX_THREADS (4 * TILE)
+#endif
+#define UKFB_PRAGMA_(x) _Pragma(#x)
+#ifdef UKFB_SIMT_EMU
+#define UKFB_LOOP_UNROLL(n)
+#else
+#define UKFB_LOOP_UNROLL(n) UKFB_PRAGMA_(unroll n)
+#endif
+
 
 /* shared-memory slots (doubles per lane).  The factor is stored as two square blocks with explicit zeros above the
  * diagonal so that the column loops need no triangular index tests:
@@ -118,6 +139,107 @@ UKFB_D void pf_matvec(const double* Rm, const double* v, double* out)
     out[2] = Rm[6] * v[0] + Rm[7] * v[1] + Rm[8] * v[2];
 }
 
+/* ---- two sigma points at a time -----------------------------------------------------------------------------------
+ * A dependent FP64 instruction can issue 15 cycles after its producer on B200 while the pipe accepts one warp
+ * instruction every 2 cycles (tools/microbench.cu, profiles/r02d_microbench.txt): a scheduler needs ~8 independent FP64
+ * instructions in flight, and with the two resident warps per scheduler that 255 registers allow each warp has to bring
+ * about four.  The +/- points of a sigma-point pair are independent, but written one after the other they are also
+ * SCHEDULED one after the other (ptxas keeps the source order of equal-priority chains).  D2 carries both points through
+ * the same expressions, so that every source line emits the two points' instructions next to each other and a chain's
+ * next instruction finds twice as many independent ones in between. */
+struct D2 {
+    double a, b;
+    UKFB_D D2() {}
+    UKFB_D explicit D2(double x) : a(x), b(x) {}
+    UKFB_D D2(double x, double y) : a(x), b(y) {}
+};
+UKFB_D D2 operator+(D2 x, D2 y) { return D2(x.a + y.a, x.b + y.b); }
+UKFB_D D2 operator-(D2 x, D2 y) { return D2(x.a - y.a, x.b - y.b); }
+UKFB_D D2 operator*(D2 x, D2 y) { return D2(x.a * y.a, x.b * y.b); }
+UKFB_D D2 operator-(D2 x) { return D2(-x.a, -x.b); }
+UKFB_D D2 operator+(D2 x, double y) { return D2(x.a + y, x.b + y); }
+UKFB_D D2 operator-(D2 x, double y) { return D2(x.a - y, x.b - y); }
+UKFB_D D2 operator*(D2 x, double y) { return D2(x.a * y, x.b * y); }
+UKFB_D D2 operator*(double x, D2 y) { return D2(x * y.a, x * y.b); }
+UKFB_D D2 operator+(double x, D2 y) { return D2(x + y.a, x + y.b); }
+UKFB_D double tfma(double x, double y, double z) { return fma(x, y, z); }
+UKFB_D D2 tfma(D2 x, D2 y, D2 z) { return D2(fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)); }
+UKFB_D D2 tfma(double x, D2 y, D2 z) { return D2(fma(x, y.a, z.a), fma(x, y.b, z.b)); }
+UKFB_D D2 tfma(D2 x, double y, D2 z) { return D2(fma(x.a, y, z.a), fma(x.b, y, z.b)); }
+UKFB_D D2 tfma(D2 x, D2 y, double z) { return D2(fma(x.a, y.a, z), fma(x.b, y.b, z)); }
+UKFB_D D2 tfma(double x, D2 y, double z) { return D2(fma(x, y.a, z), fma(x, y.b, z)); }
+UKFB_D D2 tfma(D2 x, double y, double z) { return D2(fma(x.a, y, z), fma(x.b, y, z)); }
+UKFB_D D2 tfma(double x, double y, D2 z) { return D2(fma(x, y, z.a), fma(x, y, z.b)); }
+UKFB_D bool all_le(D2 x, double lim) { return (x.a <= lim) && (x.b <= lim); }
+UKFB_D bool all_ge(D2 x, double lim) { return (x.a >= lim) && (x.b >= lim); }
+#define UKFB_TPOLY5(C, v, v2) tfma(tfma(C[5], v, C[4]), (v2) * (v2), tfma(tfma(C[3], v, C[2]), v2, tfma(C[1], v, C[0])))
+
+/* pf_exp / pf_log / pf_rotate and the quaternion products of so3.cuh, the same expressions, on a pair */
+UKFB_D void pf_exp(const D2* v, double scale, D2* q, bool& slow)
+{
+    const double half = scale * 0.5;
+    const D2 norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const D2 x2 = (half * half) * norm2;
+    slow = slow || !all_le(x2, SO3_EXP5_FAST_X2);
+    const D2 x4 = x2 * x2;
+    const D2 c = UKFB_TPOLY5(SO3_COS5_C, x2, x4);
+    const D2 mult = UKFB_TPOLY5(SO3_SINC5_C, x2, x4) * half;
+    q[0] = mult * v[0];
+    q[1] = mult * v[1];
+    q[2] = mult * v[2];
+    q[3] = c;
+}
+
+UKFB_D D2 two_asin_over_s_poly(D2 y)
+{
+    const D2 y2 = y * y, y4 = y2 * y2;
+    const D2 p01 = tfma(SO3_ASIN_C[1], y, SO3_ASIN_C[0]), p23 = tfma(SO3_ASIN_C[3], y, SO3_ASIN_C[2]);
+    const D2 p45 = tfma(SO3_ASIN_C[5], y, SO3_ASIN_C[4]), p67 = tfma(SO3_ASIN_C[7], y, SO3_ASIN_C[6]);
+    const D2 q0 = tfma(p23, y2, p01), q1 = tfma(p67, y2, p45);
+    return tfma(tfma(SO3_ASIN_C[8], y4, q1), y4, q0);
+}
+
+UKFB_D void pf_log(const D2* q, D2* out, bool& slow)
+{
+    const D2 nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const D2 w = q[3];
+    const D2 d = tfma(w, w, nv2) - 1.0;
+    slow = slow || !all_ge(w, SO3_LOG_FAST_W);
+    const D2 s0 = two_asin_over_s_poly(tfma(-nv2, d, nv2));
+    const D2 s = tfma(s0, -0.5 * d, s0);
+    out[0] = s * q[0];
+    out[1] = s * q[1];
+    out[2] = s * q[2];
+}
+
+UKFB_D void pf_rotate(const D2* q, const D2* v, D2* out)
+{
+    const D2 ux = tfma(q[1], v[2], -(q[2] * v[1]));
+    const D2 uy = tfma(q[2], v[0], -(q[0] * v[2]));
+    const D2 uz = tfma(q[0], v[1], -(q[1] * v[0]));
+    out[0] = tfma(2.0, tfma(q[3], ux, tfma(q[1], uz, -(q[2] * uy))), v[0]);
+    out[1] = tfma(2.0, tfma(q[3], uy, tfma(q[2], ux, -(q[0] * uz))), v[1]);
+    out[2] = tfma(2.0, tfma(q[3], uz, tfma(q[0], uy, -(q[1] * ux))), v[2]);
+}
+
+/* r = a * b and r = a * conj(b); B is D2 or double (a factor both points share) */
+template <class B>
+UKFB_D void quat_mul(const D2* a, const B* b, D2* r)
+{
+    r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+template <class B>
+UKFB_D void quat_mul_conj(const D2* a, const B* b, D2* r)
+{
+    r[3] = a[3] * b[3] + a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    r[0] = -a[3] * b[0] + a[0] * b[3] - a[1] * b[2] + a[2] * b[1];
+    r[1] = -a[3] * b[1] + a[1] * b[3] - a[2] * b[0] + a[0] * b[2];
+    r[2] = -a[3] * b[2] + a[2] * b[3] - a[0] * b[1] + a[1] * b[0];
+}
+
 /* ---- Cholesky of a packed lower 12x12 in registers, first NCOL columns (LAPACK dpotf2('L') order) ------------- */
 template <int NCOL>
 UKFB_D bool pf_cholesky(double* a)
@@ -175,18 +297,18 @@ UKFB_D void prefetch_next_wave(const StepParams& p, long long tile, int lane)
     if (p.do_predict && !p.time_mode && p.dt && o < TILE * 8 * p.dt_stride) prefetch_l2(reinterpret_cast<const char*>(p.dt + nb * p.dt_stride) + o);
 }
 
-/* one propagated sigma point: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
-UKFB_D void pf_point(const double* qs, const double* ps, const double* vs, const double* ws, double dt, const double* ref_p,
-                     const double* ref_q, double* d, bool& slow)
+/* a pair of propagated sigma points: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
+UKFB_D void pf_point2(const D2* qs, const D2* ps, const D2* vs, const D2* ws, double dt, const double* ref_p, const double* ref_q,
+                      D2* d, bool& slow)
 {
-    double rv[3], e[4], qn[4], r[4];
+    D2 rv[3], e[4], qn[4], r[4];
     pf_rotate(qs, vs, rv);
     /* q [+] (q w) dt = exp((q w) dt) q = q exp(w dt) q^-1 q = q exp(w dt) for a unit q: w needs no rotation */
     pf_exp(ws, dt, e, slow);
     quat_mul(qs, e, qn);
-    d[0] = fma(dt, rv[0], ps[0]) - ref_p[0];
-    d[1] = fma(dt, rv[1], ps[1]) - ref_p[1];
-    d[2] = fma(dt, rv[2], ps[2]) - ref_p[2];
+    d[0] = tfma(dt, rv[0], ps[0]) - ref_p[0];
+    d[1] = tfma(dt, rv[1], ps[1]) - ref_p[1];
+    d[2] = tfma(dt, rv[2], ps[2]) - ref_p[2];
     quat_mul_conj(qn, ref_q, r);
     pf_log(r, d + 3, slow);
 }
@@ -205,20 +327,15 @@ UKFB_D void pf_pair_a(const double* sm, int lane, int j, const PoseMu& m, const 
     const double t1 = e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
     const double t2 = e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
     const double t3 = -(e[0] * q[0] + e[1] * q[1] + e[2] * q[2]);
-    {
-        const double qs[4] = {fma(e[3], q[0], t0), fma(e[3], q[1], t1), fma(e[3], q[2], t2), fma(e[3], q[3], t3)};
-        const double ps[3] = {m.p[0] + L[0], m.p[1] + L[1], m.p[2] + L[2]};
-        const double vs[3] = {vm[0] + L[6], vm[1] + L[7], vm[2] + L[8]};
-        const double ws[3] = {m.w[0] + L[9], m.w[1] + L[10], m.w[2] + L[11]};
-        pf_point(qs, ps, vs, ws, dt, ref_p, ref_q, dpl, slow);
-    }
-    {
-        const double qs[4] = {fma(e[3], q[0], -t0), fma(e[3], q[1], -t1), fma(e[3], q[2], -t2), fma(e[3], q[3], -t3)};
-        const double ps[3] = {m.p[0] - L[0], m.p[1] - L[1], m.p[2] - L[2]};
-        const double vs[3] = {vm[0] - L[6], vm[1] - L[7], vm[2] - L[8]};
-        const double ws[3] = {m.w[0] - L[9], m.w[1] - L[10], m.w[2] - L[11]};
-        pf_point(qs, ps, vs, ws, dt, ref_p, ref_q, dmi, slow);
-    }
+    const D2 qs[4] = {D2(fma(e[3], q[0], t0), fma(e[3], q[0], -t0)), D2(fma(e[3], q[1], t1), fma(e[3], q[1], -t1)),
+                      D2(fma(e[3], q[2], t2), fma(e[3], q[2], -t2)), D2(fma(e[3], q[3], t3), fma(e[3], q[3], -t3))};
+    const D2 ps[3] = {D2(m.p[0] + L[0], m.p[0] - L[0]), D2(m.p[1] + L[1], m.p[1] - L[1]), D2(m.p[2] + L[2], m.p[2] - L[2])};
+    const D2 vs[3] = {D2(vm[0] + L[6], vm[0] - L[6]), D2(vm[1] + L[7], vm[1] - L[7]), D2(vm[2] + L[8], vm[2] - L[8])};
+    const D2 ws[3] = {D2(m.w[0] + L[9], m.w[0] - L[9]), D2(m.w[1] + L[10], m.w[1] - L[10]), D2(m.w[2] + L[11], m.w[2] - L[11])};
+    D2 d[6];
+    pf_point2(qs, ps, vs, ws, dt, ref_p, ref_q, d, slow);
+    UKFB_UNROLL
+    for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
 }
 
 /* the +/- sigma points of a column j >= 6: position and orientation unperturbed.
@@ -233,20 +350,13 @@ UKFB_D void pf_pair_b(const double* sm, int lane, int j, const double* Rm, const
     pf_matvec(Rm, L + 3, u);
     pf_matvec(Rm, L, rv);
     wv[0] = dt * rv[0], wv[1] = dt * rv[1], wv[2] = dt * rv[2];
-    {
-        const double rw[3] = {rw0[0] + u[0], rw0[1] + u[1], rw0[2] + u[2]};
-        double e[4], r[4];
-        pf_exp(rw, dt, e, slow);
-        quat_mul(e, c, r);
-        pf_log(r, dopl, slow);
-    }
-    {
-        const double rw[3] = {rw0[0] - u[0], rw0[1] - u[1], rw0[2] - u[2]};
-        double e[4], r[4];
-        pf_exp(rw, dt, e, slow);
-        quat_mul(e, c, r);
-        pf_log(r, domi, slow);
-    }
+    const D2 rw[3] = {D2(rw0[0] + u[0], rw0[0] - u[0]), D2(rw0[1] + u[1], rw0[1] - u[1]), D2(rw0[2] + u[2], rw0[2] - u[2])};
+    D2 e[4], r[4], d[3];
+    pf_exp(rw, dt, e, slow);
+    quat_mul(e, c, r);
+    pf_log(r, d, slow);
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) dopl[i] = d[i].a, domi[i] = d[i].b;
 }
 
 /* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
@@ -408,7 +518,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         /* X0 and the 12 points of columns 6..11 deviate by d0 in position (the +- offsets cancel) */
         md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
         md[3] = d0[3], md[4] = d0[4], md[5] = d0[5];
-        UKFB_NOUNROLL
+        UKFB_LOOP_UNROLL(UKFB_PF_MEAN_UNROLL)
         for (int j = 0; j < 6; ++j) {
             double L[12], dpl[6], dmi[6];
             pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
@@ -417,7 +527,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         }
         double c[4];
         quat_mul_conj(m.q, ref_q, c);
-        UKFB_NOUNROLL
+        UKFB_LOOP_UNROLL(UKFB_PF_MEAN_UNROLL)
         for (int j = 6; j < 12; ++j) {
             double L[6], dopl[3], domi[3], wv[3];
             pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
@@ -446,7 +556,12 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
     }
     if (slow) return false;
 
-    /* ---- covariance: C = position/orientation block, X = cross block (rows 6..11 x columns 0..5) */
+    /* ---- covariance: C = position/orientation block, X = cross block (rows 6..11 x columns 0..5).
+     * X = sum_j L[6:12, j] (d+_j - d-_j)^T is NOT accumulated point by point: 36 accumulators next to the 21 of C and the
+     * ~46 doubles of per-filter context pushed the loops over the register file (spills reloaded on every column).  The
+     * differences d+_j - d-_j of columns 0..5 go to the six slots L[0:6, j] of the column they came from (consumed once the
+     * column's sigma points exist), the columns 6..11 accumulate only their orientation part (18 values; their position
+     * part is the closed form 2 dt R L[6:9, j]), and X is formed after the loops from the factor rows still in place. */
     double C[21], X[36];
     {
         double d0[6], r[4];
@@ -458,9 +573,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
             UKFB_UNROLL
             for (int k = 0; k <= i; ++k) C[tri(i, k)] = d0[i] * d0[k];
         }
-        UKFB_UNROLL
-        for (int i = 0; i < 36; ++i) X[i] = 0.0;
-        UKFB_NOUNROLL
+        UKFB_LOOP_UNROLL(UKFB_PF_COV_UNROLL)
         for (int j = 0; j < 6; ++j) {
             double L[12], dpl[6], dmi[6];
             pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
@@ -470,15 +583,14 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
                 for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
             }
             UKFB_UNROLL
-            for (int k = 0; k < 6; ++k) {
-                const double dd = dpl[k] - dmi[k];
-                UKFB_UNROLL
-                for (int i = 0; i < 6; ++i) X[i * 6 + k] = fma(L[6 + i], dd, X[i * 6 + k]);
-            }
+            for (int k = 0; k < 6; ++k) UKFB_PS(PF_LA + j * 12 + k) = dpl[k] - dmi[k];
         }
+        double Xb[18]; /* columns 6..11: sum_j L[6:12, j] (do+_j - do-_j)^T, the orientation part of their differences */
+        UKFB_UNROLL
+        for (int i = 0; i < 18; ++i) Xb[i] = 0.0;
         double c[4];
         quat_mul_conj(m.q, ref_q, c);
-        UKFB_NOUNROLL
+        UKFB_LOOP_UNROLL(UKFB_PF_COV_UNROLL)
         for (int j = 6; j < 12; ++j) {
             double L[6], dpl[6], dmi[6], wv[3];
             pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dpl + 3, dmi + 3, wv, slow);
@@ -490,14 +602,45 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
                 for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
             }
             UKFB_UNROLL
-            for (int k = 0; k < 6; ++k) {
-                const double dd = k < 3 ? 2.0 * wv[k] : dpl[k] - dmi[k];
+            for (int k = 0; k < 3; ++k) {
+                const double dd = dpl[3 + k] - dmi[3 + k];
                 UKFB_UNROLL
-                for (int i = 0; i < 6; ++i) X[i * 6 + k] = fma(L[i], dd, X[i * 6 + k]);
+                for (int i = 0; i < 6; ++i) Xb[i * 3 + k] = fma(L[i], dd, Xb[i * 3 + k]);
+            }
+        }
+        if (slow) return false;
+        /* X, after the loops */
+        UKFB_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) X[i * 6 + k] = 0.0, X[i * 6 + 3 + k] = Xb[i * 3 + k];
+        }
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) { /* columns 0..5: the stored differences against rows 6..11 of the column */
+            double dd[6];
+            UKFB_UNROLL
+            for (int k = 0; k < 6; ++k) dd[k] = UKFB_PS(PF_LA + j * 12 + k);
+            UKFB_UNROLL
+            for (int i = 0; i < 6; ++i) {
+                const double l = UKFB_PS(PF_LA + j * 12 + 6 + i);
+                UKFB_UNROLL
+                for (int k = 0; k < 6; ++k) X[i * 6 + k] = fma(l, dd[k], X[i * 6 + k]);
+            }
+        }
+        UKFB_UNROLL
+        for (int j = 6; j < 9; ++j) { /* columns 6..8: position differences 2 (R L[6:9, j]) dt; columns 9..11 have L[6:9, j] = 0 */
+            double Lc[6], rv[3];
+            UKFB_UNROLL
+            for (int i = 0; i < 6; ++i) Lc[i] = i >= j - 6 ? UKFB_PS(PF_LB + (j - 6) * 6 + i) : 0.0;
+            pf_matvec(Rm, Lc, rv);
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                const double dd = 2.0 * (dt * rv[k]);
+                UKFB_UNROLL
+                for (int i = j - 6; i < 6; ++i) X[i * 6 + k] = fma(Lc[i], dd, X[i * 6 + k]);
             }
         }
     }
-    if (slow) return false;
 
     /* ---- new covariance = 1/2 C + process noise (PoseUKF.cpp:182-191), committed to the record.  qv(i, k) = Q[i][k], i >= k:
      * a load, or for a broadcast diagonal Q (the reference's default and the usual configuration) a load on the diagonal
@@ -658,15 +801,15 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
             UKFB_NOUNROLL
             for (int j = 0; j < 6; ++j) {
-                double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
+                D2 e[4], r2[4], d[3]; /* exp(L_ori[:, j]) and its conjugate, side by side */
                 UKFB_UNROLL
-                for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
-                en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
-                quat_mul(e, c, rp);
-                quat_mul(en, c, rn);
-                pf_log(rp, dp, slow);
-                pf_log(rn, dn, slow);
-                md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
+                for (int i = 0; i < 4; ++i) {
+                    const double x = UKFB_PS(PF_E + 4 * j + i);
+                    e[i] = D2(x, i < 3 ? -x : x);
+                }
+                quat_mul(e, c, r2);
+                pf_log(r2, d, slow);
+                md[0] += d[0].a + d[0].b, md[1] += d[1].a + d[1].b, md[2] += d[2].a + d[2].b;
             }
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) md[i] = div_ns<PoseF::NS>(md[i]);
@@ -694,19 +837,19 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             }
             UKFB_NOUNROLL
             for (int j = 0; j < 6; ++j) {
-                double e[4], en[4], rp[4], rn[4], dp[3], dn[3];
+                D2 e[4], r2[4], d[3];
                 UKFB_UNROLL
-                for (int i = 0; i < 4; ++i) e[i] = UKFB_PS(PF_E + 4 * j + i);
-                en[0] = -e[0], en[1] = -e[1], en[2] = -e[2], en[3] = e[3];
-                quat_mul(e, c, rp);
-                quat_mul(en, c, rn);
-                pf_log(rp, dp, slow);
-                pf_log(rn, dn, slow);
+                for (int i = 0; i < 4; ++i) {
+                    const double x = UKFB_PS(PF_E + 4 * j + i);
+                    e[i] = D2(x, i < 3 ? -x : x);
+                }
+                quat_mul(e, c, r2);
+                pf_log(r2, d, slow);
                 UKFB_UNROLL
                 for (int r = 0; r < 3; ++r) {
                     UKFB_UNROLL
-                    for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = fma(dp[r], dp[cc], fma(dn[r], dn[cc], S[r * 3 + cc]));
-                    UKFB_PS(PF_E + 4 * j + r) = dp[r] - dn[r];
+                    for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = fma(d[r].a, d[cc].a, fma(d[r].b, d[cc].b, S[r * 3 + cc]));
+                    UKFB_PS(PF_E + 4 * j + r) = d[r].a - d[r].b;
                 }
             }
             double r4[4];
@@ -844,20 +987,16 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
         md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
         UKFB_NOUNROLL
         for (int j = 0; j < 6; ++j) {
-            double vp[3], vn[3], ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
+            D2 v[3], e[4], r2[4], d[3]; /* the + and - point of the column, side by side */
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) {
                 const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
-                vp[i] = delta[3 + i] + l;
-                vn[i] = delta[3 + i] - l;
+                v[i] = D2(delta[3 + i] + l, delta[3 + i] - l);
             }
-            pf_exp(vp, 1.0, ep, slow);
-            pf_exp(vn, 1.0, en, slow);
-            quat_mul(ep, c, rp);
-            quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
-            md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
+            pf_exp(v, 1.0, e, slow);
+            quat_mul(e, c, r2);
+            pf_log(r2, d, slow);
+            md[0] += d[0].a + d[0].b, md[1] += d[1].a + d[1].b, md[2] += d[2].a + d[2].b;
         }
         double n2 = 0.0;
         UKFB_UNROLL
@@ -890,34 +1029,41 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
             UKFB_UNROLL
             for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = 13.0 * d0[i] * d0[k];
         }
-        UKFB_UNROLL
-        for (int i = 0; i < 27; ++i) Xc[i] = 0.0;
+        /* the cross block is formed after the loop (as X in the predict): the differences dp - dn of column j go to the slots
+         * L[3:6, j] the column's two points were just generated from */
         UKFB_NOUNROLL
         for (int j = 0; j < 6; ++j) {
-            double L[12], vp[3], vn[3], ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
-            UKFB_UNROLL
-            for (int i = 0; i < 12; ++i) L[i] = UKFB_PS(PF_LA + j * 12 + i);
+            D2 v[3], e[4], r2[4], d[3];
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) {
-                vp[i] = delta[3 + i] + L[3 + i];
-                vn[i] = delta[3 + i] - L[3 + i];
+                const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
+                v[i] = D2(delta[3 + i] + l, delta[3 + i] - l);
             }
-            pf_exp(vp, 1.0, ep, slow);
-            pf_exp(vn, 1.0, en, slow);
-            quat_mul(ep, c, rp);
-            quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
+            pf_exp(v, 1.0, e, slow);
+            quat_mul(e, c, r2);
+            pf_log(r2, d, slow);
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) {
                 UKFB_UNROLL
-                for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = fma(dp[i], dp[k], fma(dn[i], dn[k], Coo[tri(i, k)]));
+                for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = fma(d[i].a, d[k].a, fma(d[i].b, d[k].b, Coo[tri(i, k)]));
             }
             UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) {
-                const double dd = dp[k] - dn[k];
+            for (int k = 0; k < 3; ++k) UKFB_PS(PF_LA + j * 12 + 3 + k) = d[k].a - d[k].b;
+        }
+        UKFB_UNROLL
+        for (int i = 0; i < 27; ++i) Xc[i] = 0.0;
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) {
+            double dd[3];
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) dd[k] = UKFB_PS(PF_LA + j * 12 + 3 + k);
+            UKFB_UNROLL
+            for (int t = 0; t < 9; ++t) {
+                const int row = t < 3 ? t : t + 3;
+                if (row < j) continue; /* L is lower triangular */
+                const double l = UKFB_PS(PF_LA + j * 12 + row);
                 UKFB_UNROLL
-                for (int t = 0; t < 9; ++t) Xc[t * 3 + k] = fma(L[t < 3 ? t : t + 3], dd, Xc[t * 3 + k]);
+                for (int k = 0; k < 3; ++k) Xc[t * 3 + k] = fma(l, dd[k], Xc[t * 3 + k]);
             }
         }
     }
@@ -979,7 +1125,7 @@ UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const
  * is compiled into the slow-path call; the larger callee costs the hot path about 3 % (register allocation around the
  * call), which is why there are two instances. */
 template <bool WITH_ORI>
-UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
+UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef PoseF F;
     UKFB_SMEM_DECL
