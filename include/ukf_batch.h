@@ -328,11 +328,13 @@ int64_t ukfb_launch_count(const ukfb_handle* h);
 /* peak of an unrolled independent-DFMA microkernel on the handle's device, in
  * FLOP/s (FMA = 2), the FP64 roofline denominator. */
 int ukfb_measure_fp64_peak(ukfb_handle* h, double* flops_per_s);
-/* self-test of the device arithmetic the kernels are built on (csrc/so3.cuh, csrc/simt.cuh): for i < n,
- * out[14 i + 0..3] = SO3 exp(v[3 i ..]) (x, y, z, w), out[+4..6] = SO3 log of that quaternion, out[+7] = 1 / x[i],
- * out[+8], out[+9] = sqrt(x[i]), 1 / sqrt(x[i]); out[+10..12] = the fast kernels' branch-free log (no reciprocal) of
- * their polynomial exp of v, out[+13] = 1 if v lies outside the range of that pair (the kernels then run the
- * literal code), else 0.  tests/ compare them with extended-precision values. */
+/* self-test of the device arithmetic the kernels are built on (csrc/so3.cuh, csrc/simt.cuh): for i < n, with
+ * o = out + UKFB_SELFTEST_STRIDE i:  o[0..3] = SO3 exp(v[3 i ..]) (x, y, z, w), o[4..6] = SO3 log of that quaternion,
+ * o[7] = 1 / x[i], o[8], o[9] = sqrt(x[i]), 1 / sqrt(x[i]); o[10..12] = the fast kernels' branch-free log (no reciprocal)
+ * of their polynomial exp of v, o[13] = 1 if v lies outside the range of that pair (the kernels then use the any-angle
+ * pair), else 0; o[14..17] = the any-angle exp of v, o[18..20] = the any-angle log of that quaternion.
+ * tests/ compare them with extended-precision values. */
+#define UKFB_SELFTEST_STRIDE 21
 int ukfb_selftest_so3(ukfb_handle* h, int64_t n, const double* v, const double* x, double* out);
 
 #ifdef __cplusplus

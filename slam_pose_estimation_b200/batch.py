@@ -423,12 +423,12 @@ class UkfBatch:
         return int(self.lib.ukfb_launch_count(self.h))
 
     def selftest_so3(self, v, x):
-        """device exp / log / reciprocal / sqrt of csrc/so3.cuh and simt.cuh on n inputs -> (n, 14), see the header"""
+        """device exp / log / reciprocal / sqrt of csrc/so3.cuh and simt.cuh on n inputs -> (n, 21), see the header"""
         v, pv = _host(v, np.float64)
         x, px = _host(x, np.float64)
         n = x.size
         assert v.size == 3 * n
-        out = np.empty((n, 14))
+        out = np.empty((n, 21))
         self._chk(self.lib.ukfb_selftest_so3(self.h, n, pv, px, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -2006,7 +2006,7 @@ __global__ void so3_selftest_kernel(const double* __restrict__ v, const double* 
         so3_exp(v + 3 * i, 1.0, q);
         so3_log(q, w);
         fast_sqrt_rsqrt(x[i], sq, rs);
-        double* o = out + 14 * i;
+        double* o = out + UKFB_SELFTEST_STRIDE * i;
         o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
         o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
         /* the branch-free pair of the fast kernels (ukf_pose_fast.cuh): polynomial exp, reciprocal-free log */
@@ -2015,6 +2015,15 @@ __global__ void so3_selftest_kernel(const double* __restrict__ v, const double* 
         pf_exp(v + 3 * i, 1.0, qf, slow);
         pf_log(qf, wf, slow);
         o[10] = wf[0], o[11] = wf[1], o[12] = wf[2], o[13] = slow ? 1.0 : 0.0;
+        /* their any-angle pair: eighth-angle polynomial + three squarings, three square roots + asin form; run as the pair
+         * type the kernels use (second slot: the opposite rotation) */
+        D2 v2[3] = {D2(v[3 * i], -v[3 * i]), D2(v[3 * i + 1], -v[3 * i + 1]), D2(v[3 * i + 2], -v[3 * i + 2])}, q2[4], w2[3];
+        bool hard = false;
+        pf_exp_wide<D2>(v2, 1.0, q2, hard);
+        pf_log_wide<D2>(q2, w2);
+        o[14] = q2[0].a, o[15] = q2[1].a, o[16] = q2[2].a, o[17] = q2[3].a;
+        o[18] = w2[0].a, o[19] = w2[1].a, o[20] = hard ? 1.0 : w2[2].a;
+        if (!hard && !(w2[0].b == -w2[0].a && w2[1].b == -w2[1].a && w2[2].b == -w2[2].a)) o[20] = 1.0 / 0.0; /* the two slots must mirror */
     }
 }
 
@@ -2023,7 +2032,7 @@ extern "C" int ukfb_selftest_so3(ukfb_handle* h, int64_t n, const double* v, con
     CHECK_H(h);
     if (n < 1 || !v || !x || !out) return fail(UKFB_ERR_INVALID, "ukfb_selftest_so3: bad argument");
     if (is_sharded(h)) return ukfb_selftest_so3(h->shards[0], n, v, x, out);
-    const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * 14;
+    const size_t bv = align256(sizeof(double) * n * 3), bx = align256(sizeof(double) * n), bo = sizeof(double) * n * UKFB_SELFTEST_STRIDE;
     int rc = stage_reserve(h, bv + bx + bo);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->stage, v, sizeof(double) * n * 3, cudaMemcpyHostToDevice, h->stream));

@@ -240,6 +240,91 @@ UKFB_D void quat_mul_conj(const D2* a, const B* b, D2* r)
     r[2] = -a[3] * b[2] + a[2] * b[3] - a[0] * b[1] + a[1] * b[0];
 }
 
+/* ---- the second tier: SO(3) exp / log for ANY rotation angle, still branch-free, still no libm ----------------------
+ * A filter whose heading is barely known (sigma_ori of a radian or more: the normal start-up state of a pose filter) has
+ * sigma points far outside the 0.58 rad of the short polynomials above.  Columns whose points leave that range are redone
+ * with this pair instead of sending the whole filter to the literal code:
+ *   exp: the polynomial pair at an eighth of the angle (degree 6, half angle / 8 <= 0.4 rad), then three quaternion
+ *        squarings q <- q q (w <- w^2 - |v|^2, v <- 2 w v); rotations up to 6.4 rad;
+ *   log: q == -q folded to w >= 0, three quaternion square roots ((v, w) -> (v / (2 c), c), c = sqrt((1 + w) / 2): Goldschmidt
+ *        from the hardware reciprocal-square-root seed), which leaves a half angle <= pi / 16, then the reciprocal-free
+ *        asin form of pf_log, times 8.
+ * Against 50-digit values both are within 2e-15 of MTK's cos / sinc / atan expressions (tests/test_so3_kernels.py). */
+constexpr double PF_EXP_WIDE_X2 = 10.24; /* (half angle)^2 bound of pf_exp_wide: 3.2 rad */
+constexpr double PF_WIDE_TRACE = 1.0;    /* trace(Sigma_ori) above this (0.58 rad per axis): sigma points certainly outside the short polynomials */
+#define UKFB_TPOLY6(C, v, v2) \
+    tfma(tfma(C[6], v2, tfma(C[5], v, C[4])), (v2) * (v2), tfma(tfma(C[3], v, C[2]), v2, tfma(C[1], v, C[0])))
+UKFB_D bool all_le(double x, double lim) { return x <= lim; }
+UKFB_D double v_sign(double w) { return w < 0.0 ? -1.0 : 1.0; }
+UKFB_D D2 v_sign(D2 w) { return D2(v_sign(w.a), v_sign(w.b)); }
+UKFB_D void v_sqrt_rsqrt(double x, double& sq, double& rs) { fast_sqrt_rsqrt(x, sq, rs); }
+UKFB_D void v_sqrt_rsqrt(D2 x, D2& sq, D2& rs)
+{
+    fast_sqrt_rsqrt(x.a, sq.a, rs.a);
+    fast_sqrt_rsqrt(x.b, sq.b, rs.b);
+}
+
+template <class V>
+UKFB_D void pf_exp_wide(const V* v, double scale, V* q, bool& hard)
+{
+    const double half = scale * 0.5;
+    const V norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const V x2 = (half * half) * norm2;
+    hard = hard || !all_le(x2, PF_EXP_WIDE_X2);
+    const V y2 = x2 * (1.0 / 64.0), y4 = y2 * y2;
+    V w = UKFB_TPOLY6(SO3_COS_C, y2, y4);
+    const V mult = UKFB_TPOLY6(SO3_SINC_C, y2, y4) * (half * 0.125);
+    V a = mult * v[0], b = mult * v[1], c = mult * v[2];
+    UKFB_UNROLL
+    for (int k = 0; k < 3; ++k) {
+        const V t = w + w, n = a * a + b * b + c * c;
+        w = tfma(w, w, -n);
+        a = t * a, b = t * b, c = t * c;
+    }
+    q[0] = a, q[1] = b, q[2] = c, q[3] = w;
+}
+
+template <class V>
+UKFB_D void pf_log_wide(const V* q, V* out)
+{
+    V x = q[0], y = q[1], z = q[2], w = q[3];
+    /* |q| = 1 + O(1e-7) (pf_unit): normalised to first order, then q == -q folded to w >= 0 (MTK's atan(nv / w) form) */
+    const V n2 = tfma(w, w, x * x + y * y + z * z);
+    const V k = v_sign(w) * tfma(n2 - 1.0, -0.5, 1.0);
+    x = x * k, y = y * k, z = z * k, w = w * k;
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) { /* (v, w) <- its square root */
+        V c, rc;
+        v_sqrt_rsqrt((w + 1.0) * 0.5, c, rc);
+        const V h = rc * 0.5;
+        x = x * h, y = y * h, z = z * h, w = c;
+    }
+    const V nv2 = x * x + y * y + z * z;
+    const V d = tfma(w, w, nv2) - 1.0;
+    const V s0 = two_asin_over_s_poly(tfma(-nv2, d, nv2));
+    const V sc = tfma(s0, -0.5 * d, s0) * 8.0;
+    out[0] = sc * x, out[1] = sc * y, out[2] = sc * z;
+}
+
+/* single values in the two instances of the structured code: the hot one (WIDE = false) uses the short polynomials and
+ * flags a range exit, the out-of-line one (WIDE = true) the any-angle pair (`slow`: beyond even its range) */
+template <bool WIDE>
+UKFB_D void pf_exp1(const double* v, double scale, double* q, bool& slow)
+{
+    if (WIDE)
+        pf_exp_wide<double>(v, scale, q, slow);
+    else
+        pf_exp(v, scale, q, slow);
+}
+template <bool WIDE>
+UKFB_D void pf_log1(const double* q, double* out, bool& slow)
+{
+    if (WIDE)
+        pf_log_wide<double>(q, out);
+    else
+        pf_log(q, out, slow);
+}
+
 /* ---- Cholesky of a packed lower 12x12 in registers, first NCOL columns (LAPACK dpotf2('L') order) ------------- */
 template <int NCOL>
 UKFB_D bool pf_cholesky(double* a)
@@ -297,30 +382,51 @@ UKFB_D void prefetch_next_wave(const StepParams& p, long long tile, int lane)
     if (p.do_predict && !p.time_mode && p.dt && o < TILE * 8 * p.dt_stride) prefetch_l2(reinterpret_cast<const char*>(p.dt + nb * p.dt_stride) + o);
 }
 
+/* exp / log of a pair with the short polynomials (WIDE = false: `flag` collects range exits, the values are then meaningless
+ * and the caller redoes the column with WIDE = true) or with the any-angle pair (`flag`: beyond even its range) */
+template <bool WIDE, class V>
+UKFB_D void pf_exp_t(const V* v, double scale, V* q, bool& flag)
+{
+    if (WIDE)
+        pf_exp_wide<V>(v, scale, q, flag);
+    else
+        pf_exp(v, scale, q, flag);
+}
+template <bool WIDE, class V>
+UKFB_D void pf_log_t(const V* q, V* out, bool& flag)
+{
+    if (WIDE)
+        pf_log_wide<V>(q, out);
+    else
+        pf_log(q, out, flag);
+}
+
 /* a pair of propagated sigma points: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
+template <bool WIDE>
 UKFB_D void pf_point2(const D2* qs, const D2* ps, const D2* vs, const D2* ws, double dt, const double* ref_p, const double* ref_q,
                       D2* d, bool& slow)
 {
     D2 rv[3], e[4], qn[4], r[4];
     pf_rotate(qs, vs, rv);
     /* q [+] (q w) dt = exp((q w) dt) q = q exp(w dt) q^-1 q = q exp(w dt) for a unit q: w needs no rotation */
-    pf_exp(ws, dt, e, slow);
+    pf_exp_t<WIDE>(ws, dt, e, slow);
     quat_mul(qs, e, qn);
     d[0] = tfma(dt, rv[0], ps[0]) - ref_p[0];
     d[1] = tfma(dt, rv[1], ps[1]) - ref_p[1];
     d[2] = tfma(dt, rv[2], ps[2]) - ref_p[2];
     quat_mul_conj(qn, ref_q, r);
-    pf_log(r, d + 3, slow);
+    pf_log_t<WIDE>(r, d + 3, slow);
 }
 
 /* the +/- sigma points of a column j < 6 through the process model; L receives the column (12 entries) */
+template <bool WIDE>
 UKFB_D void pf_pair_a(const double* sm, int lane, int j, const PoseMu& m, const double* vm, double dt, const double* ref_p,
                       const double* ref_q, double* L, double* dpl, double* dmi, bool& slow)
 {
     UKFB_UNROLL
     for (int i = 0; i < 12; ++i) L[i] = UKFB_PS(PF_LA + j * 12 + i);
     double e[4];
-    pf_exp(L + 3, 1.0, e, slow);
+    pf_exp_t<WIDE>(L + 3, 1.0, e, slow);
     /* exp(+-Lo) * q = e.w q +- t,  t = (e.vec, 0) * q */
     const double* q = m.q;
     const double t0 = e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
@@ -333,7 +439,7 @@ UKFB_D void pf_pair_a(const double* sm, int lane, int j, const PoseMu& m, const 
     const D2 vs[3] = {D2(vm[0] + L[6], vm[0] - L[6]), D2(vm[1] + L[7], vm[1] - L[7]), D2(vm[2] + L[8], vm[2] - L[8])};
     const D2 ws[3] = {D2(m.w[0] + L[9], m.w[0] - L[9]), D2(m.w[1] + L[10], m.w[1] - L[10]), D2(m.w[2] + L[11], m.w[2] - L[11])};
     D2 d[6];
-    pf_point2(qs, ps, vs, ws, dt, ref_p, ref_q, d, slow);
+    pf_point2<WIDE>(qs, ps, vs, ws, dt, ref_p, ref_q, d, slow);
     UKFB_UNROLL
     for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
 }
@@ -341,6 +447,7 @@ UKFB_D void pf_pair_a(const double* sm, int lane, int j, const PoseMu& m, const 
 /* the +/- sigma points of a column j >= 6: position and orientation unperturbed.
  * rw0 = R w, c = q * conj(ref_q).  Outputs the orientation deviations and wv = (R Lv) dt, the +- offset of the
  * propagated position; L receives rows 6..11 of the column. */
+template <bool WIDE>
 UKFB_D void pf_pair_b(const double* sm, int lane, int j, const double* Rm, const double* rw0, const double* c, double dt,
                       double* L, double* dopl, double* domi, double* wv, bool& slow)
 {
@@ -352,21 +459,81 @@ UKFB_D void pf_pair_b(const double* sm, int lane, int j, const double* Rm, const
     wv[0] = dt * rv[0], wv[1] = dt * rv[1], wv[2] = dt * rv[2];
     const D2 rw[3] = {D2(rw0[0] + u[0], rw0[0] - u[0]), D2(rw0[1] + u[1], rw0[1] - u[1]), D2(rw0[2] + u[2], rw0[2] - u[2])};
     D2 e[4], r[4], d[3];
-    pf_exp(rw, dt, e, slow);
+    pf_exp_t<WIDE>(rw, dt, e, slow);
     quat_mul(e, c, r);
-    pf_log(r, d, slow);
+    pf_log_t<WIDE>(r, d, slow);
     UKFB_UNROLL
     for (int i = 0; i < 3; ++i) dopl[i] = d[i].a, domi[i] = d[i].b;
 }
 
-/* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
+/* the +/- points of column j < 6 of apply_delta: exp(delta_ori +- L_ori[:, j]) c, deviations from the reference */
+template <bool WIDE>
+UKFB_D void pf_pair_d(const double* sm, int lane, int j, const double* delta, const double* c, double* dp, double* dn, bool& slow)
+{
+    D2 v[3], e[4], r2[4], d[3]; /* the + and - point of the column, side by side */
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
+        v[i] = D2(delta[3 + i] + l, delta[3 + i] - l);
+    }
+    pf_exp_t<WIDE>(v, 1.0, e, slow);
+    quat_mul(e, c, r2);
+    pf_log_t<WIDE>(r2, d, slow);
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) dp[i] = d[i].a, dn[i] = d[i].b;
+}
+
+/* The column pairs as the two instances of the structured code call them.  The hot instance (WIDE = false) knows only the
+ * short polynomials.  The out-of-line instance (WIDE = true) picks per column: orientation entries this large go to the
+ * any-angle pair at once; any other column (the position columns, the velocity / angular-velocity columns of a filter
+ * that is unsure of its attitude only) tries the short polynomials first and is redone if a point left their range. */
+constexpr double PF_WIDE_COLUMN_N2 = 0.2; /* |L_ori[:, j]|^2 above this: do not bother with the short polynomials */
+template <bool WIDE>
+UKFB_D void pf_pair_a_sel(const double* sm, int lane, int j, const PoseMu& m, const double* vm, double dt, const double* ref_p,
+                          const double* ref_q, double* L, double* dpl, double* dmi, bool& slow)
+{
+    if (!WIDE) {
+        pf_pair_a<false>(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+        return;
+    }
+    const double l3 = UKFB_PS(PF_LA + j * 12 + 3), l4 = UKFB_PS(PF_LA + j * 12 + 4), l5 = UKFB_PS(PF_LA + j * 12 + 5);
+    bool redo = l3 * l3 + l4 * l4 + l5 * l5 > PF_WIDE_COLUMN_N2;
+    if (!redo) pf_pair_a<false>(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, redo);
+    if (redo) pf_pair_a<true>(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+}
+template <bool WIDE>
+UKFB_D void pf_pair_b_sel(const double* sm, int lane, int j, const double* Rm, const double* rw0, const double* c, double dt,
+                          double* L, double* dopl, double* domi, double* wv, bool& slow)
+{
+    if (!WIDE) {
+        pf_pair_b<false>(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
+        return;
+    }
+    bool redo = false;
+    pf_pair_b<false>(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, redo);
+    if (redo) pf_pair_b<true>(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
+}
+template <bool WIDE>
+UKFB_D void pf_pair_d_sel(const double* sm, int lane, int j, const double* delta, const double* c, double* dp, double* dn, bool& slow)
+{
+    if (!WIDE) {
+        pf_pair_d<false>(sm, lane, j, delta, c, dp, dn, slow);
+        return;
+    }
+    const double l3 = UKFB_PS(PF_LA + j * 12 + 3), l4 = UKFB_PS(PF_LA + j * 12 + 4), l5 = UKFB_PS(PF_LA + j * 12 + 5);
+    bool redo = l3 * l3 + l4 * l4 + l5 * l5 > PF_WIDE_COLUMN_N2;
+    if (!redo) pf_pair_d<false>(sm, lane, j, delta, c, dp, dn, redo);
+    if (redo) pf_pair_d<true>(sm, lane, j, delta, c, dp, dn, slow);
+}
+
 #ifdef UKFB_SIMT_EMU
 /* host emulation only: how often each fallback ran (predict, update, apply), so the tests can tell that they did */
-inline unsigned long long pf_fallbacks[3] = {0, 0, 0};
+inline unsigned long long pf_fallbacks[5] = {0, 0, 0, 0, 0}; /* [3], [4]: predicts / apply_deltas served by the any-angle instance */
 #define UKFB_PF_COUNT(i) __atomic_fetch_add(&pf_fallbacks[i], 1ull, __ATOMIC_RELAXED)
 #else
 #define UKFB_PF_COUNT(i)
 #endif
+/* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
 struct PfLit { /* result of a literal fallback, returned by value so that the caller's state stays in registers */
     PoseMu m;
     uint32_t status;
@@ -460,10 +627,17 @@ UKFB_DNI PfLit pf_literal_update(double* sig, int kind, const double* zm, const 
 /* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
 /* On success: m holds the new mean, the record and (when to_smem) slots 0..77 hold the new covariance.
  * `a` (the prior covariance, packed lower) is destroyed. */
-UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig, double* a, const double* Qp, const double* acov,
+/* WIDE = false: the hot instance, inlined into the kernel: short polynomials only, gives up (false) at the first sigma
+ * point outside their range.  WIDE = true: the instance behind pf_predict_wide (out of line), which serves filters of
+ * any orientation uncertainty by running the passes that need it through pf_predict_pass_wide. */
+template <bool WIDE>
+UKFB_D bool pf_predict(int q_diagonal, double* sm, int lane, double* sig, double* a, const double* Qp, const double* acov,
                        const ModelArgs& ma, PoseMu& m, bool to_smem, uint32_t& status, int& passes_out, bool& spd)
 {
     const double dt = ma.dt;
+    /* a filter whose orientation uncertainty is this large certainly has sigma points outside the range of the short
+     * polynomials: the hot instance does not even start (nothing has been modified) */
+    if (!WIDE && a[tri(3, 3)] + a[tri(4, 4)] + a[tri(5, 5)] > PF_WIDE_TRACE) return false;
     /* Cholesky of the covariance (a: loaded from the record by the caller), in registers; the factor goes to the
      * LA / LB blocks */
     {
@@ -498,7 +672,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         p0n[0] = fma(dt, rv0[0], m.p[0]);
         p0n[1] = fma(dt, rv0[1], m.p[1]);
         p0n[2] = fma(dt, rv0[2], m.p[2]);
-        pf_exp(rw0, dt, e0, slow);
+        pf_exp1<WIDE>(rw0, dt, e0, slow);
         quat_mul(e0, m.q, q0n);
     }
     double ref_p[3] = {p0n[0], p0n[1], p0n[2]};
@@ -513,7 +687,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
             double r[4];
             d0[0] = p0n[0] - ref_p[0], d0[1] = p0n[1] - ref_p[1], d0[2] = p0n[2] - ref_p[2];
             quat_mul_conj(q0n, ref_q, r);
-            pf_log(r, d0 + 3, slow);
+            pf_log1<WIDE>(r, d0 + 3, slow);
         }
         /* X0 and the 12 points of columns 6..11 deviate by d0 in position (the +- offsets cancel) */
         md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
@@ -521,7 +695,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_LOOP_UNROLL(UKFB_PF_MEAN_UNROLL)
         for (int j = 0; j < 6; ++j) {
             double L[12], dpl[6], dmi[6];
-            pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+            pf_pair_a_sel<WIDE>(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) md[i] += dpl[i] + dmi[i];
         }
@@ -530,7 +704,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_LOOP_UNROLL(UKFB_PF_MEAN_UNROLL)
         for (int j = 6; j < 12; ++j) {
             double L[6], dopl[3], domi[3], wv[3];
-            pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
+            pf_pair_b_sel<WIDE>(sm, lane, j, Rm, rw0, c, dt, L, dopl, domi, wv, slow);
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) md[3 + i] += dopl[i] + domi[i];
         }
@@ -543,7 +717,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         ref_p[0] += md[0], ref_p[1] += md[1], ref_p[2] += md[2];
         {
             double e[4], r[4];
-            pf_exp(md + 3, 1.0, e, slow);
+            pf_exp1<WIDE>(md + 3, 1.0, e, slow);
             quat_mul(e, ref_q, r);
             ref_q[0] = r[0], ref_q[1] = r[1], ref_q[2] = r[2], ref_q[3] = r[3];
         }
@@ -567,7 +741,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         double d0[6], r[4];
         d0[0] = p0n[0] - ref_p[0], d0[1] = p0n[1] - ref_p[1], d0[2] = p0n[2] - ref_p[2];
         quat_mul_conj(q0n, ref_q, r);
-        pf_log(r, d0 + 3, slow);
+        pf_log1<WIDE>(r, d0 + 3, slow);
         UKFB_UNROLL
         for (int i = 0; i < 6; ++i) {
             UKFB_UNROLL
@@ -576,7 +750,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_LOOP_UNROLL(UKFB_PF_COV_UNROLL)
         for (int j = 0; j < 6; ++j) {
             double L[12], dpl[6], dmi[6];
-            pf_pair_a(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
+            pf_pair_a_sel<WIDE>(sm, lane, j, m, vm, dt, ref_p, ref_q, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) {
                 UKFB_UNROLL
@@ -593,7 +767,7 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_LOOP_UNROLL(UKFB_PF_COV_UNROLL)
         for (int j = 6; j < 12; ++j) {
             double L[6], dpl[6], dmi[6], wv[3];
-            pf_pair_b(sm, lane, j, Rm, rw0, c, dt, L, dpl + 3, dmi + 3, wv, slow);
+            pf_pair_b_sel<WIDE>(sm, lane, j, Rm, rw0, c, dt, L, dpl + 3, dmi + 3, wv, slow);
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) dpl[i] = d0[i] + wv[i], dmi[i] = d0[i] - wv[i];
             UKFB_UNROLL
@@ -710,9 +884,9 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
             }
         }
     };
-    if (par.q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
+    if (q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
         commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, TrueT());
-    else if (par.q_diagonal)
+    else if (q_diagonal)
         commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, FalseT());
     else
         commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); }, FalseT());
@@ -721,6 +895,31 @@ UKFB_D bool pf_predict(const StepParams& par, double* sm, int lane, double* sig,
     m.v[0] = vm[0], m.v[1] = vm[1], m.v[2] = vm[2];
     passes_out = passes;
     return true;
+}
+
+/* Everything the hot predict does not do, out of line (one call site in the kernel): a filter whose sigma points leave the
+ * range of the short polynomials (known from its orientation variance, or found out by the hot instance, which then has
+ * modified nothing) is served by the any-angle instance of the same structured code; one beyond that too (a quaternion
+ * off the unit sphere, a rotation above 6.4 rad) by the literal code of ukf_thread.cuh. */
+UKFB_DNI PfLit pf_predict_slow(double* sm, int lane, double* sig, const double* Qp, const double* acov, ModelArgs ma, PoseMu m,
+                               int to_smem, int q_diagonal, int* in_smem)
+{
+    {
+        double a[PoseF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < PoseF::LP; ++e) a[e] = sig[e * TILE];
+        PfLit r;
+        r.m = m, r.status = 0, r.passes = 0;
+        bool spd = true;
+        if (pf_predict<true>(q_diagonal, sm, lane, sig, a, Qp, acov, ma, r.m, to_smem != 0, r.status, r.passes, spd)) {
+            UKFB_PF_COUNT(3);
+            if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+            *in_smem = spd ? to_smem : 0;
+            return r;
+        }
+    }
+    *in_smem = 0;
+    return pf_literal_predict(sig, Qp, acov, ma, m);
 }
 
 /* tangent index of measurement component c of a selector kind (PoseUKF.cpp:7-69), -1 = unused component */
@@ -751,6 +950,123 @@ UKFB_D double pf_mu_tangent(const PoseMu& m, int t)
     r = t == 10 ? m.w[1] : r;
     r = t == 11 ? m.w[2] : r;
     return r;
+}
+
+/* ---- apply_delta of the structured update: orientation rows only.  Slots LA hold the first six factor columns of the
+ * downdated covariance, which is in the record.  WIDE = false: the hot instance (short polynomials; gives up with
+ * stage = 2 when a sigma point leaves their range before anything was overwritten, stage = 1 otherwise);
+ * WIDE = true: the out-of-line instance for any orientation uncertainty (gives up with stage = 1: literal code). */
+template <bool WIDE>
+UKFB_D bool pf_apply_delta(double* sm, int lane, double* sig, PoseMu& m, const double* delta, uint32_t& status, int& passes_out, int& stage)
+{
+    bool slow = !pf_unit(m.q);
+    const bool off_sphere = slow;
+    bool lost_factor = false;
+    double e0[4], q0n[4];
+    pf_exp1<WIDE>(delta + 3, 1.0, e0, slow);
+    quat_mul(e0, m.q, q0n);
+    double ref_q[4] = {q0n[0], q0n[1], q0n[2], q0n[3]};
+    int it = 0, passes = 0;
+    while (true) {
+        double c[4], r[4], d0[3], md[3];
+        quat_mul_conj(m.q, ref_q, c);
+        quat_mul(e0, c, r);
+        pf_log1<WIDE>(r, d0, slow);
+        md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double dp[3], dn[3];
+            pf_pair_d_sel<WIDE>(sm, lane, j, delta, c, dp, dn, slow);
+            md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
+        }
+        double n2 = 0.0;
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            md[i] = div_ns<PoseF::NS>(md[i]);
+            n2 += md[i] * md[i];
+        }
+        {
+            double e[4], rr[4];
+            pf_exp1<WIDE>(md, 1.0, e, slow);
+            quat_mul(e, ref_q, rr);
+            ref_q[0] = rr[0], ref_q[1] = rr[1], ref_q[2] = rr[2], ref_q[3] = rr[3];
+        }
+        ++passes;
+        if (slow || !(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
+        if (++it >= UKFB_MEAN_MAX_IT) {
+            status |= UKFB_STATUS_MEAN_NO_CONVERGE;
+            break;
+        }
+    }
+    /* covariance of the orientation rows: Coo (6) and the cross block with the 9 Euclidean components */
+    double Coo[6], Xc[27];
+    if (!slow) {
+        double c[4], r[4], d0[3];
+        quat_mul_conj(m.q, ref_q, c);
+        quat_mul(e0, c, r);
+        pf_log1<WIDE>(r, d0, slow);
+        UKFB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = 13.0 * d0[i] * d0[k];
+        }
+        /* the cross block is formed after the loop (as X in the predict): the differences dp - dn of column j go to the slots
+         * L[3:6, j] the column's two points were just generated from */
+        bool late = false;
+        UKFB_NOUNROLL
+        for (int j = 0; j < 6; ++j) {
+            double dp[3], dn[3];
+            pf_pair_d_sel<WIDE>(sm, lane, j, delta, c, dp, dn, late);
+            UKFB_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                UKFB_UNROLL
+                for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = fma(dp[i], dp[k], fma(dn[i], dn[k], Coo[tri(i, k)]));
+            }
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) UKFB_PS(PF_LA + j * 12 + 3 + k) = dp[k] - dn[k];
+        }
+        slow = slow || late;
+        lost_factor = late; /* the column slots hold differences now */
+        UKFB_UNROLL
+        for (int i = 0; i < 27; ++i) Xc[i] = 0.0;
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) {
+            double dd[3];
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) dd[k] = UKFB_PS(PF_LA + j * 12 + 3 + k);
+            UKFB_UNROLL
+            for (int t = 0; t < 9; ++t) {
+                const int row = t < 3 ? t : t + 3;
+                if (row < j) continue; /* L is lower triangular */
+                const double l = UKFB_PS(PF_LA + j * 12 + row);
+                UKFB_UNROLL
+                for (int k = 0; k < 3; ++k) Xc[t * 3 + k] = fma(l, dd[k], Xc[t * 3 + k]);
+            }
+        }
+    }
+    if (slow) { /* Sigma - K S K^T is in the record, mu untouched: the caller hands mu and delta on */
+        stage = (WIDE || lost_factor || off_sphere) ? 1 : 2; /* 2: the any-angle instance can take over (factor columns intact) */
+        return false;
+    }
+    /* commit */
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        UKFB_UNROLL
+        for (int k = 0; k <= i; ++k) sig[tri(3 + i, 3 + k) * TILE] = 0.5 * Coo[tri(i, k)];
+        UKFB_UNROLL
+        for (int t = 0; t < 3; ++t) sig[tri(3 + i, t) * TILE] = 0.5 * Xc[t * 3 + i];         /* orientation x position */
+        UKFB_UNROLL
+        for (int t = 3; t < 9; ++t) sig[tri(t + 3, 3 + i) * TILE] = 0.5 * Xc[t * 3 + i];     /* (vel, angvel) x orientation */
+    }
+    UKFB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        m.p[i] += delta[i];
+        m.v[i] += delta[6 + i];
+        m.w[i] += delta[9 + i];
+    }
+    m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
+    passes_out = passes;
+    return true;
 }
 
 /* ---- structured update with a selector measurement.  Slots 0..77 hold the prior covariance (packed lower), which
@@ -962,6 +1278,7 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
         }
     }
     stage = 1; /* the record holds Sigma - K S K^T */
+    const bool wide_trace = a[tri(3, 3)] + a[tri(4, 4)] + a[tri(5, 5)] > PF_WIDE_TRACE; /* as in the predict */
     /* first six columns of the factor of the updated covariance (the reference factorises all of it: a failure in the
      * later columns shows at the next factorisation of this filter instead) */
     spd = pf_cholesky<6>(a);
@@ -973,120 +1290,11 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
     }
 
     /* ---- apply_delta: orientation rows only */
-    bool slow = !pf_unit(m.q);
-    double e0[4], q0n[4];
-    pf_exp(delta + 3, 1.0, e0, slow);
-    quat_mul(e0, m.q, q0n);
-    double ref_q[4] = {q0n[0], q0n[1], q0n[2], q0n[3]};
-    int it = 0, passes = 0;
-    while (true) {
-        double c[4], r[4], d0[3], md[3];
-        quat_mul_conj(m.q, ref_q, c);
-        quat_mul(e0, c, r);
-        pf_log(r, d0, slow);
-        md[0] = 13.0 * d0[0], md[1] = 13.0 * d0[1], md[2] = 13.0 * d0[2];
-        UKFB_NOUNROLL
-        for (int j = 0; j < 6; ++j) {
-            D2 v[3], e[4], r2[4], d[3]; /* the + and - point of the column, side by side */
-            UKFB_UNROLL
-            for (int i = 0; i < 3; ++i) {
-                const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
-                v[i] = D2(delta[3 + i] + l, delta[3 + i] - l);
-            }
-            pf_exp(v, 1.0, e, slow);
-            quat_mul(e, c, r2);
-            pf_log(r2, d, slow);
-            md[0] += d[0].a + d[0].b, md[1] += d[1].a + d[1].b, md[2] += d[2].a + d[2].b;
-        }
-        double n2 = 0.0;
-        UKFB_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            md[i] = div_ns<PoseF::NS>(md[i]);
-            n2 += md[i] * md[i];
-        }
-        {
-            double e[4], rr[4];
-            pf_exp(md, 1.0, e, slow);
-            quat_mul(e, ref_q, rr);
-            ref_q[0] = rr[0], ref_q[1] = rr[1], ref_q[2] = rr[2], ref_q[3] = rr[3];
-        }
-        ++passes;
-        if (slow || !(n2 > UKFB_MEAN_TOL * UKFB_MEAN_TOL)) break;
-        if (++it >= UKFB_MEAN_MAX_IT) {
-            status |= UKFB_STATUS_MEAN_NO_CONVERGE;
-            break;
-        }
+    if (wide_trace) {
+        stage = 2; /* a wide filter: straight to the out-of-line instance; the factor columns are in place */
+        return false;
     }
-    /* covariance of the orientation rows: Coo (6) and the cross block with the 9 Euclidean components */
-    double Coo[6], Xc[27];
-    if (!slow) {
-        double c[4], r[4], d0[3];
-        quat_mul_conj(m.q, ref_q, c);
-        quat_mul(e0, c, r);
-        pf_log(r, d0, slow);
-        UKFB_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            UKFB_UNROLL
-            for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = 13.0 * d0[i] * d0[k];
-        }
-        /* the cross block is formed after the loop (as X in the predict): the differences dp - dn of column j go to the slots
-         * L[3:6, j] the column's two points were just generated from */
-        UKFB_NOUNROLL
-        for (int j = 0; j < 6; ++j) {
-            D2 v[3], e[4], r2[4], d[3];
-            UKFB_UNROLL
-            for (int i = 0; i < 3; ++i) {
-                const double l = UKFB_PS(PF_LA + j * 12 + 3 + i);
-                v[i] = D2(delta[3 + i] + l, delta[3 + i] - l);
-            }
-            pf_exp(v, 1.0, e, slow);
-            quat_mul(e, c, r2);
-            pf_log(r2, d, slow);
-            UKFB_UNROLL
-            for (int i = 0; i < 3; ++i) {
-                UKFB_UNROLL
-                for (int k = 0; k <= i; ++k) Coo[tri(i, k)] = fma(d[i].a, d[k].a, fma(d[i].b, d[k].b, Coo[tri(i, k)]));
-            }
-            UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) UKFB_PS(PF_LA + j * 12 + 3 + k) = d[k].a - d[k].b;
-        }
-        UKFB_UNROLL
-        for (int i = 0; i < 27; ++i) Xc[i] = 0.0;
-        UKFB_UNROLL
-        for (int j = 0; j < 6; ++j) {
-            double dd[3];
-            UKFB_UNROLL
-            for (int k = 0; k < 3; ++k) dd[k] = UKFB_PS(PF_LA + j * 12 + 3 + k);
-            UKFB_UNROLL
-            for (int t = 0; t < 9; ++t) {
-                const int row = t < 3 ? t : t + 3;
-                if (row < j) continue; /* L is lower triangular */
-                const double l = UKFB_PS(PF_LA + j * 12 + row);
-                UKFB_UNROLL
-                for (int k = 0; k < 3; ++k) Xc[t * 3 + k] = fma(l, dd[k], Xc[t * 3 + k]);
-            }
-        }
-    }
-    if (slow) return false; /* the caller hands mu and delta to the literal apply_delta; Sigma - K S K^T is in the record */
-    /* commit */
-    UKFB_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        UKFB_UNROLL
-        for (int k = 0; k <= i; ++k) sig[tri(3 + i, 3 + k) * TILE] = 0.5 * Coo[tri(i, k)];
-        UKFB_UNROLL
-        for (int t = 0; t < 3; ++t) sig[tri(3 + i, t) * TILE] = 0.5 * Xc[t * 3 + i];         /* orientation x position */
-        UKFB_UNROLL
-        for (int t = 3; t < 9; ++t) sig[tri(t + 3, 3 + i) * TILE] = 0.5 * Xc[t * 3 + i];     /* (vel, angvel) x orientation */
-    }
-    UKFB_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        m.p[i] += delta[i];
-        m.v[i] += delta[6 + i];
-        m.w[i] += delta[9 + i];
-    }
-    m.q[0] = ref_q[0], m.q[1] = ref_q[1], m.q[2] = ref_q[2], m.q[3] = ref_q[3];
-    passes_out = passes;
-    return true;
+    return pf_apply_delta<false>(sm, lane, sig, m, delta, status, passes_out, stage);
 }
 
 /* Everything the selector kinds' structured update does not do, out of line (one call site, where few registers are
@@ -1095,9 +1303,9 @@ UKFB_D bool pf_update(double* sm, int lane, double* sig, int kind, const double*
  * first = true: nothing has been modified yet; false: the record holds Sigma - K S K^T and `delta` = K innov. */
 template <bool WITH_ORI>
 UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma,
-                              PoseMu m, PfDelta delta, bool first, double gate_d2)
+                              PoseMu m, PfDelta delta, int stage, double gate_d2)
 {
-    if (WITH_ORI && first && kind == UKFB_MEAS_POSE_ORIENTATION) {
+    if (WITH_ORI && stage == 0 && kind == UKFB_MEAS_POSE_ORIENTATION) {
         /* the prior covariance into slots 0..77, as the structured update expects it; under the trace guard
          * (mu [+] L_j) [-] mu = L_j holds and the structured instance applies */
         UKFB_UNROLL
@@ -1107,16 +1315,24 @@ UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const
             PfLit r;
             r.m = m, r.status = 0, r.passes = 0;
             bool spd = true;
-            int stage = 0;
             const bool done = pf_update<true>(sm, lane, sig, kind, zm, Rm, r_ld, r.m, delta.d, r.status, r.passes, spd, gate_d2, stage);
             if (done) {
                 if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
                 return r;
             }
-            first = stage == 0; /* a polynomial range was left: literal from where the structured code stopped */
+            /* stage now tells where the structured code stopped */
         }
     }
-    return pf_literal_update(sig, kind, zm, Rm, r_ld, ma, m, delta, first, gate_d2);
+    if (stage == 2) { /* Sigma - K S K^T in the record, its factor columns in place, delta = K innov: apply_delta with the any-angle pair */
+        PfLit r;
+        r.m = m, r.status = 0, r.passes = 0;
+        if (pf_apply_delta<true>(sm, lane, sig, r.m, delta.d, r.status, r.passes, stage)) {
+            UKFB_PF_COUNT(4);
+            return r;
+        }
+        stage = 1; /* beyond that too: the literal apply_delta (nothing was committed) */
+    }
+    return pf_literal_update(sig, kind, zm, Rm, r_ld, ma, m, delta, stage == 0, gate_d2);
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
@@ -1245,7 +1461,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf
             ma.has_acc = (fabs(ma.acc[0]) <= big) && (fabs(ma.acc[1]) <= big) && (fabs(ma.acc[2]) <= big);
             bool spd = true;
             const bool want_smem = do_upd && kind != UKFB_MEAS_POSE_ORIENTATION;
-            if (pf_predict(p, sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
+            if (pf_predict<false>(p.q_diagonal, sm, lane, sig, a, Qp, acov, ma, m, want_smem, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
                     do_upd = false; /* every later factorisation of this covariance fails too */
@@ -1253,14 +1469,16 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf
                     sigma_in_smem = want_smem;
                     dirty_mu = true;
                 }
-            } else { /* a polynomial range was left: nothing was modified, run the literal code */
-                const PfLit r = pf_literal_predict(sig, Qp, acov, ma, m);
+            } else { /* a wide filter, or a sigma point left the range of the short polynomials: nothing was modified */
+                int in_smem = 0;
+                const PfLit r = pf_predict_slow(sm, lane, sig, Qp, acov, ma, m, want_smem ? 1 : 0, p.q_diagonal, &in_smem);
                 status |= r.status;
                 passes_a = r.passes;
                 if (r.status & UKFB_STATUS_NOT_SPD)
                     do_upd = false;
                 else {
                     m = r.m;
+                    sigma_in_smem = in_smem != 0;
                     dirty_mu = true;
                 }
             }
@@ -1319,8 +1537,8 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf
                     PfDelta dl;
                     UKFB_UNROLL
                     for (int i = 0; i < 12; ++i) dl.d[i] = delta[i];
-                    /* the selector instance only gives up after the downdate (stage 1), so `literal` alone tells the stage */
-                    const PfLit r = pf_update_slow<WITH_ORI>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal, p.gate_d2);
+                    /* stage: 0 = nothing done yet, 1 / 2 = where the selector instance stopped after the downdate */
+                    const PfLit r = pf_update_slow<WITH_ORI>(sm, lane, sig, kind, zm, Rmeas, p.r_ld, ma, m, dl, literal ? 0 : stage, p.gate_d2);
                     status |= r.status;
                     passes_b = r.passes;
                     if (!(r.status & UKFB_STATUS_NOT_SPD)) {

@@ -59,9 +59,9 @@ extern "C" int emu_pose_fast_step(const StepParams* p)
     return 0;
 }
 
-extern "C" void emu_pose_fast_fallbacks(unsigned long long* out3)
+extern "C" void emu_pose_fast_fallbacks(unsigned long long* out5)
 {
-    for (int i = 0; i < 3; ++i) out3[i] = pf_fallbacks[i];
+    for (int i = 0; i < 5; ++i) out5[i] = pf_fallbacks[i];
 }
 
 /* the structure-exploiting OrientationUKF kernel (ukf_ori_fast.cuh), same tiles */
@@ -75,9 +75,10 @@ extern "C" int emu_ori_fast_step(const StepParams* p)
     return 0;
 }
 
-extern "C" void emu_ori_fast_fallbacks(unsigned long long* out3)
+extern "C" void emu_ori_fast_fallbacks(unsigned long long* out5)
 {
-    for (int i = 0; i < 3; ++i) out3[i] = of_fallbacks[i];
+    for (int i = 0; i < 3; ++i) out5[i] = of_fallbacks[i];
+    out5[3] = out5[4] = 0;
 }
 
 /* the SO(3) kernels of so3.cuh as the host build evaluates them (same layout as ukfb_selftest_so3) */
@@ -88,7 +89,7 @@ extern "C" void emu_selftest_so3(long long n, const double* v, const double* x, 
         so3_exp(v + 3 * i, 1.0, q);
         so3_log(q, w);
         fast_sqrt_rsqrt(x[i], sq, rs);
-        double* o = out + 14 * i;
+        double* o = out + 21 * i;
         o[0] = q[0], o[1] = q[1], o[2] = q[2], o[3] = q[3], o[4] = w[0], o[5] = w[1], o[6] = w[2];
         o[7] = fast_rcp(x[i]), o[8] = sq, o[9] = rs;
         /* the branch-free pair of the fast kernels (ukf_pose_fast.cuh): polynomial exp, reciprocal-free log */
@@ -97,6 +98,13 @@ extern "C" void emu_selftest_so3(long long n, const double* v, const double* x, 
         pf_exp(v + 3 * i, 1.0, qf, slow);
         pf_log(qf, wf, slow);
         o[10] = wf[0], o[11] = wf[1], o[12] = wf[2], o[13] = slow ? 1.0 : 0.0;
+        /* the any-angle pair of the fast kernels, as the pair type they use */
+        D2 v2[3] = {D2(v[3 * i], -v[3 * i]), D2(v[3 * i + 1], -v[3 * i + 1]), D2(v[3 * i + 2], -v[3 * i + 2])}, q2[4], w2[3];
+        bool hard = false;
+        pf_exp_wide<D2>(v2, 1.0, q2, hard);
+        pf_log_wide<D2>(q2, w2);
+        o[14] = q2[0].a, o[15] = q2[1].a, o[16] = q2[2].a, o[17] = q2[3].a;
+        o[18] = w2[0].a, o[19] = w2[1].a, o[20] = hard ? 1.0 : w2[2].a;
     }
 }
 

@@ -1,7 +1,9 @@
 """The SO(3) exp / log kernels (csrc/so3.cuh: near-minimax polynomials inside their ranges, libm outside) and the
 Newton reciprocal / square root of csrc/simt.cuh against 50-digit mpmath values, over the whole range the filters can
 reach: rotation angles from 1e-12 to just below pi, across the polynomial boundaries (half angle 0.5 rad in exp, 33 degrees
-in log), and the fast kernels' own pair (degree-5 exp, reciprocal-free log) on its range of 0.58 rad.  CPU: the host build of the same source; GPU: ukfb_selftest_so3."""
+in log), the fast kernels' own pair (degree-5 exp, reciprocal-free log) on its range of 0.58 rad, and their any-angle pair
+(eighth-angle polynomial + three quaternion squarings; three quaternion square roots + the asin form) over all angles.
+CPU: the host build of the same source; GPU: ukfb_selftest_so3."""
 from __future__ import annotations
 
 import ctypes as C
@@ -52,6 +54,12 @@ def check(got, v, x):
     assert fast[ang < 0.57].all() and not fast[ang > 0.6].any()
     ef = np.abs(got[fast, 10:13] - ref[fast, 4:7]).max(axis=1) / ang[fast]
     assert ef.max() < 8e-16, f"fast log: {ef.max():.2e} at angle {ang[fast][ef.argmax()]}"
+    # the any-angle pair: every angle below pi (log(exp(v)) = v there), same conditioning near pi
+    ew = np.abs(got[:, 14:18] - ref[:, :4]).max(axis=1)
+    assert ew.max() < 2e-15, f"wide exp: {ew.max():.2e} at angle {ang[ew.argmax()]}"
+    lw = np.abs(got[:, 18:21] - ref[:, 4:7]).max(axis=1) / ang
+    boundw = 4e-15 * np.maximum(1.0, 0.2 / (np.pi - ang))
+    assert (lw < boundw).all(), f"wide log: {lw.max():.2e} at angle {ang[(lw / boundw).argmax()]}"
     for col, name in ((7, "rcp"), (8, "sqrt"), (9, "rsqrt")):
         rel = np.abs(got[:, col] / ref[:, col] - 1.0)
         assert rel.max() < 3e-16, f"{name}: {rel.max():.2e}"
@@ -63,7 +71,7 @@ def test_host_build_of_the_so3_kernels():
     lib = emu_lib.load()
     v, x = inputs()
     v, x = np.ascontiguousarray(v), np.ascontiguousarray(x)
-    out = np.empty((x.size, 14))
+    out = np.empty((x.size, 21))
     lib.emu_selftest_so3(C.c_longlong(x.size), v.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     check(out, v, x)
 
