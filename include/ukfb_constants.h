@@ -25,8 +25,13 @@
 #define UKFB_SO3_BOXPLUS_LEFT 1
 #endif
 
-/* ukfom::ukf::sigma_points_mean: loop `while (norm(mean_delta) > tol && ++i < max_it)`. */
+/* ukfom::ukf::sigma_points_mean: loop `while (norm(mean_delta) > tol && ++i < max_it)`.
+ * The tolerance is a recollection of the un-vendored slam/mtk like everything else in this file; it decides how many
+ * passes a mean takes (one at 1e-5 on the benchmark workload).  tools/bench_mean_tol.py builds engine and oracle with a
+ * tighter value to put the cost of a second pass on record (profiles/). */
+#ifndef UKFB_MEAN_TOL
 #define UKFB_MEAN_TOL 1e-5
+#endif
 #define UKFB_MEAN_MAX_IT 10000
 
 /* MTK::tolerance<double>() -- the floor on ||q.vec|| inside SO3::log (mtkmath.hpp). */

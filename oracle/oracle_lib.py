@@ -47,7 +47,7 @@ def load(variant: str = "left") -> C.CDLL:
             raise RuntimeError("oracle/_ref/libref.so is missing and /root/reference is not here to build it")
         path = REF_LIB
     else:
-        name = "liboracle.so" if variant == "left" else "liboracle_right.so"
+        name = {"left": "liboracle.so", "right": "liboracle_right.so", "tight": "liboracle_tight.so"}[variant]
         path = os.path.join(_DIR, "build", name)
         if not os.path.exists(path):
             build()

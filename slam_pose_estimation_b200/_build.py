@@ -30,12 +30,13 @@ def nvcc() -> str:
 
 
 def source_hash() -> str:
-    """sha256 (first 16 hex digits) of the kernel sources the library is built from: profiles/traffic.json is stamped
-    with it, so that ncu figures of an older kernel are not reported for a newer one"""
+    """sha256 (first 16 hex digits) of the KERNEL sources (csrc/*.cuh; the host side of the ABI in ukf_batch.cu does not
+    change what a kernel executes) the library is built from: profiles/traffic.json is stamped with it, so that ncu
+    figures of an older kernel are not reported for a newer one"""
     import hashlib
 
     h = hashlib.sha256()
-    for d in sorted(x for x in DEPS if x.endswith((".cu", ".cuh"))):
+    for d in sorted(x for x in DEPS if x.endswith(".cuh")):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(d.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]

@@ -366,3 +366,39 @@ def test_diagonal_noise_paths_equal_the_general_one(monkeypatch):
         x.set_process_noise(Qd)
         P.run_pose_c3(x, B, 4)
     P.assert_parity(0, e.get_state(), o.get_state(), tol=TOL, what="anisotropic diagonal Q")
+
+
+def check_not_spd_deferral(cls, kw):
+    """The one documented behavioural difference of the fast PoseUKF kernel (csrc/ukf_pose_fast.cuh, header of pf_update).
+    ukfom's update factorises Sigma - K S K^T in full inside apply_delta; the structured update needs only the six leading
+    columns of that factor and checks only their pivots.  An EXACT velocity measurement (R = 0) makes the velocity block of
+    the downdated covariance zero up to rounding: the oracle (the reference's sequence) flags NOT_SPD in that update and
+    leaves the mean alone; the fast kernel completes the update and flags the filter at its next factorisation -- the
+    following predict -- after which both hold a flagged, frozen filter."""
+    B = 6
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(cls, B, **kw)
+    z, _ = syn.pose_measurement(4, B, 1)
+    for x in (o, e):
+        x.predict_dt(0.01)
+        x.update(4, z, np.zeros((3, 3)))
+    assert (o.get_status() == 8).all()           # reference: at once
+    early = e.get_status()
+    assert ((early == 0) | (early == 8)).all()   # fast kernel: now (rounding made a leading pivot fail) or ...
+    for x in (o, e):
+        x.predict_dt(0.01)
+    assert (e.get_status() == 8).all() and (o.get_status() == 8).all()  # ... at the next factorisation, never later
+    frozen = e.get_state()
+    e.predict_dt(0.01)
+    assert np.array_equal(e.get_state()[0], frozen[0]) and np.array_equal(e.get_state()[1], frozen[1])
+    # a measurement that is merely very accurate is no such case: both integrate it and agree
+    o, e = P.make_pose(OracleBatch, B), P.make_pose(cls, B, **kw)
+    for x in (o, e):
+        x.predict_dt(0.01)
+        x.update(4, z, np.eye(3) * 1e-10)
+        x.predict_dt(0.01)
+    assert not o.get_status().any() and not e.get_status().any()
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=1e-9, what="very accurate velocity measurement")
+
+
+def test_fast_kernel_not_spd_deferral_is_one_factorisation():
+    check_not_spd_deferral(EmuBatch, dict(kernel="fast"))

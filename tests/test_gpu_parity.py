@@ -538,3 +538,12 @@ def test_streaming_calls_match_the_blocking_ones(Ukf):
     b.step(syn.DT, 8, zs[0].numpy(), R)
     a.step(syn.DT, 8, zs[0].numpy(), R)
     assert np.array_equal(a.get_state()[0], b.get_state()[0])
+
+
+@pytest.mark.gpu
+def test_fast_kernel_not_spd_deferral_is_one_factorisation():
+    """see tests/test_emu_lane_kernels.py::check_not_spd_deferral: the documented one-step deferral, on the device"""
+    from slam_pose_estimation_b200 import UkfBatch
+    from test_emu_lane_kernels import check_not_spd_deferral
+
+    check_not_spd_deferral(UkfBatch, {})
