@@ -77,6 +77,7 @@ constexpr int PF_LA = 0;
 constexpr int PF_LB = 72;
 constexpr int PF_PER_LANE = 108;
 constexpr double PF_PI2_GUARD = 9.0; /* trace(Sigma_ori) below this (< pi^2) makes (mu [+] L_j) [-] mu = L_j exact */
+constexpr double PF_PI2_COLUMN = 9.6; /* what that needs: every |L_ori[:, j]|^2 below pi^2 (checked out of line when the trace is not) */
 
 /* ---- branch-free SO(3) kernels: polynomial path only, `slow` collects range violations ------------------------ */
 UKFB_D void pf_exp(const double* v, double scale, double* q, bool& slow)
@@ -250,8 +251,14 @@ UKFB_D void quat_mul_conj(const D2* a, const B* b, D2* r)
  *        from the hardware reciprocal-square-root seed), which leaves a half angle <= pi / 16, then the reciprocal-free
  *        asin form of pf_log, times 8.
  * Against 50-digit values both are within 2e-15 of MTK's cos / sinc / atan expressions (tests/test_so3_kernels.py). */
+#ifndef UKFB_PF_WIDE_CALLS
+#define UKFB_PF_WIDE_CALLS 1
+#endif
 constexpr double PF_EXP_WIDE_X2 = 10.24; /* (half angle)^2 bound of pf_exp_wide: 3.2 rad */
-constexpr double PF_WIDE_TRACE = 1.0;    /* trace(Sigma_ori) above this (0.58 rad per axis): sigma points certainly outside the short polynomials */
+#ifndef UKFB_PF_WIDE_TRACE
+#define UKFB_PF_WIDE_TRACE 1.0
+#endif
+constexpr double PF_WIDE_TRACE = UKFB_PF_WIDE_TRACE;    /* trace(Sigma_ori) above this (0.58 rad per axis): sigma points certainly outside the short polynomials */
 #define UKFB_TPOLY6(C, v, v2) \
     tfma(tfma(C[6], v2, tfma(C[5], v, C[4])), (v2) * (v2), tfma(tfma(C[3], v, C[2]), v2, tfma(C[1], v, C[0])))
 UKFB_D bool all_le(double x, double lim) { return x <= lim; }
@@ -306,13 +313,58 @@ UKFB_D void pf_log_wide(const V* q, V* out)
     out[0] = sc * x, out[1] = sc * y, out[2] = sc * z;
 }
 
+/* The any-angle pair is only ever reached from the out-of-line instance, whose code the warps of an SM stream through
+ * the instruction cache at different places: one copy of each (a call) instead of one per use keeps that instance's
+ * footprint near the hot path's (profiles/r02_kernel_experiments.txt: instruction-fetch stalls). */
+template <class V> struct PfV3 { V v[3]; };
+template <class V> struct PfQ4 { V q[4]; bool hard; };
+#if UKFB_PF_WIDE_CALLS
+template <class V>
+UKFB_DNI PfQ4<V> pf_exp_wide_call(PfV3<V> v, double scale)
+{
+    PfQ4<V> r;
+    r.hard = false;
+    pf_exp_wide<V>(v.v, scale, r.q, r.hard);
+    return r;
+}
+template <class V>
+UKFB_DNI PfV3<V> pf_log_wide_call(PfQ4<V> q)
+{
+    PfV3<V> r;
+    pf_log_wide<V>(q.q, r.v);
+    return r;
+}
+template <class V>
+UKFB_D void pf_exp_wide_shared(const V* v, double scale, V* q, bool& hard)
+{
+    PfV3<V> a;
+    a.v[0] = v[0], a.v[1] = v[1], a.v[2] = v[2];
+    const PfQ4<V> r = pf_exp_wide_call<V>(a, scale);
+    q[0] = r.q[0], q[1] = r.q[1], q[2] = r.q[2], q[3] = r.q[3];
+    hard = hard || r.hard;
+}
+template <class V>
+UKFB_D void pf_log_wide_shared(const V* q, V* out)
+{
+    PfQ4<V> a;
+    a.q[0] = q[0], a.q[1] = q[1], a.q[2] = q[2], a.q[3] = q[3], a.hard = false;
+    const PfV3<V> r = pf_log_wide_call<V>(a);
+    out[0] = r.v[0], out[1] = r.v[1], out[2] = r.v[2];
+}
+#else
+template <class V>
+UKFB_D void pf_exp_wide_shared(const V* v, double scale, V* q, bool& hard) { pf_exp_wide<V>(v, scale, q, hard); }
+template <class V>
+UKFB_D void pf_log_wide_shared(const V* q, V* out) { pf_log_wide<V>(q, out); }
+#endif
+
 /* single values in the two instances of the structured code: the hot one (WIDE = false) uses the short polynomials and
  * flags a range exit, the out-of-line one (WIDE = true) the any-angle pair (`slow`: beyond even its range) */
 template <bool WIDE>
 UKFB_D void pf_exp1(const double* v, double scale, double* q, bool& slow)
 {
     if (WIDE)
-        pf_exp_wide<double>(v, scale, q, slow);
+        pf_exp_wide_shared<double>(v, scale, q, slow);
     else
         pf_exp(v, scale, q, slow);
 }
@@ -320,7 +372,7 @@ template <bool WIDE>
 UKFB_D void pf_log1(const double* q, double* out, bool& slow)
 {
     if (WIDE)
-        pf_log_wide<double>(q, out);
+        pf_log_wide_shared<double>(q, out);
     else
         pf_log(q, out, slow);
 }
@@ -379,6 +431,8 @@ UKFB_D void prefetch_next_wave(const StepParams& p, long long tile, int lane)
     if (p.acc_mu && o < TILE * 24) prefetch_l2(reinterpret_cast<const char*>(p.acc_mu + nb * 3) + o);
     if (F::KIND == 1 && p.gyro_mu && o < TILE * 24) prefetch_l2(reinterpret_cast<const char*>(p.gyro_mu + nb * 3) + o);
     if (p.do_update && p.z && o < TILE * 8 * p.z_stride) prefetch_l2(reinterpret_cast<const char*>(p.z + nb * p.z_stride) + o);
+    if (p.do_update && p.R && p.r_stride > 0 && o < TILE * 8 * p.r_stride) /* one measurement covariance per filter */
+        prefetch_l2(reinterpret_cast<const char*>(p.R + nb * p.r_stride) + o);
     if (p.do_predict && !p.time_mode && p.dt && o < TILE * 8 * p.dt_stride) prefetch_l2(reinterpret_cast<const char*>(p.dt + nb * p.dt_stride) + o);
 }
 
@@ -388,7 +442,7 @@ template <bool WIDE, class V>
 UKFB_D void pf_exp_t(const V* v, double scale, V* q, bool& flag)
 {
     if (WIDE)
-        pf_exp_wide<V>(v, scale, q, flag);
+        pf_exp_wide_shared<V>(v, scale, q, flag);
     else
         pf_exp(v, scale, q, flag);
 }
@@ -396,10 +450,11 @@ template <bool WIDE, class V>
 UKFB_D void pf_log_t(const V* q, V* out, bool& flag)
 {
     if (WIDE)
-        pf_log_wide<V>(q, out);
+        pf_log_wide_shared<V>(q, out);
     else
         pf_log(q, out, flag);
 }
+
 
 /* a pair of propagated sigma points: g(x) [-] ref for the position and orientation components (PoseUKF.cpp:75-83) */
 template <bool WIDE>
@@ -487,7 +542,10 @@ UKFB_D void pf_pair_d(const double* sm, int lane, int j, const double* delta, co
  * short polynomials.  The out-of-line instance (WIDE = true) picks per column: orientation entries this large go to the
  * any-angle pair at once; any other column (the position columns, the velocity / angular-velocity columns of a filter
  * that is unsure of its attitude only) tries the short polynomials first and is redone if a point left their range. */
-constexpr double PF_WIDE_COLUMN_N2 = 0.2; /* |L_ori[:, j]|^2 above this: do not bother with the short polynomials */
+#ifndef UKFB_PF_WIDE_COLUMN_N2
+#define UKFB_PF_WIDE_COLUMN_N2 0.2
+#endif
+constexpr double PF_WIDE_COLUMN_N2 = UKFB_PF_WIDE_COLUMN_N2; /* |L_ori[:, j]|^2 above this: do not bother with the short polynomials */
 template <bool WIDE>
 UKFB_D void pf_pair_a_sel(const double* sm, int lane, int j, const PoseMu& m, const double* vm, double dt, const double* ref_p,
                           const double* ref_q, double* L, double* dpl, double* dmi, bool& slow)
@@ -1321,6 +1379,33 @@ UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const
                 return r;
             }
             /* stage now tells where the structured code stopped */
+        }
+    }
+    if (stage == 0 && kind != UKFB_MEAS_POSE_ORIENTATION) {
+        /* sent here by the caller's trace guard, which bounds every |L_ori[:, j]| by sqrt(trace): sufficient, not necessary.
+         * What the structured update rests on, (mu [+] L_j) [-] mu = L_j, needs each column below pi, so look at the
+         * columns themselves (a filter that does not know its attitude at all: 1.8 rad and more per axis).  The prior
+         * covariance is in slots 0..77 and has been shown to be positive definite. */
+        double a[PoseF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < PoseF::LP; ++e) a[e] = UKFB_PS(e);
+        bool ok = pf_cholesky<6>(a);
+        UKFB_UNROLL
+        for (int j = 0; j < 6; ++j) {
+            double n2 = a[tri(5, j)] * a[tri(5, j)];
+            if (j <= 4) n2 += a[tri(4, j)] * a[tri(4, j)];
+            if (j <= 3) n2 += a[tri(3, j)] * a[tri(3, j)];
+            ok = ok && n2 < PF_PI2_COLUMN;
+        }
+        if (ok) {
+            PfLit r;
+            r.m = m, r.status = 0, r.passes = 0;
+            bool spd = true;
+            if (pf_update<false>(sm, lane, sig, kind, zm, Rm, r_ld, r.m, delta.d, r.status, r.passes, spd, gate_d2, stage)) {
+                if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+                return r;
+            }
+            /* stage 2: the downdate is done, apply_delta is next */
         }
     }
     if (stage == 2) { /* Sigma - K S K^T in the record, its factor columns in place, delta = K innov: apply_delta with the any-angle pair */

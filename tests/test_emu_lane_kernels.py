@@ -84,13 +84,13 @@ def test_not_spd_leaves_the_filter_untouched(kernel):
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_pose_large_angles_take_the_literal_expressions(kernel):
     """Orientation spread and rates far outside the ranges of the short polynomials (0.58 rad) and an orientation
-    variance beyond the selector-update guard.  The fast kernel redoes the COLUMNS whose sigma points leave the range with
+    column of the covariance factor beyond the selector-update guard (|L_ori[:, j]| next to pi).  The fast kernel redoes the COLUMNS whose sigma points leave the range with
     its any-angle exp / log (no literal predict any more), hands the lane behind the update guard to the literal code,
     and still agrees with the oracle."""
     B = 4
     mu, sg = syn.pose_initial(B)
     sg[0, 3:6, 3:6] *= 150.0  # sqrt(1.5) rad orientation sigma: exp and log leave the polynomial range
-    sg[1, 3:6, 3:6] *= 400.0  # trace 12 > 9: selector-update guard
+    sg[1, 5, 5] = 3.13**2  # a factor column at the branch cut of the SO(3) log: selector-update guard
     mu[2, 10:13] = [3.0, -40.0, 25.0]  # 47 rad/s: |w| dt = 0.94 rad with dt = 0.02 stays fast; with 0.05 it does not
     o, e = OracleBatch(0, B), EmuBatch(0, B, kernel=kernel)
     before = e.fallbacks()
@@ -109,12 +109,14 @@ def test_pose_large_angles_take_the_literal_expressions(kernel):
     assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
 
 
-@pytest.mark.parametrize("sig", [(0.7, 0.7, 0.7), (1.0, 1.0, 1.0), (1.6, 1.6, 1.6), (0.1, 0.1, 2.9)])
+@pytest.mark.parametrize("sig", [(0.7, 0.7, 0.7), (1.0, 1.0, 1.0), (1.6, 1.6, 1.6), (0.1, 0.1, 2.9), (2.0, 2.0, 2.0), (3.0, 3.0, 3.0),
+                                 (0.1, 0.1, 3.05)])
 def test_pose_wide_orientation_uncertainty_stays_in_the_fast_kernel(sig):
     """A filter that barely knows its attitude (or, last case, its heading: the usual start-up state): the sigma points
     of the orientation columns are radians apart.  The fast kernel keeps such filters -- no literal predict / update /
     apply_delta call -- by redoing those columns with its any-angle exp / log, and matches the oracle, the number of
-    mean passes included."""
+    mean passes included.  The last three have trace(Sigma_ori) >= 9, beyond the hot path's guard: the out-of-line code
+    looks at the columns of the factor themselves (each below pi) and still runs the structured update."""
     B = 8
     mu, sg = syn.pose_initial(B, perturb=True)
     sg[:, 3:6, 3:6] = np.diag(np.square(sig))
@@ -131,6 +133,25 @@ def test_pose_wide_orientation_uncertainty_stays_in_the_fast_kernel(sig):
     fb = e.fallbacks() - before
     assert not fb[:3].any(), f"literal fallbacks were taken: {fb}"
     assert fb[3] > 0 and fb[4] > 0, f"the any-angle columns were not exercised: {fb}"
+
+
+def test_pose_heading_uncertainty_at_the_branch_cut_runs_the_literal_update():
+    """A factor column within 0.04 rad of pi: (mu [+] L_j) [-] mu = L_j is no longer safe to assume, the literal update
+    (which forms the sigma points) serves the filter and matches the oracle."""
+    B = 8
+    mu, sg = syn.pose_initial(B, perturb=True)
+    sg[:, 3:6, 3:6] = np.diag(np.square((0.1, 0.1, 3.12)))
+    o, e = OracleBatch(0, B), EmuBatch(0, B, kernel="fast")
+    before = e.fallbacks()
+    for x in (o, e):
+        x.initialize(mu, sg)
+        for k in (1, 2):
+            z, R = syn.pose_measurement(8, B, k)
+            x.step(0.01, 8, z, R)
+    assert np.array_equal(e.get_status(), o.get_status())
+    P.assert_parity(0, e.get_state(), o.get_state(), tol=1e-11, what="heading sigma 3.12 rad")
+    fb = e.fallbacks() - before
+    assert fb[1] == 2 * B and fb[0] == 0, f"expected the literal update, the structured predict: {fb}"
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

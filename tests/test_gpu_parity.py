@@ -397,7 +397,8 @@ def test_pose_fast_kernel_fallback_lanes(Ukf):
     B = 64
     mu, sg = syn.pose_initial(B)
     sg[0::4, 3:6, 3:6] *= 150.0
-    sg[1::4, 3:6, 3:6] *= 400.0
+    sg[1::4, 3:6, 3:6] *= 400.0  # trace 12: the out-of-line column check keeps the structured update
+    sg[3::4, 5, 5] = 3.13**2  # a factor column next to pi: the literal update
     mu[2::4, 10:13] = [3.0, -40.0, 25.0]
     g, o = Ukf(0, B), OracleBatch(0, B)
     for x in (g, o):

@@ -99,13 +99,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--filters", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--sigmas", type=float, nargs="*", help="only these points of sweep (a), and no sweep (b)")
     args = ap.parse_args()
     B = args.filters
-    for s in (0.05, 0.1, 0.2, 0.3, 0.45, 0.6, 0.8, 1.0, 1.5, 2.0, 2.5, float(np.pi)):
+    for s in args.sigmas or (0.05, 0.1, 0.2, 0.3, 0.45, 0.6, 0.8, 1.0, 1.5, 2.0, 2.5, 3.0, float(np.pi)):
         r = run(B, s, args.steps, f"all filters sigma_ori = {s:.3f} rad")
         r["sigma_ori"] = s
         print(json.dumps(r), flush=True)
-    for frac in (0.0, 1 / 32, 1 / 8, 1 / 4, 1 / 2, 1.0):
+    for frac in () if args.sigmas else (0.0, 1 / 32, 1 / 8, 1 / 4, 1 / 2, 1.0):
         period = int(round(1 / frac)) if frac else 0
         sig = np.full(B, 0.1)
         if period:
