@@ -91,21 +91,22 @@ struct OriCtx {
     double omega[3], acc[3], earth[3];
 };
 
-/* one propagated sigma point (OrientationUKF.cpp:12-32): orientation and velocity deviations from the reference.
- * qs, vs: the point's orientation and velocity; wb = omega - bg, ab = acc - ba, gs = gravity of the point. */
-UKFB_D void of_point(const double* qs, const double* vs, const double* wb, const double* ab, double gs, const OriCtx& cx,
-                     const double* ref_q, const double* ref_v, double* d, bool& slow)
+/* a pair of propagated sigma points (OrientationUKF.cpp:12-32), the + and the - point of a column side by side (D2, as in
+ * ukf_pose_fast.cuh): orientation and velocity deviations from the reference.
+ * qs, vs: the points' orientation and velocity; wb = omega - bg, ab = acc - ba, gs = gravity of the points. */
+UKFB_D void of_point2(const D2* qs, const D2* vs, const D2* wb, const D2* ab, D2 gs, const OriCtx& cx, const double* ref_q,
+                      const double* ref_v, D2* d, bool& slow)
 {
-    double av[3], e[4], qn[4], an[3], r[4];
+    D2 av[3], e[4], qn[4], an[3], r[4];
     pf_rotate(qs, wb, av);
-    av[0] -= cx.earth[0], av[1] -= cx.earth[1], av[2] -= cx.earth[2];
+    av[0] = av[0] - cx.earth[0], av[1] = av[1] - cx.earth[1], av[2] = av[2] - cx.earth[2];
     pf_exp(av, cx.dt, e, slow);
     quat_mul(e, qs, qn);
     pf_rotate(qn, ab, an); /* with the UPDATED orientation (:22-23) */
-    an[2] -= gs;
-    d[3] = fma(cx.dt, an[0], vs[0]) - ref_v[0];
-    d[4] = fma(cx.dt, an[1], vs[1]) - ref_v[1];
-    d[5] = fma(cx.dt, an[2], vs[2]) - ref_v[2];
+    an[2] = an[2] - gs;
+    d[3] = tfma(cx.dt, an[0], vs[0]) - ref_v[0];
+    d[4] = tfma(cx.dt, an[1], vs[1]) - ref_v[1];
+    d[5] = tfma(cx.dt, an[2], vs[2]) - ref_v[2];
     quat_mul_conj(qn, ref_q, r);
     pf_log(r, d, slow);
 }
@@ -123,20 +124,19 @@ UKFB_D void of_pair_a(const double* sm, int lane, int j, const OriMu& m, const O
     const double t1 = e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
     const double t2 = e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
     const double t3 = -(e[0] * q[0] + e[1] * q[1] + e[2] * q[2]);
-    {
-        const double qs[4] = {fma(e[3], q[0], t0), fma(e[3], q[1], t1), fma(e[3], q[2], t2), fma(e[3], q[3], t3)};
-        const double vs[3] = {m.v[0] + L[3], m.v[1] + L[4], m.v[2] + L[5]};
-        const double wb[3] = {cx.omega[0] - (m.bg[0] + L[6]), cx.omega[1] - (m.bg[1] + L[7]), cx.omega[2] - (m.bg[2] + L[8])};
-        const double ab[3] = {cx.acc[0] - (m.ba[0] + L[9]), cx.acc[1] - (m.ba[1] + L[10]), cx.acc[2] - (m.ba[2] + L[11])};
-        of_point(qs, vs, wb, ab, m.g + L[12], cx, ref_q, ref_v, dpl, slow);
-    }
-    {
-        const double qs[4] = {fma(e[3], q[0], -t0), fma(e[3], q[1], -t1), fma(e[3], q[2], -t2), fma(e[3], q[3], -t3)};
-        const double vs[3] = {m.v[0] - L[3], m.v[1] - L[4], m.v[2] - L[5]};
-        const double wb[3] = {cx.omega[0] - (m.bg[0] - L[6]), cx.omega[1] - (m.bg[1] - L[7]), cx.omega[2] - (m.bg[2] - L[8])};
-        const double ab[3] = {cx.acc[0] - (m.ba[0] - L[9]), cx.acc[1] - (m.ba[1] - L[10]), cx.acc[2] - (m.ba[2] - L[11])};
-        of_point(qs, vs, wb, ab, m.g - L[12], cx, ref_q, ref_v, dmi, slow);
-    }
+    const D2 qs[4] = {D2(fma(e[3], q[0], t0), fma(e[3], q[0], -t0)), D2(fma(e[3], q[1], t1), fma(e[3], q[1], -t1)),
+                      D2(fma(e[3], q[2], t2), fma(e[3], q[2], -t2)), D2(fma(e[3], q[3], t3), fma(e[3], q[3], -t3))};
+    const D2 vs[3] = {D2(m.v[0] + L[3], m.v[0] - L[3]), D2(m.v[1] + L[4], m.v[1] - L[4]), D2(m.v[2] + L[5], m.v[2] - L[5])};
+    const D2 wb[3] = {D2(cx.omega[0] - (m.bg[0] + L[6]), cx.omega[0] - (m.bg[0] - L[6])),
+                      D2(cx.omega[1] - (m.bg[1] + L[7]), cx.omega[1] - (m.bg[1] - L[7])),
+                      D2(cx.omega[2] - (m.bg[2] + L[8]), cx.omega[2] - (m.bg[2] - L[8]))};
+    const D2 ab[3] = {D2(cx.acc[0] - (m.ba[0] + L[9]), cx.acc[0] - (m.ba[0] - L[9])),
+                      D2(cx.acc[1] - (m.ba[1] + L[10]), cx.acc[1] - (m.ba[1] - L[10])),
+                      D2(cx.acc[2] - (m.ba[2] + L[11]), cx.acc[2] - (m.ba[2] - L[11]))};
+    D2 d[6];
+    of_point2(qs, vs, wb, ab, D2(m.g + L[12], m.g - L[12]), cx, ref_q, ref_v, d, slow);
+    UKFB_UNROLL
+    for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
 }
 
 /* the +/- sigma points of a column 3 <= j < 9: orientation unperturbed.  Rm = R(q), w0 = R (omega - bg) - earth,
@@ -148,24 +148,24 @@ UKFB_D void of_pair_b(const double* sm, int lane, int j, const OriMu& m, const O
     for (int i = 0; i < 10; ++i) L[i] = UKFB_OS(OF_OB + (j - 3) * 10 + i);
     double u[3];
     pf_matvec(Rm, L + 3, u);
+    const D2 av[3] = {D2(w0[0] - u[0], w0[0] + u[0]), D2(w0[1] - u[1], w0[1] + u[1]), D2(w0[2] - u[2], w0[2] + u[2])};
+    D2 e[4], qn[4], r[4], an[3], d[6];
+    pf_exp(av, cx.dt, e, slow);
+    quat_mul(e, m.q, qn);
+    const D2 ab[3] = {D2(cx.acc[0] - (m.ba[0] + L[6]), cx.acc[0] - (m.ba[0] - L[6])),
+                      D2(cx.acc[1] - (m.ba[1] + L[7]), cx.acc[1] - (m.ba[1] - L[7])),
+                      D2(cx.acc[2] - (m.ba[2] + L[8]), cx.acc[2] - (m.ba[2] - L[8]))};
+    pf_rotate(qn, ab, an);
+    an[2] = an[2] - D2(m.g + L[9], m.g - L[9]);
+    d[3] = tfma(cx.dt, an[0], D2(m.v[0] + L[0], m.v[0] - L[0])) - ref_v[0];
+    d[4] = tfma(cx.dt, an[1], D2(m.v[1] + L[1], m.v[1] - L[1])) - ref_v[1];
+    d[5] = tfma(cx.dt, an[2], D2(m.v[2] + L[2], m.v[2] - L[2])) - ref_v[2];
+    quat_mul(e, c, r);
+    pf_log(r, d, slow);
     UKFB_UNROLL
-    for (int s = 0; s < 2; ++s) {
-        const double sg = s == 0 ? 1.0 : -1.0;
-        double* d = s == 0 ? dpl : dmi;
-        const double av[3] = {w0[0] - sg * u[0], w0[1] - sg * u[1], w0[2] - sg * u[2]};
-        double e[4], qn[4], r[4], an[3];
-        pf_exp(av, cx.dt, e, slow);
-        quat_mul(e, m.q, qn);
-        const double ab[3] = {cx.acc[0] - (m.ba[0] + sg * L[6]), cx.acc[1] - (m.ba[1] + sg * L[7]), cx.acc[2] - (m.ba[2] + sg * L[8])};
-        pf_rotate(qn, ab, an);
-        an[2] -= m.g + sg * L[9];
-        d[3] = fma(cx.dt, an[0], m.v[0] + sg * L[0]) - ref_v[0];
-        d[4] = fma(cx.dt, an[1], m.v[1] + sg * L[1]) - ref_v[1];
-        d[5] = fma(cx.dt, an[2], m.v[2] + sg * L[2]) - ref_v[2];
-        quat_mul(e, c, r);
-        pf_log(r, d, slow);
-    }
+    for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
 }
+
 
 /* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
 #ifdef UKFB_SIMT_EMU
@@ -366,6 +366,11 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
 
     /* ---- covariance: C = orientation/velocity block (21), X = cross block (rows 6..12 x columns 0..5) */
     const double cg = fma(dt, ma.neg_inv_tau_g, 1.0), ca = fma(dt, ma.neg_inv_tau_a, 1.0);
+    /* X = sum_j L[6:13, j] (d+_j - d-_j)^T is only partly accumulated point by point (as in ukf_pose_fast.cuh: 42 accumulators
+     * next to C and the per-filter context are more than the register file holds).  The differences of columns 0..2 go to the
+     * slots of rows 0..5 of their column, the orientation part of the differences of columns 3..8 to the three slots of their
+     * velocity rows (both consumed once the column's sigma points exist); only the velocity part of columns 3..8 is accumulated
+     * in the loop (Xv, 21 values), and X is formed after the loops from the factor rows still in place. */
     double C[21], X[42];
     {
         double d0[6], r[4];
@@ -377,8 +382,6 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
             UKFB_UNROLL
             for (int k = 0; k <= i; ++k) C[tri(i, k)] = d0[i] * d0[k];
         }
-        UKFB_UNROLL
-        for (int i = 0; i < 42; ++i) X[i] = 0.0;
         UKFB_NOUNROLL
         for (int j = 0; j < 3; ++j) {
             double L[13], dpl[6], dmi[6];
@@ -389,12 +392,11 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
                 for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
             }
             UKFB_UNROLL
-            for (int k = 0; k < 6; ++k) {
-                const double dd = dpl[k] - dmi[k];
-                UKFB_UNROLL
-                for (int i = 0; i < 7; ++i) X[i * 6 + k] = fma(L[6 + i], dd, X[i * 6 + k]);
-            }
+            for (int k = 0; k < 6; ++k) UKFB_OS(j * 13 + k) = dpl[k] - dmi[k];
         }
+        double Xv[21]; /* columns 3..8: sum_j L[6:13, j] (dv+_j - dv-_j)^T, the velocity part of their differences */
+        UKFB_UNROLL
+        for (int i = 0; i < 21; ++i) Xv[i] = 0.0;
         double c[4];
         quat_mul_conj(m.q, ref_q, c);
         UKFB_NOUNROLL
@@ -407,10 +409,42 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
                 for (int k = 0; k <= i; ++k) C[tri(i, k)] = fma(dpl[i], dpl[k], fma(dmi[i], dmi[k], C[tri(i, k)]));
             }
             UKFB_UNROLL
-            for (int k = 0; k < 6; ++k) {
-                const double dd = dpl[k] - dmi[k];
+            for (int k = 0; k < 3; ++k) UKFB_OS(OF_OB + (j - 3) * 10 + k) = dpl[k] - dmi[k];
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                const double dd = dpl[3 + k] - dmi[3 + k];
                 UKFB_UNROLL
-                for (int i = 0; i < 7; ++i) X[i * 6 + k] = fma(L[3 + i], dd, X[i * 6 + k]);
+                for (int i = 0; i < 7; ++i) Xv[i * 3 + k] = fma(L[3 + i], dd, Xv[i * 3 + k]);
+            }
+        }
+        /* X, after the loops */
+        UKFB_UNROLL
+        for (int i = 0; i < 7; ++i) {
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) X[i * 6 + k] = 0.0, X[i * 6 + 3 + k] = Xv[i * 3 + k];
+        }
+        UKFB_NOUNROLL
+        for (int j = 0; j < 3; ++j) {
+            double dd[6];
+            UKFB_UNROLL
+            for (int k = 0; k < 6; ++k) dd[k] = UKFB_OS(j * 13 + k);
+            UKFB_UNROLL
+            for (int i = 0; i < 7; ++i) {
+                const double l = UKFB_OS(j * 13 + 6 + i);
+                UKFB_UNROLL
+                for (int k = 0; k < 6; ++k) X[i * 6 + k] = fma(l, dd[k], X[i * 6 + k]);
+            }
+        }
+        UKFB_NOUNROLL
+        for (int j = 3; j < 9; ++j) {
+            double dd[3];
+            UKFB_UNROLL
+            for (int k = 0; k < 3; ++k) dd[k] = UKFB_OS(OF_OB + (j - 3) * 10 + k);
+            UKFB_UNROLL
+            for (int i = 0; i < 7; ++i) {
+                const double l = UKFB_OS(OF_OB + (j - 3) * 10 + 3 + i);
+                UKFB_UNROLL
+                for (int k = 0; k < 3; ++k) X[i * 6 + k] = fma(l, dd[k], X[i * 6 + k]);
             }
         }
         /* columns 9..12: orientation deviation d0, velocity deviation d0 -+ wv, wv = dt (R' L_ba + L_g e3) */
