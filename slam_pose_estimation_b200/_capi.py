@@ -83,6 +83,7 @@ SIGNATURES = {
     "ukfb_event_record": (I, [P, I]),
     "ukfb_event_elapsed_ms": (I, [P, I, I, C.POINTER(C.c_float)]),
     "ukfb_launch_count": (L, [P]),
+    "ukfb_overlapped_launch_count": (L, [P]),
     "ukfb_measure_fp64_peak": (I, [P, C.POINTER(D)]),
     "ukfb_selftest_so3": (I, [P, L, P, P, P]),
 }

@@ -422,6 +422,10 @@ class UkfBatch:
     def launch_count(self) -> int:
         return int(self.lib.ukfb_launch_count(self.h))
 
+    def overlapped_launch_count(self) -> int:
+        """how many of those were ordered tile by tile against their predecessor instead of launch by launch"""
+        return int(self.lib.ukfb_overlapped_launch_count(self.h))
+
     def selftest_so3(self, v, x):
         """device exp / log / reciprocal / sqrt of csrc/so3.cuh and simt.cuh on n inputs -> (n, 21), see the header"""
         v, pv = _host(v, np.float64)

@@ -47,6 +47,29 @@ UKFB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];"
 /* value of `v` held by lane `src` (all 32 lanes must call) */
 UKFB_D double warp_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+/* Programmatic dependent launch: the next kernel of the stream (if it was launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization) may be scheduled once every block of this grid has issued this or
+ * exited -- i.e. into the slots the grid's last, partial wave leaves empty.  Ordering of the DATA is then the kernels' own
+ * business: tile_done_add / tile_done_wait below. */
+UKFB_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+/* every lane of the warp that owned a tile in a launch adds 1 to the tile's counter once its stores are issued (release);
+ * every lane of the warp that owns it in the next launch waits until the counter shows all 32 (acquire): one
+ * release/acquire pair per lane pair through the read-modify-write chain on the counter */
+UKFB_D void tile_done_add(unsigned long long* counter)
+{
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ull) : "memory");
+}
+UKFB_D void tile_done_wait(const unsigned long long* counter, unsigned long long need)
+{
+    unsigned long long v;
+    for (unsigned spins = 0;; ++spins) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        if (v >= need) break;
+        if (spins > 40000000u) __trap(); /* ~10 s: the previous launch never finished this tile -- fail, do not hang */
+        __nanosleep(200);
+    }
+}
+
 /* C(8x8) += A(8x4) * B(4x8) on the FP64 tensor-core path.  Fragment layout (PTX m8n8k4.f64):
  * lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4)] and C[l/4][2*(l%4)+1]. */
 UKFB_D void warp_dmma(double& c0, double& c1, double a, double b)
@@ -116,6 +139,13 @@ using std::fabs;
 using std::fma;
 using std::sqrt;
 inline void prefetch_l2(const void*) {}
+inline void pdl_launch_dependents() {}
+inline void tile_done_add(unsigned long long* counter) { __atomic_fetch_add(counter, 1ull, __ATOMIC_RELEASE); }
+inline void tile_done_wait(const unsigned long long* counter, unsigned long long need)
+{
+    while (__atomic_load_n(counter, __ATOMIC_ACQUIRE) < need) {
+    }
+}
 inline void ukfb_sincos(double x, double* s, double* c)
 {
     *s = std::sin(x);

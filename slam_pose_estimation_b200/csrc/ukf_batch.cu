@@ -98,7 +98,12 @@ struct ukfb_handle {
     struct FastCfg {
         bool attr_set = false;
         long long prefetch_tiles = -1; /* -1 = not computed yet */
+        long long resident_warps = 0;  /* of this kernel on the device (occupancy API) */
     } fast_cfg[2];
+    /* consecutive launches of the fast kernels overlap at their ends (StepParams::tile_done): one counter per tile and the
+     * number of fast launches made on this handle so far */
+    unsigned long long* tile_done = nullptr;
+    unsigned long long fast_launches = 0;
     /* sharded parent (ukfb_create_sharded): owns no device memory itself; shard i = filters first[i] .. first[i + 1] */
     std::vector<ukfb_handle*> shards;
     std::vector<long long> first;
@@ -497,6 +502,9 @@ struct EnvKnobs {
     long smem_pad_kb;          /* UKFB_SMEM_PAD_KB: unused dynamic shared memory per block (occupancy experiments) */
     int prefetch_bytes;        /* UKFB_PREFETCH_BYTES: request granularity of the next-wave prefetch (one L2 line) */
     long long prefetch_tiles;  /* UKFB_PREFETCH_TILES: forced prefetch distance, -1 = from the occupancy API, 0 = off */
+    bool overlap;              /* UKFB_OVERLAP_LAUNCHES=0: every fast-kernel launch waits for the whole previous one */
+    int overlap_max_waves;     /* UKFB_OVERLAP_MAX_WAVES: overlap launches of grids up to this many waves of resident warps (12) */
+    int overlap_min_waves_pct; /* UKFB_OVERLAP_MIN_WAVES_PCT: ... and of more than this many hundredths of a wave (100) */
     EnvKnobs()
     {
         const char* e = getenv("UKFB_FAST_WPB");
@@ -508,6 +516,12 @@ struct EnvKnobs {
         prefetch_bytes = e && atoi(e) >= 8 ? atoi(e) : UKFB_DEFAULT_PREFETCH_BYTES;
         e = getenv("UKFB_PREFETCH_TILES");
         prefetch_tiles = e ? atoll(e) : -1;
+        e = getenv("UKFB_OVERLAP_LAUNCHES");
+        overlap = e ? atoi(e) != 0 : true;
+        e = getenv("UKFB_OVERLAP_MAX_WAVES");
+        overlap_max_waves = e && atoi(e) > 0 ? atoi(e) : 12;
+        e = getenv("UKFB_OVERLAP_MIN_WAVES_PCT");
+        overlap_min_waves_pct = e ? atoi(e) : 100;
     }
 };
 static const EnvKnobs& knobs()
@@ -570,14 +584,16 @@ static cudaError_t launch_thread_f(const ukfb_handle* h, const StepParams& p)
     return cudaGetLastError();
 }
 
+/* kernel: the plain instance; kernel_overlap: the one whose launches overlap at their ends (chosen per handle, below) */
 template <class K>
-static cudaError_t launch_fast(K kernel, int per_lane, ukfb_handle* h, const StepParams& p, ukfb_handle::FastCfg& cfg)
+static cudaError_t launch_fast(K kernel, K kernel_overlap, int per_lane, ukfb_handle* h, const StepParams& p, ukfb_handle::FastCfg& cfg)
 {
     const EnvKnobs& kn = knobs();
     const int wpb = kn.fast_wpb;
     const size_t smem = sizeof(double) * per_lane * TILE * wpb + size_t(kn.smem_pad_kb) * 1024;
     if (!cfg.attr_set) {
         cudaError_t e = ensure_smem_attr(kernel, h->device, smem);
+        if (e == cudaSuccess) e = ensure_smem_attr(kernel_overlap, h->device, smem);
         if (e != cudaSuccess) return e;
         cfg.attr_set = true;
     }
@@ -588,32 +604,59 @@ static cudaError_t launch_fast(K kernel, int per_lane, ukfb_handle* h, const Ste
      * flat optimum from 32 to 444 tiles with 1184 resident warps, -2 % at 888, no gain from 1184 on;
      * UKFB_PREFETCH_TILES overrides, 0 = off), request granularity UKFB_PREFETCH_BYTES (one L2 line) */
     if (cfg.prefetch_tiles < 0) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE * wpb, smem) != cudaSuccess) per_sm = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) sms = 0;
+        cfg.resident_warps = (long long)per_sm * wpb * sms;
         long long r = kn.prefetch_tiles;
         if (r < 0) {
-            int per_sm = 0, sms = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE * wpb, smem) != cudaSuccess) per_sm = 0;
-            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) sms = 0;
-            r = (long long)per_sm * wpb * sms / 4;
+            r = cfg.resident_warps / 4;
             if (r < 32 && per_sm > 0) r = 32;
         }
         cfg.prefetch_tiles = r > 0 ? r : 0;
     }
     q.prefetch_tiles = cfg.prefetch_tiles;
     q.prefetch_bytes = kn.prefetch_bytes;
-    kernel<<<unsigned(grid), TILE * wpb, smem, h->stream>>>(q);
+    /* Launch number n of this handle's fast kernels waits, tile by tile, for launch n - 1 (tile_done), so the stream need not
+     * hold it back until the whole of n - 1 has drained: with programmatic stream serialization its blocks are scheduled as
+     * soon as every block of n - 1 has started, i.e. into the slots the last, partial wave of n - 1 leaves empty.
+     * The handshake costs every warp an L2 round trip before its first load and a fence after its last store (measured: 3 %
+     * of a step), the overlap recovers about half a wave plus the launch gap: it pays for grids of a few waves (a shard of
+     * 128 Ki filters: +9 %, 256 Ki: +4 %) and not for many (1 Mi filters, 28 waves: -2 %), and the blocks of a grid of
+     * less than one wave would all be resident, waiting.  The batch size of a handle is fixed, so a handle either always
+     * or never launches this way.  Whatever else is in the stream (copies, the pack / unpack kernels, another kernel
+     * family) keeps full stream order on both sides. */
+    const bool overlap = kn.overlap && cfg.resident_warps > 0 && grid * wpb * 100 > kn.overlap_min_waves_pct * cfg.resident_warps &&
+                         grid * wpb <= kn.overlap_max_waves * cfg.resident_warps;
+    q.tile_done = overlap ? h->tile_done : nullptr;
+    q.launch_seq = h->fast_launches + 1;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(unsigned(grid));
+    lc.blockDim = dim3(TILE * wpb);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = overlap ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&lc, overlap ? kernel_overlap : kernel, q);
+    if (e != cudaSuccess) return e;
+    if (overlap) h->fast_launches++; /* only a launch that was made adds to the counters */
     return cudaGetLastError();
 }
 
 static cudaError_t launch_pose_fast(ukfb_handle* h, const StepParams& p, bool may_have_orientation_meas)
 {
-    if (may_have_orientation_meas) return launch_fast(ukf_pose_fast_kernel<true>, PF_PER_LANE, h, p, h->fast_cfg[1]);
-    return launch_fast(ukf_pose_fast_kernel<false>, PF_PER_LANE, h, p, h->fast_cfg[0]);
+    if (may_have_orientation_meas) return launch_fast(ukf_pose_fast_kernel<true, false>, ukf_pose_fast_kernel<true, true>, PF_PER_LANE, h, p, h->fast_cfg[1]);
+    return launch_fast(ukf_pose_fast_kernel<false, false>, ukf_pose_fast_kernel<false, true>, PF_PER_LANE, h, p, h->fast_cfg[0]);
 }
 
 static cudaError_t launch_ori_fast(ukfb_handle* h, const StepParams& p)
 {
-    if (p.ori_params) return launch_fast(ukf_ori_fast_kernel<true>, OF_PER_LANE, h, p, h->fast_cfg[1]);
-    return launch_fast(ukf_ori_fast_kernel<false>, OF_PER_LANE, h, p, h->fast_cfg[0]);
+    if (p.ori_params) return launch_fast(ukf_ori_fast_kernel<true, false>, ukf_ori_fast_kernel<true, true>, OF_PER_LANE, h, p, h->fast_cfg[1]);
+    return launch_fast(ukf_ori_fast_kernel<false, false>, ukf_ori_fast_kernel<false, true>, OF_PER_LANE, h, p, h->fast_cfg[0]);
 }
 
 static int launch_step(ukfb_handle* h, const StepParams& p)
@@ -733,6 +776,8 @@ extern "C" int ukfb_create(int filter_kind, int64_t batch, int device, ukfb_hand
     CUH(cudaMalloc(&h->acc_cov, sizeof(double) * B * 9));
     CUH(cudaMalloc(&h->gyro_mu, sizeof(double) * B * 3));
     CUH(cudaMalloc(&h->summary, sizeof(long long) * 2));
+    CUH(cudaMalloc(&h->tile_done, sizeof(unsigned long long) * (Bpad / TILE)));
+    CUH(cudaMemsetAsync(h->tile_done, 0, sizeof(unsigned long long) * (Bpad / TILE), h->stream));
     CUH(cudaMemsetAsync(h->state, 0, sizeof(double) * Bpad * h->REC, h->stream));
     CUH(cudaMemsetAsync(h->status, 0, sizeof(uint32_t) * B, h->stream));
     CUH(cudaMemsetAsync(h->t_last, 0, sizeof(long long) * B, h->stream));
@@ -842,7 +887,7 @@ extern "C" int ukfb_destroy(ukfb_handle* h)
     }
     Bind bind_(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist);
+    cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist), cudaFree(h->tile_done);
     cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary), cudaFree(h->ori_params);
     for (int k = 0; k < UKFB_MEAS_KIND_COUNT; ++k) cudaFree(h->meas_cov[k]);
     for (int i = 0; i < 16; ++i)
@@ -1995,6 +2040,14 @@ extern "C" int64_t ukfb_launch_count(const ukfb_handle* h)
     if (!h) return 0;
     long long n = h->launches;
     for (const ukfb_handle* s : h->shards) n += s->launches;
+    return n;
+}
+
+extern "C" int64_t ukfb_overlapped_launch_count(const ukfb_handle* h)
+{
+    if (!h) return 0;
+    long long n = (long long)h->fast_launches;
+    for (const ukfb_handle* s : h->shards) n += (long long)s->fast_launches;
     return n;
 }
 

@@ -154,6 +154,11 @@ struct StepParams {
      * configuration): only its diagonal is loaded; 2 = moreover entries 0..2 are equal and entries 3..5 are equal, so the
      * two blocks the filters rotate into the navigation frame (R Q_blk R^T) are multiples of the identity and stay so */
     int q_diagonal;
+    /* fast kernels: launches of one handle may overlap (the next launch starts in the slots this one's last wave leaves
+     * empty: simt.cuh, pdl_launch_dependents).  tile_done[t] counts the lanes that have finished tile t, 32 per launch;
+     * the warp that owns tile t in launch number `launch_seq` (1, 2, ...) first waits for 32 (launch_seq - 1).  Null: off. */
+    unsigned long long* tile_done;
+    unsigned long long launch_seq;
 };
 
 UKFB_HD int meas_dim(int kind)

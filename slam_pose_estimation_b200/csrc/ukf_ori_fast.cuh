@@ -853,7 +853,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
 /* PER_FILTER_PARAMS = false: time constants and earth rotation are launch constants (constant-bank operands, no
  * registers); true: each filter's own set is loaded (ukfb_set_orientation_params_per_filter).  Two instances because the
  * ten extra live registers cost the common case 3 %. */
-template <bool PER_FILTER_PARAMS>
+template <bool PER_FILTER_PARAMS, bool OVERLAP = false> /* OVERLAP: as in ukf_pose_fast_kernel */
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef OriF F;
@@ -863,7 +863,11 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     double* sm = ukfb_smem + wib * (OF_PER_LANE * TILE);
+    /* overlapped launches (StepParams::tile_done): the next launch may take the slots this grid's last wave leaves empty,
+     * and every warp waits for its own tile of the previous launch */
+    if (OVERLAP) pdl_launch_dependents();
     if (tile * TILE >= p.B) return; /* a warp past the last tile (no barriers in this kernel) */
+    if (OVERLAP) tile_done_wait(p.tile_done + tile, 32ull * (p.launch_seq - 1));
     const long long b = tile * TILE + lane;
     const bool valid = b < p.B;
     const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
@@ -1095,6 +1099,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
         for (int k = 1; k < 8; ++k)
             if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);
     }
+    if (OVERLAP) tile_done_add(p.tile_done + tile); /* everything this lane stores for the tile has been issued */
 }
 
 #undef UKFB_OS

@@ -1425,7 +1425,9 @@ UKFB_DNI PfLit pf_update_slow(double* sm, int lane, double* sig, int kind, const
  * kind other than 3): an orientation measurement would run the literal code.  WITH_ORI = true: its structured instance
  * is compiled into the slow-path call; the larger callee costs the hot path about 3 % (register allocation around the
  * call), which is why there are two instances. */
-template <bool WITH_ORI>
+/* OVERLAP = true: the instance for handles whose launches overlap at their ends (StepParams::tile_done).  A separate
+ * instance because the handshake code costs the other one 1.8 % even when it is skipped at run time. */
+template <bool WITH_ORI, bool OVERLAP = false>
 UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf_pose_fast_kernel(const UKFB_GRID_CONSTANT StepParams p)
 {
     typedef PoseF F;
@@ -1435,7 +1437,11 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     double* sm = ukfb_smem + wib * (PF_PER_LANE * TILE);
+    /* overlapped launches (StepParams::tile_done): the next launch may take the slots this grid's last wave leaves empty,
+     * and every warp waits for its own tile of the previous launch */
+    if (OVERLAP) pdl_launch_dependents();
     if (tile * TILE >= p.B) return; /* a warp past the last tile (no barriers in this kernel) */
+    if (OVERLAP) tile_done_wait(p.tile_done + tile, 32ull * (p.launch_seq - 1));
     const long long b = tile * TILE + lane;
     const bool valid = b < p.B;
     const long long bb = valid ? b : p.B - 1; /* lanes past the end shadow the last filter and never store */
@@ -1658,6 +1664,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(UKFB_PF_MAX_THREADS, UKFB_PF_MIN_BLOCKS) ukf
         for (int k = 1; k < 8; ++k)
             if (hist[k]) atomicAdd(hs + k, (unsigned long long)hist[k]);
     }
+    if (OVERLAP) tile_done_add(p.tile_done + tile); /* everything this lane stores for the tile has been issued */
 }
 
 #undef UKFB_PS

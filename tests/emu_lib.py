@@ -35,6 +35,7 @@ class StepParams(C.Structure):
         ("tick_kinds", C.c_void_p), ("imu", C.c_void_p), ("imu_kstride", C.c_longlong),
         ("events", C.c_int), ("r_kind_stride", C.c_longlong), ("gate_d2", C.c_double),
         ("ori_params", C.c_void_p), ("prefetch_tiles", C.c_longlong), ("prefetch_bytes", C.c_int), ("q_diagonal", C.c_int),
+        ("tile_done", C.c_void_p), ("launch_seq", C.c_ulonglong),
     ]
 
 
@@ -94,6 +95,8 @@ class EmuBatch:
         self._first_init = True
         self.gate_d2 = np.inf
         self.ori_params = None
+        self.tile_done = np.zeros(self.Bpad // 32, np.uint64)  # fast kernels: lanes finished per tile, 32 per launch
+        self.fast_launches = 0
 
     def initialize(self, mu, sigma):
         mu = np.asarray(mu, float).reshape(self.B, self.MU)
@@ -185,6 +188,10 @@ class EmuBatch:
         if self.tiled:  # [tile][entry][lane] in memory
             dev = np.ascontiguousarray(self.state.reshape(-1, 32, self.REC).transpose(0, 2, 1))
             p.state = _ptr(dev)
+            if self.fast:  # as the engine launches them: each launch waits, tile by tile, for the one before
+                p.tile_done = _ptr(self.tile_done)
+                self.fast_launches += 1
+                p.launch_seq = self.fast_launches
             if self.fast and self.kind == 1:
                 rc = self.lib.emu_ori_fast_step(C.byref(p))
             elif self.fast:
@@ -192,6 +199,8 @@ class EmuBatch:
             else:
                 rc = self.lib.emu_thread_step(C.c_int(self.kind), C.byref(p))
             self.state[:] = dev.transpose(0, 2, 1).reshape(self.Bpad, self.REC)
+            if self.fast:
+                assert (self.tile_done == 32 * self.fast_launches).all(), "a lane did not report its tile done"
         else:
             rc = self.lib.emu_step(C.c_int(self.kind), C.c_int(self.G), C.byref(p))
         assert rc == 0

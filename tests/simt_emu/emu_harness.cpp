@@ -55,7 +55,7 @@ extern "C" int emu_thread_step(int filter_kind, const StepParams* p)
 extern "C" int emu_pose_fast_step(const StepParams* p)
 {
     const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
-    simt_emu::launch(ukf_pose_fast_kernel<true>, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
+    simt_emu::launch(p->tile_done ? ukf_pose_fast_kernel<true, true> : ukf_pose_fast_kernel<true, false>, grid, TILE, sizeof(double) * PF_PER_LANE * TILE, *p);
     return 0;
 }
 
@@ -69,9 +69,9 @@ extern "C" int emu_ori_fast_step(const StepParams* p)
 {
     const unsigned grid = unsigned((p->B + TILE - 1) / TILE);
     if (p->ori_params)
-        simt_emu::launch(ukf_ori_fast_kernel<true>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
+        simt_emu::launch(p->tile_done ? ukf_ori_fast_kernel<true, true> : ukf_ori_fast_kernel<true, false>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
     else
-        simt_emu::launch(ukf_ori_fast_kernel<false>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
+        simt_emu::launch(p->tile_done ? ukf_ori_fast_kernel<false, true> : ukf_ori_fast_kernel<false, false>, grid, TILE, sizeof(double) * OF_PER_LANE * TILE, *p);
     return 0;
 }
 

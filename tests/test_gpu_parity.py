@@ -548,3 +548,64 @@ def test_fast_kernel_not_spd_deferral_is_one_factorisation():
     from test_emu_lane_kernels import check_not_spd_deferral
 
     check_not_spd_deferral(UkfBatch, {})
+
+
+@pytest.mark.parametrize("filt", [0, 1])
+def test_overlapped_launches_equal_launches_in_stream_order(Ukf, filt):
+    """A handle whose batch is a few waves of warps orders its step launches tile by tile (launch n starts in the slots
+    the last wave of launch n - 1 leaves empty: include/ukf_batch.h, ukfb_overlapped_launch_count).  64 Ki filters are 1.7
+    waves on a B200; its two halves, one handle each, are less than a wave and launch in plain stream order.  Same device
+    inputs, launches back to back: the results must be equal bit for bit, and match the oracle on a sample."""
+    import torch
+
+    B, H, K = 65536, 32768, 12
+    dev = torch.device("cuda", 0)
+    mu, sg = syn.pose_initial(B) if filt == 0 else syn.orientation_initial(B)
+    whole, halves = Ukf(filt, B), [Ukf(filt, H), Ukf(filt, H)]
+    objs = [(whole, slice(0, B))] + [(h, slice(i * H, (i + 1) * H)) for i, h in enumerate(halves)]
+    d_dt = torch.full((1,), syn.DT, dtype=torch.float64, device=dev)
+    for x, sl in objs:
+        x.initialize(mu[sl], sg[sl])
+        if filt == 1:
+            x.set_process_noise(syn.ORI_Q)
+            x.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+    if filt == 0:
+        zs = [syn.pose_measurement(8, B, k + 1) for k in range(K)]
+        for x, sl in objs:
+            d_z = [torch.from_numpy(np.ascontiguousarray(z[sl])).to(dev) for z, _ in zs]
+            d_R = torch.from_numpy(zs[0][1]).to(dev)
+            torch.cuda.synchronize()
+            for k in range(K):  # nothing but step launches in the stream
+                x.step_dev(d_dt, False, 8, d_z[k], d_R, False)
+            x.synchronize()
+    else:
+        imu = np.stack([np.concatenate(syn.orientation_imu(B, k + 1), axis=1) for k in range(K)])  # K x B x 6
+        for x, sl in objs:
+            d_imu = torch.from_numpy(np.ascontiguousarray(imu[:, sl])).to(dev)
+            torch.cuda.synchronize()
+            d_dt3 = torch.full((3,), syn.DT, dtype=torch.float64, device=dev)
+            for k in range(0, K, 3):  # launches of three ticks each
+                x.run_dev(3, d_dt3, False, d_imu=d_imu[k:k + 3])
+            x.synchronize()
+    n_launches = K if filt == 0 else K // 3
+    assert whole.overlapped_launch_count() == n_launches, "the 64 Ki handle did not overlap its launches (not a B200?)"
+    assert halves[0].overlapped_launch_count() == 0
+    m, s = whole.get_state()
+    for h, (_, sl) in zip(halves, objs[1:]):
+        mh, sh = h.get_state()
+        assert np.array_equal(m[sl], mh) and np.array_equal(s[sl], sh)
+    assert not whole.get_status().any()
+    idx = np.arange(0, B, B // 16)
+    o = OracleBatch(filt, idx.size)
+    o.initialize(mu[idx], sg[idx])
+    if filt == 0:
+        for k in range(K):
+            o.step(syn.DT, 8, zs[k][0][idx], zs[k][1])
+    else:
+        o.set_process_noise(syn.ORI_Q)
+        o.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+        for k in range(K):
+            o.set_rotation_rate(imu[k, idx, 0:3])
+            o.set_acceleration(imu[k, idx, 3:6])
+            o.predict_dt(syn.DT)
+    P.assert_parity(filt, (m[idx], s[idx]), o.get_state(), what="overlapped launches")
