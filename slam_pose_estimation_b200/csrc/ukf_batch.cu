@@ -104,6 +104,11 @@ struct ukfb_handle {
      * number of fast launches made on this handle so far */
     unsigned long long* tile_done = nullptr;
     unsigned long long fast_launches = 0;
+    /* ukfb_run_dev: the K tick kinds of the last call, on the device and on the host -- a caller streaming launches with the
+     * same schedule then puts nothing but kernels into the stream (a copy between two launches is a full ordering point) */
+    int8_t* tick_kinds_dev = nullptr;
+    size_t tick_kinds_cap = 0;
+    std::vector<int8_t> tick_kinds_last;
     /* sharded parent (ukfb_create_sharded): owns no device memory itself; shard i = filters first[i] .. first[i + 1] */
     std::vector<ukfb_handle*> shards;
     std::vector<long long> first;
@@ -887,7 +892,7 @@ extern "C" int ukfb_destroy(ukfb_handle* h)
     }
     Bind bind_(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist), cudaFree(h->tile_done);
+    cudaFree(h->state), cudaFree(h->Q), cudaFree(h->status), cudaFree(h->t_last), cudaFree(h->hist), cudaFree(h->tile_done), cudaFree(h->tick_kinds_dev);
     cudaFree(h->acc_mu), cudaFree(h->acc_cov), cudaFree(h->gyro_mu), cudaFree(h->stage), cudaFree(h->summary), cudaFree(h->ori_params);
     for (int k = 0; k < UKFB_MEAS_KIND_COUNT; ++k) cudaFree(h->meas_cov[k]);
     for (int i = 0; i < 16; ++i)
@@ -1748,12 +1753,24 @@ extern "C" int ukfb_run_dev(ukfb_handle* h, int K, const double* d_dt, int dt_pe
     p.dt_stride = dt_per_filter ? 1 : 0;
     p.dt_kstride = dt_per_filter ? h->B : 1;
     if (any) {
-        /* the K tick kinds ride in a small device array owned by the handle's staging tail */
-        int rc = stage_reserve(h, align256(size_t(K)));
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(h->stage, kinds_host, size_t(K), cudaMemcpyHostToDevice, h->stream));
+        /* the K tick kinds ride in a small device array of the handle, rewritten only when the schedule changes */
+        if (h->tick_kinds_cap < size_t(K)) {
+            CU(cudaStreamSynchronize(h->stream));
+            if (h->tick_kinds_dev) CU(cudaFree(h->tick_kinds_dev));
+            h->tick_kinds_dev = nullptr, h->tick_kinds_cap = 0;
+            h->tick_kinds_last.clear();
+            const size_t want = align256(size_t(K));
+            cudaError_t e = cudaMalloc(&h->tick_kinds_dev, want);
+            if (e != cudaSuccess) return fail(UKFB_ERR_NOMEM, "tick kinds of %zu bytes: %s", want, cudaGetErrorString(e));
+            h->tick_kinds_cap = want;
+        }
+        if (h->tick_kinds_last.size() != size_t(K) || memcmp(h->tick_kinds_last.data(), kinds_host, size_t(K)) != 0) {
+            h->tick_kinds_last.assign(kinds_host, kinds_host + K);
+            /* from the handle's own copy: it stays unchanged until the next call replaces it, after this copy in stream order */
+            CU(cudaMemcpyAsync(h->tick_kinds_dev, h->tick_kinds_last.data(), size_t(K), cudaMemcpyHostToDevice, h->stream));
+        }
         p.do_update = 1;
-        p.tick_kinds = reinterpret_cast<const int8_t*>(h->stage);
+        p.tick_kinds = h->tick_kinds_dev;
         p.z = d_mu3;
         p.z_stride = 3;
         p.z_kstride = h->B * 3;

@@ -23,7 +23,7 @@ def parse(path):
         m = re.search(name + r" \[(\w+)\] = ([0-9.]+)", t)
         return float(m.group(2)) * unit[m.group(1)]
     m = re.search(r"dadd (\d+) dmul (\d+) dfma (\d+)\s+= (\d+) instr, (\d+) flops", t)
-    return {"kernel": re.search(r"kernel: void (\S+)\(", t).group(1), "dram_bytes_read_per_launch": int(bytes_(r"dram__bytes_read\.sum")),
+    return {"kernel": re.search(r"kernel: void (.+?)\(", t).group(1), "dram_bytes_read_per_launch": int(bytes_(r"dram__bytes_read\.sum")),
             "dram_bytes_write_per_launch": int(bytes_(r"dram__bytes_write\.sum")), "fp64_instructions": int(m.group(4)),
             "fp64_flops": int(m.group(5)),
             "fp64_pipe_active_pct": num(r"sm__pipe_fp64_cycles_active\.avg\.pct_of_peak_sustained_active \[%\] = ([0-9.]+)"),
