@@ -47,6 +47,10 @@ UKFB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];"
 /* value of `v` held by lane `src` (all 32 lanes must call) */
 UKFB_D double warp_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+/* upper 32 bits of a double: for positive finite values (and +inf, NaN above them) ordered like the values themselves, so
+ * a range check can be an integer comparison instead of an instruction of the FP64 pipe */
+UKFB_D int hi_word(double x) { return __double2hiint(x); }
+
 /* Programmatic dependent launch: the next kernel of the stream (if it was launched with
  * cudaLaunchAttributeProgrammaticStreamSerialization) may be scheduled once every block of this grid has issued this or
  * exited -- i.e. into the slots the grid's last, partial wave leaves empty.  Ordering of the DATA is then the kernels' own
@@ -81,15 +85,21 @@ UKFB_D void warp_dmma(double& c0, double& c1, double a, double b)
 
 /* 1/x and 1/sqrt(x) for normal, positive-or-negative (rcp) / positive (rsq) x: hardware seed
  * (about 20 bits) refined by Newton steps in FMA arithmetic; error below 1 ulp, no
- * special-case branches (callers guarantee the operand range). */
+ * special-case branches (callers guarantee the operand range).  Two quadratic steps take 20 bits beyond
+ * 53 (the third one the first version carried changed nothing: tests/test_so3_kernels.py on the device). */
+#ifndef UKFB_SEED_REFINEMENTS
+#define UKFB_SEED_REFINEMENTS 2
+#endif
 UKFB_D double fast_rcp(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
+#if UKFB_SEED_REFINEMENTS >= 3
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
+#endif
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
@@ -102,8 +112,10 @@ UKFB_D void fast_sqrt_rsqrt(double x, double& s, double& r)
     double g = x * y, h = 0.5 * y;
     double e = fma(-g, h, 0.5);
     g = fma(g, e, g), h = fma(h, e, h);
+#if UKFB_SEED_REFINEMENTS >= 3
     e = fma(-g, h, 0.5);
     g = fma(g, e, g), h = fma(h, e, h);
+#endif
     e = fma(-g, h, 0.5);
     g = fma(g, e, g), h = fma(h, e, h);
     const double d = fma(-g, g, x);
@@ -139,6 +151,13 @@ using std::fabs;
 using std::fma;
 using std::sqrt;
 inline void prefetch_l2(const void*) {}
+inline int hi_word(double x)
+{
+    long long b;
+    static_assert(sizeof(b) == sizeof(x), "");
+    __builtin_memcpy(&b, &x, sizeof(b));
+    return int(b >> 32);
+}
 inline void pdl_launch_dependents() {}
 inline void tile_done_add(unsigned long long* counter) { __atomic_fetch_add(counter, 1ull, __ATOMIC_RELEASE); }
 inline void tile_done_wait(const unsigned long long* counter, unsigned long long need)

@@ -56,7 +56,7 @@ UKFB_D bool reg_cholesky(double* a, Store store)
     UKFB_UNROLL
     for (int j = 0; j < NCOL; ++j) {
         double ajj = a[tri(j, j)];
-        if (!(ajj > 0.0) || !(ajj < 1.0e300)) {
+        if (!pivot_ok(ajj)) {
             ok = false;
             ajj = 1.0;
         }

@@ -79,13 +79,28 @@ constexpr int PF_PER_LANE = 108;
 constexpr double PF_PI2_GUARD = 9.0; /* trace(Sigma_ori) below this (< pi^2) makes (mu [+] L_j) [-] mu = L_j exact */
 constexpr double PF_PI2_COLUMN = 9.6; /* what that needs: every |L_ori[:, j]|^2 below pi^2 (checked out of line when the trace is not) */
 
+/* The range checks of the polynomial pair, on the upper words (simt.cuh, hi_word): integer instructions instead of two
+ * FP64-pipe comparisons per sigma point.  Conservative by less than 1e-6 of the bound: x2 is in range when its upper word
+ * is BELOW that of the bound (a NaN or a negative value is not), w when its upper word lies above that of its bound and
+ * not above that of 1 + 2e-6 (a NaN, an infinity or a negative w does not). */
+UKFB_D bool pf_exp_in_range(double x2) { return unsigned(hi_word(x2)) < unsigned(hi_word(SO3_EXP5_FAST_X2)); }
+UKFB_D bool pf_log_in_range(double w)
+{
+    const unsigned first = unsigned(hi_word(SO3_LOG_FAST_W)) + 1u, span = unsigned(hi_word(1.000002)) - first;
+    return unsigned(hi_word(w)) - first <= span;
+}
+
+/* a Cholesky pivot the factorisation can go on with: positive, normal and below 1e300 (dpotf2 stops at ajj <= 0 or NaN; an
+ * infinite or subnormal pivot is treated the same here), again on the upper word */
+UKFB_D bool pivot_ok(double ajj) { return unsigned(hi_word(ajj)) - 0x00100000u < unsigned(hi_word(1.0e300)) - 0x00100000u; }
+
 /* ---- branch-free SO(3) kernels: polynomial path only, `slow` collects range violations ------------------------ */
 UKFB_D void pf_exp(const double* v, double scale, double* q, bool& slow)
 {
     const double half = scale * 0.5;
     const double norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     const double x2 = half * half * norm2;
-    slow = slow || !(x2 <= SO3_EXP5_FAST_X2);
+    slow = slow || !pf_exp_in_range(x2);
     const double x4 = x2 * x2;
     const double c = UKFB_POLY5(SO3_COS5_C, x2, x4);
     const double mult = UKFB_POLY5(SO3_SINC5_C, x2, x4) * half;
@@ -104,7 +119,7 @@ UKFB_D void pf_log(const double* q, double* out, bool& slow)
     const double nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
     const double w = q[3];
     const double d = fma(w, w, nv2) - 1.0;
-    slow = slow || !(w >= SO3_LOG_FAST_W); /* one comparison: w > 0 and nv2 within the polynomial's range (|q| = 1 to 1e-7) */
+    slow = slow || !pf_log_in_range(w); /* one comparison: w > 0 and nv2 within the polynomial's range (|q| = 1 to 1e-7) */
     const double s0 = two_asin_over_s_poly(fma(-nv2, d, nv2));
     const double s = fma(s0, -0.5 * d, s0);
     out[0] = s * q[0];
@@ -172,7 +187,6 @@ UKFB_D D2 tfma(double x, D2 y, double z) { return D2(fma(x, y.a, z), fma(x, y.b,
 UKFB_D D2 tfma(D2 x, double y, double z) { return D2(fma(x.a, y, z), fma(x.b, y, z)); }
 UKFB_D D2 tfma(double x, double y, D2 z) { return D2(fma(x, y, z.a), fma(x, y, z.b)); }
 UKFB_D bool all_le(D2 x, double lim) { return (x.a <= lim) && (x.b <= lim); }
-UKFB_D bool all_ge(D2 x, double lim) { return (x.a >= lim) && (x.b >= lim); }
 #define UKFB_TPOLY5(C, v, v2) tfma(tfma(C[5], v, C[4]), (v2) * (v2), tfma(tfma(C[3], v, C[2]), v2, tfma(C[1], v, C[0])))
 
 /* pf_exp / pf_log / pf_rotate and the quaternion products of so3.cuh, the same expressions, on a pair */
@@ -181,7 +195,7 @@ UKFB_D void pf_exp(const D2* v, double scale, D2* q, bool& slow)
     const double half = scale * 0.5;
     const D2 norm2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     const D2 x2 = (half * half) * norm2;
-    slow = slow || !all_le(x2, SO3_EXP5_FAST_X2);
+    slow = slow || !(pf_exp_in_range(x2.a) && pf_exp_in_range(x2.b));
     const D2 x4 = x2 * x2;
     const D2 c = UKFB_TPOLY5(SO3_COS5_C, x2, x4);
     const D2 mult = UKFB_TPOLY5(SO3_SINC5_C, x2, x4) * half;
@@ -205,7 +219,7 @@ UKFB_D void pf_log(const D2* q, D2* out, bool& slow)
     const D2 nv2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
     const D2 w = q[3];
     const D2 d = tfma(w, w, nv2) - 1.0;
-    slow = slow || !all_ge(w, SO3_LOG_FAST_W);
+    slow = slow || !(pf_log_in_range(w.a) && pf_log_in_range(w.b));
     const D2 s0 = two_asin_over_s_poly(tfma(-nv2, d, nv2));
     const D2 s = tfma(s0, -0.5 * d, s0);
     out[0] = s * q[0];
@@ -387,7 +401,7 @@ UKFB_D bool pf_cholesky(double* a)
         double ajj = a[tri(j, j)];
         UKFB_UNROLL
         for (int k = 0; k < j; ++k) ajj -= a[tri(j, k)] * a[tri(j, k)];
-        if (!(ajj > 0.0) || !(ajj < 1.0e300)) {
+        if (!pivot_ok(ajj)) {
             ok = false;
             ajj = 1.0;
         }
