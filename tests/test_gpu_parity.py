@@ -554,14 +554,14 @@ def test_fast_kernel_not_spd_deferral_is_one_factorisation():
 def test_overlapped_launches_equal_launches_in_stream_order(Ukf, filt):
     """A handle whose batch is a few waves of warps orders its step launches tile by tile (launch n starts in the slots
     the last wave of launch n - 1 leaves empty: include/ukf_batch.h, ukfb_overlapped_launch_count).  64 Ki filters are 1.7
-    waves on a B200; its two halves, one handle each, are less than a wave and launch in plain stream order.  Same device
-    inputs, launches back to back: the results must be equal bit for bit, and match the oracle on a sample."""
+    waves on a B200; its four quarters, one handle each, are less than half a wave and launch in plain stream order.  Same
+    device inputs, launches back to back: the results must be equal bit for bit, and match the oracle on a sample."""
     import torch
 
-    B, H, K = 65536, 32768, 12
+    B, H, K = 65536, 16384, 12
     dev = torch.device("cuda", 0)
     mu, sg = syn.pose_initial(B) if filt == 0 else syn.orientation_initial(B)
-    whole, halves = Ukf(filt, B), [Ukf(filt, H), Ukf(filt, H)]
+    whole, halves = Ukf(filt, B), [Ukf(filt, H) for _ in range(B // H)]
     objs = [(whole, slice(0, B))] + [(h, slice(i * H, (i + 1) * H)) for i, h in enumerate(halves)]
     d_dt = torch.full((1,), syn.DT, dtype=torch.float64, device=dev)
     for x, sl in objs:
