@@ -284,6 +284,35 @@ def test_pose_10k_steps_run_dev(Ukf):
     assert not g.get_status().any()
 
 
+def test_run_dev_with_a_schedule_that_changes_between_calls(Ukf):
+    """ukfb_run_dev keeps the K tick kinds of its last call on the device and rewrites them only when they change (a copy
+    between two launches is a full ordering point): same schedule twice, another schedule, a longer one, the first again"""
+    import torch
+
+    B = 70
+    g, o = both(Ukf, 0, B)
+    dev = torch.device("cuda:0")
+    tick = 0
+    for kinds in ([8, 8, 4, 8], [8, 8, 4, 8], [0, -1, 8, 7], [8, 4, 8, 8, 0, 8, -1, 2, 8], [8, 8, 4, 8]):
+        K = len(kinds)
+        zs, Rs = np.zeros((K, B, 3)), np.tile(np.eye(3), (K, 1, 1))
+        for j, kind in enumerate(kinds):
+            tick += 1
+            if kind >= 0:
+                z, R = syn.pose_measurement(kind, B, tick)
+                m = z.shape[1]
+                zs[j, :, :m], Rs[j, :m, :m] = z, R
+        g.run_dev(K, torch.full((K,), syn.DT, dtype=torch.float64, device=dev), False, np.array(kinds, np.int8),
+                  torch.from_numpy(zs).to(dev), torch.from_numpy(Rs).to(dev), False)
+        for j, kind in enumerate(kinds):
+            o.predict_dt(syn.DT)
+            if kind >= 0:
+                m = g.meas_dim(kind)
+                o.update(kind, zs[j, :, :m], Rs[j, :m, :m])
+    P.assert_parity(0, g.get_state(), o.get_state(), what="run_dev, changing schedules")
+    assert np.array_equal(g.get_status(), o.get_status())
+
+
 def test_pose_c3_10k_steps_mixed_updates(Ukf):
     """north star: 1e-9 after 10k steps on the C3 schedule (angular velocity every tick, velocity every 10th, position
     every 100th), through the single calls"""
