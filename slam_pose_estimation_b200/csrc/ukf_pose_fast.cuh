@@ -17,7 +17,8 @@
  *     The +/- points of a column share exp(L_ori), conj for the minus point.
  *   update with a component-selector measurement (all PoseUKF models but the orientation one, PoseUKF.cpp:7-69):
  *     Z_p = mu[sel] +- L[sel,j], so zbar = mu[sel], S = Sigma[sel,sel] + R and Sigma_xz = Sigma[:,sel] exactly
- *     (valid while every |L_ori[:,j]| < pi, guaranteed by trace(Sigma_ori) < pi^2, else the literal path runs);
+ *     (valid while every |L_ori[:,j]| < pi: guaranteed by trace(Sigma_ori) < 9 in the hot path, checked column by column
+ *     out of line beyond that -- only a column next to pi sends the filter's update to the literal code);
  *     gain and delta = K innov follow the reference's expression order; in Sigma - K S K^T the product K S is taken as
  *     Sigma_xz (K = Sigma_xz S^-1), which the reference recomputes.
  *   update with the orientation measurement (PoseUKF.cpp:28-33,133-138): Z_p = exp(+-L_ori[:,j]) q for columns 0..5, q
@@ -29,9 +30,12 @@
  *     six columns of the second Cholesky factor are needed.
  *
  * All SO(3) exp/log calls here are branch-free polynomial kernels (pf_exp: degree-5 cos / sinc; pf_log: no reciprocal, for
- * quaternions of unit norm, which pf_unit checks once per phase); a lane whose argument leaves the
- * polynomial range or that fails a guard falls back to the literal code of
- * ukf_thread.cuh (out of line, cold), which is also what UKFB_KERNEL=thread runs for every filter.
+ * quaternions of unit norm, which pf_unit checks once per phase; their range checks are integer comparisons).  A lane
+ * whose argument leaves the polynomial range -- a filter that barely knows its attitude -- is served by a second,
+ * out-of-line instance of the same structured code with an any-angle exp / log pair (pf_predict_slow / pf_update_slow);
+ * what is beyond even that, or fails a guard, falls back to the literal code of ukf_thread.cuh (cold), which is also
+ * what UKFB_KERNEL=thread runs for every filter.  The kernel has a second instance (OVERLAP) for handles whose
+ * consecutive launches are ordered tile by tile instead of launch by launch (StepParams::tile_done).
  * Covariance accumulators (57 / 33 doubles) and the state stay in registers, both Cholesky factorisations run in
  * registers on statically indexed arrays; shared memory ([entry][lane], conflict free) only holds the factor
  * columns, which the sigma-point loops index dynamically.
