@@ -24,8 +24,10 @@
  *     Euclidean block of the new covariance is that of Sigma - K S K^T; only the orientation rows are recomputed,
  *     from the 6 points of columns 0..2, and only three columns of the second Cholesky factor are needed.
  *
- * SO(3) exp/log are the branch-free polynomial kernels of so3.cuh; a lane that leaves their range or fails the guard
- * runs the literal code of ukf_thread.cuh out of line on a per-thread local array.
+ * SO(3) exp/log are the branch-free polynomial kernels of ukf_pose_fast.cuh; a lane that leaves their range -- a filter
+ * that barely knows its attitude -- is served by a second, out-of-line instance of the same structured code with the
+ * any-angle exp / log pair (of_predict_slow / of_update_slow), and what is beyond even that, or fails a guard, runs the
+ * literal code of ukf_thread.cuh on a per-thread local array.
  */
 #ifndef UKFB_ORI_FAST_CUH
 #define UKFB_ORI_FAST_CUH
@@ -94,13 +96,14 @@ struct OriCtx {
 /* a pair of propagated sigma points (OrientationUKF.cpp:12-32), the + and the - point of a column side by side (D2, as in
  * ukf_pose_fast.cuh): orientation and velocity deviations from the reference.
  * qs, vs: the points' orientation and velocity; wb = omega - bg, ab = acc - ba, gs = gravity of the points. */
+template <bool WIDE> /* WIDE: the any-angle exp / log pair of ukf_pose_fast.cuh (pf_exp_t / pf_log_t) */
 UKFB_D void of_point2(const D2* qs, const D2* vs, const D2* wb, const D2* ab, D2 gs, const OriCtx& cx, const double* ref_q,
                       const double* ref_v, D2* d, bool& slow)
 {
     D2 av[3], e[4], qn[4], an[3], r[4];
     pf_rotate(qs, wb, av);
     av[0] = av[0] - cx.earth[0], av[1] = av[1] - cx.earth[1], av[2] = av[2] - cx.earth[2];
-    pf_exp(av, cx.dt, e, slow);
+    pf_exp_t<WIDE>(av, cx.dt, e, slow);
     quat_mul(e, qs, qn);
     pf_rotate(qn, ab, an); /* with the UPDATED orientation (:22-23) */
     an[2] = an[2] - gs;
@@ -108,17 +111,18 @@ UKFB_D void of_point2(const D2* qs, const D2* vs, const D2* wb, const D2* ab, D2
     d[4] = tfma(cx.dt, an[1], vs[1]) - ref_v[1];
     d[5] = tfma(cx.dt, an[2], vs[2]) - ref_v[2];
     quat_mul_conj(qn, ref_q, r);
-    pf_log(r, d, slow);
+    pf_log_t<WIDE>(r, d, slow);
 }
 
 /* the +/- sigma points of a column j < 3 (everything perturbed); L receives the column (13 entries) */
+template <bool WIDE>
 UKFB_D void of_pair_a(const double* sm, int lane, int j, const OriMu& m, const OriCtx& cx, const double* ref_q, const double* ref_v,
                       double* L, double* dpl, double* dmi, bool& slow)
 {
     UKFB_UNROLL
     for (int i = 0; i < 13; ++i) L[i] = UKFB_OS(j * 13 + i);
     double e[4];
-    pf_exp(L, 1.0, e, slow);
+    pf_exp1<WIDE>(L, 1.0, e, slow);
     const double* q = m.q;
     const double t0 = e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
     const double t1 = e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
@@ -134,13 +138,14 @@ UKFB_D void of_pair_a(const double* sm, int lane, int j, const OriMu& m, const O
                       D2(cx.acc[1] - (m.ba[1] + L[10]), cx.acc[1] - (m.ba[1] - L[10])),
                       D2(cx.acc[2] - (m.ba[2] + L[11]), cx.acc[2] - (m.ba[2] - L[11]))};
     D2 d[6];
-    of_point2(qs, vs, wb, ab, D2(m.g + L[12], m.g - L[12]), cx, ref_q, ref_v, d, slow);
+    of_point2<WIDE>(qs, vs, wb, ab, D2(m.g + L[12], m.g - L[12]), cx, ref_q, ref_v, d, slow);
     UKFB_UNROLL
     for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
 }
 
 /* the +/- sigma points of a column 3 <= j < 9: orientation unperturbed.  Rm = R(q), w0 = R (omega - bg) - earth,
  * c = q * conj(ref_q); L receives rows 3..12 of the column (10 entries: velocity, gyro bias, acc bias, gravity). */
+template <bool WIDE>
 UKFB_D void of_pair_b(const double* sm, int lane, int j, const OriMu& m, const OriCtx& cx, const double* Rm, const double* w0,
                       const double* c, const double* ref_v, double* L, double* dpl, double* dmi, bool& slow)
 {
@@ -150,7 +155,7 @@ UKFB_D void of_pair_b(const double* sm, int lane, int j, const OriMu& m, const O
     pf_matvec(Rm, L + 3, u);
     const D2 av[3] = {D2(w0[0] - u[0], w0[0] + u[0]), D2(w0[1] - u[1], w0[1] + u[1]), D2(w0[2] - u[2], w0[2] + u[2])};
     D2 e[4], qn[4], r[4], an[3], d[6];
-    pf_exp(av, cx.dt, e, slow);
+    pf_exp_t<WIDE>(av, cx.dt, e, slow);
     quat_mul(e, m.q, qn);
     const D2 ab[3] = {D2(cx.acc[0] - (m.ba[0] + L[6]), cx.acc[0] - (m.ba[0] - L[6])),
                       D2(cx.acc[1] - (m.ba[1] + L[7]), cx.acc[1] - (m.ba[1] - L[7])),
@@ -161,15 +166,44 @@ UKFB_D void of_pair_b(const double* sm, int lane, int j, const OriMu& m, const O
     d[4] = tfma(cx.dt, an[1], D2(m.v[1] + L[1], m.v[1] - L[1])) - ref_v[1];
     d[5] = tfma(cx.dt, an[2], D2(m.v[2] + L[2], m.v[2] - L[2])) - ref_v[2];
     quat_mul(e, c, r);
-    pf_log(r, d, slow);
+    pf_log_t<WIDE>(r, d, slow);
     UKFB_UNROLL
     for (int i = 0; i < 6; ++i) dpl[i] = d[i].a, dmi[i] = d[i].b;
+}
+
+/* The column pairs as the two instances of the structured code call them (as pf_pair_*_sel in ukf_pose_fast.cuh): the hot
+ * instance knows only the short polynomials; the out-of-line one sends an orientation column this large to the any-angle
+ * pair at once and redoes any other column whose points left the short range. */
+template <bool WIDE>
+UKFB_D void of_pair_a_sel(const double* sm, int lane, int j, const OriMu& m, const OriCtx& cx, const double* ref_q, const double* ref_v,
+                          double* L, double* dpl, double* dmi, bool& slow)
+{
+    if (!WIDE) {
+        of_pair_a<false>(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
+        return;
+    }
+    const double l0 = UKFB_OS(j * 13), l1 = UKFB_OS(j * 13 + 1), l2 = UKFB_OS(j * 13 + 2);
+    bool redo = l0 * l0 + l1 * l1 + l2 * l2 > PF_WIDE_COLUMN_N2;
+    if (!redo) of_pair_a<false>(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, redo);
+    if (redo) of_pair_a<true>(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
+}
+template <bool WIDE>
+UKFB_D void of_pair_b_sel(const double* sm, int lane, int j, const OriMu& m, const OriCtx& cx, const double* Rm, const double* w0,
+                          const double* c, const double* ref_v, double* L, double* dpl, double* dmi, bool& slow)
+{
+    if (!WIDE) {
+        of_pair_b<false>(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
+        return;
+    }
+    bool redo = false;
+    of_pair_b<false>(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, redo);
+    if (redo) of_pair_b<true>(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
 }
 
 
 /* ---- literal fallbacks (cold, out of line): the general code of ukf_thread.cuh on this lane's filter ---------- */
 #ifdef UKFB_SIMT_EMU
-inline unsigned long long of_fallbacks[3] = {0, 0, 0};
+inline unsigned long long of_fallbacks[5] = {0, 0, 0, 0, 0}; /* [3], [4]: predicts / updates served by the any-angle instance */
 #define UKFB_OF_COUNT(i) __atomic_fetch_add(&of_fallbacks[i], 1ull, __ATOMIC_RELAXED)
 #else
 #define UKFB_OF_COUNT(i)
@@ -266,9 +300,13 @@ UKFB_DNI OfLit of_literal_update(double* sig, int kind, const double* zm, const 
 
 /* ---- structured predict.  Returns false when a polynomial range was left (nothing has been modified then) ------ */
 /* On success: m holds the new mean, the record holds the new covariance.  `a` (prior covariance) is destroyed. */
-UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig, double* a, const double* Qp, const ModelArgs& ma, OriMu& m,
+/* WIDE = false: the hot instance (short polynomials; does not start on a filter whose orientation uncertainty certainly
+ * leaves their range); WIDE = true: the out-of-line instance behind of_predict_slow, any orientation uncertainty. */
+template <bool WIDE>
+UKFB_D bool of_predict(int q_diagonal, double* sm, int lane, double* sig, double* a, const double* Qp, const ModelArgs& ma, OriMu& m,
                        uint32_t& status, int& passes_out, bool& spd)
 {
+    if (!WIDE && a[tri(0, 0)] + a[tri(1, 1)] + a[tri(2, 2)] > PF_WIDE_TRACE) return false; /* nothing has been modified */
     OriCtx cx;
     cx.dt = ma.dt;
     UKFB_UNROLL
@@ -300,7 +338,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         double e0[4], an[3];
         pf_matvec(Rm, wb, w0);
         w0[0] -= cx.earth[0], w0[1] -= cx.earth[1], w0[2] -= cx.earth[2];
-        pf_exp(w0, dt, e0, slow);
+        pf_exp1<WIDE>(w0, dt, e0, slow);
         quat_mul(e0, m.q, q0n);
         quat_matrix(q0n, R0n);
         const double ab[3] = {cx.acc[0] - m.ba[0], cx.acc[1] - m.ba[1], cx.acc[2] - m.ba[2]};
@@ -320,7 +358,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         {
             double r[4];
             quat_mul_conj(q0n, ref_q, r);
-            pf_log(r, d0, slow);
+            pf_log1<WIDE>(r, d0, slow);
             d0[3] = v0n[0] - ref_v[0], d0[4] = v0n[1] - ref_v[1], d0[5] = v0n[2] - ref_v[2];
         }
         /* X0 and the 8 points of columns 9..12 share X0's orientation; their velocity offsets cancel in pairs */
@@ -329,7 +367,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_NOUNROLL
         for (int j = 0; j < 3; ++j) {
             double L[13], dpl[6], dmi[6];
-            of_pair_a(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
+            of_pair_a_sel<WIDE>(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) md[i] += dpl[i] + dmi[i];
         }
@@ -338,7 +376,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_NOUNROLL
         for (int j = 3; j < 9; ++j) {
             double L[10], dpl[6], dmi[6];
-            of_pair_b(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
+            of_pair_b_sel<WIDE>(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) md[i] += dpl[i] + dmi[i];
         }
@@ -351,7 +389,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         ref_v[0] += md[3], ref_v[1] += md[4], ref_v[2] += md[5];
         {
             double e[4], r[4];
-            pf_exp(md, 1.0, e, slow);
+            pf_exp1<WIDE>(md, 1.0, e, slow);
             quat_mul(e, ref_q, r);
             ref_q[0] = r[0], ref_q[1] = r[1], ref_q[2] = r[2], ref_q[3] = r[3];
         }
@@ -375,7 +413,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
     {
         double d0[6], r[4];
         quat_mul_conj(q0n, ref_q, r);
-        pf_log(r, d0, slow);
+        pf_log1<WIDE>(r, d0, slow);
         d0[3] = v0n[0] - ref_v[0], d0[4] = v0n[1] - ref_v[1], d0[5] = v0n[2] - ref_v[2];
         UKFB_UNROLL
         for (int i = 0; i < 6; ++i) {
@@ -385,7 +423,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_NOUNROLL
         for (int j = 0; j < 3; ++j) {
             double L[13], dpl[6], dmi[6];
-            of_pair_a(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
+            of_pair_a_sel<WIDE>(sm, lane, j, m, cx, ref_q, ref_v, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) {
                 UKFB_UNROLL
@@ -402,7 +440,7 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
         UKFB_NOUNROLL
         for (int j = 3; j < 9; ++j) {
             double L[10], dpl[6], dmi[6];
-            of_pair_b(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
+            of_pair_b_sel<WIDE>(sm, lane, j, m, cx, Rm, w0, c, ref_v, L, dpl, dmi, slow);
             UKFB_UNROLL
             for (int i = 0; i < 6; ++i) {
                 UKFB_UNROLL
@@ -538,9 +576,9 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
             }
         }
     };
-    if (par.q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
+    if (q_diagonal == 2) /* diagonal, and a multiple of the identity in each of the two rotated 3 x 3 blocks */
         commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, TrueT());
-    else if (par.q_diagonal)
+    else if (q_diagonal)
         commit([&](int i, int k) { return i == k ? UKFB_LDG(Qp + tri(i, i)) : 0.0; }, FalseT());
     else
         commit([&](int i, int k) { return UKFB_LDG(Qp + tri(i, k)); }, FalseT());
@@ -561,13 +599,31 @@ UKFB_D bool of_predict(const StepParams& par, double* sm, int lane, double* sig,
  * Returns true when done (spd = false: a factorisation failed; a rejected measurement sets its status bit).
  * Returns false when a polynomial range was left: stage = 0: nothing has been modified; stage = 1: the record holds
  * Sigma - K S K^T, `delta` = K innov, m is untouched (the caller runs the literal apply_delta). */
+template <bool WIDE>
+UKFB_D bool of_apply_delta(double* sig, double* a, OriMu& m, const double* delta, uint32_t& status, int& passes_out, bool& spd, bool slow);
+
+/* WIDE as in of_predict.  The closed forms rest on (mu [+] L_j) [-] mu = L_j, i.e. on every |L_ori[:, j]| < pi: the caller
+ * of the hot instance guarantees it through trace(Sigma_ori) < 9, the out-of-line instance looks at the three columns
+ * themselves (a filter that does not know its attitude at all) and leaves a column next to pi to the literal code. */
+template <bool WIDE>
 UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double* zm, const double* Rmeas, int r_ld, OriMu& m,
                       double* delta, uint32_t& status, int& passes_out, bool& spd, int& stage, double gate_d2)
 {
     stage = 0;
+    if (!WIDE && a[tri(0, 0)] + a[tri(1, 1)] + a[tri(2, 2)] > PF_WIDE_TRACE) return false; /* nothing has been modified */
     spd = reg_cholesky<13, 13>(a);
     if (!spd) return true;
     bool slow = !pf_unit(m.q);
+    if (WIDE) {
+        UKFB_UNROLL
+        for (int j = 0; j < 3; ++j) {
+            double n2 = a[tri(2, j)] * a[tri(2, j)];
+            if (j <= 1) n2 += a[tri(1, j)] * a[tri(1, j)];
+            if (j == 0) n2 += a[tri(0, 0)] * a[tri(0, 0)];
+            slow = slow || !(n2 < PF_PI2_COLUMN);
+        }
+        if (slow) return false;
+    }
     /* Z of X0, of the 6 points of columns 0..2, and the linear offsets of columns 3..5.  The factor stays in registers:
      * every index below is static */
 #define OF_L(i, j) ((i) >= (j) ? a[tri((i) >= (j) ? (i) : (j), (j))] : 0.0)
@@ -577,7 +633,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
     for (int j = 0; j < 3; ++j) {
         double e[4];
         const double Lo[3] = {OF_L(0, j), OF_L(1, j), OF_L(2, j)};
-        pf_exp(Lo, 1.0, e, slow);
+        pf_exp1<WIDE>(Lo, 1.0, e, slow);
         const double* q = m.q;
         const double t0 = e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
         const double t1 = e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
@@ -736,6 +792,17 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         }
     }
     stage = 1;
+    return of_apply_delta<WIDE>(sig, a, m, delta, status, passes_out, spd, slow);
+#undef OF_L
+}
+
+/* ---- apply_delta of the structured update: `a` = Sigma - K S K^T (also in the record), `delta` = K innov.  Returns false
+ * when a polynomial range was left (nothing more has been modified: the caller runs the any-angle instance or the
+ * literal apply_delta on the record). */
+template <bool WIDE>
+UKFB_D bool of_apply_delta(double* sig, double* a, OriMu& m, const double* delta, uint32_t& status, int& passes_out, bool& spd, bool slow)
+{
+#define OF_L(i, j) ((i) >= (j) ? a[tri((i) >= (j) ? (i) : (j), (j))] : 0.0)
     /* first three columns of the factor of the updated covariance (the reference factorises all of it: a failure in the
      * later columns shows at the next factorisation of this filter instead) */
     spd = reg_cholesky<13, 3>(a);
@@ -743,7 +810,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
 
     /* ---- apply_delta: orientation rows only */
     double e0[4], q0n[4];
-    pf_exp(delta, 1.0, e0, slow);
+    pf_exp1<WIDE>(delta, 1.0, e0, slow);
     quat_mul(e0, m.q, q0n);
     double ref_q[4] = {q0n[0], q0n[1], q0n[2], q0n[3]};
     double vp[9], vn[9]; /* delta_ori +- L'_ori of columns 0..2 */
@@ -761,17 +828,17 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         double c[4], r[4], d0[3], md[3];
         quat_mul_conj(m.q, ref_q, c);
         quat_mul(e0, c, r);
-        pf_log(r, d0, slow);
+        pf_log1<WIDE>(r, d0, slow);
         md[0] = 21.0 * d0[0], md[1] = 21.0 * d0[1], md[2] = 21.0 * d0[2];
         UKFB_UNROLL
         for (int j = 0; j < 3; ++j) {
             double ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
-            pf_exp(vp + 3 * j, 1.0, ep, slow);
-            pf_exp(vn + 3 * j, 1.0, en, slow);
+            pf_exp1<WIDE>(vp + 3 * j, 1.0, ep, slow);
+            pf_exp1<WIDE>(vn + 3 * j, 1.0, en, slow);
             quat_mul(ep, c, rp);
             quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
+            pf_log1<WIDE>(rp, dp, slow);
+            pf_log1<WIDE>(rn, dn, slow);
             md[0] += dp[0] + dn[0], md[1] += dp[1] + dn[1], md[2] += dp[2] + dn[2];
         }
         double n2 = 0.0;
@@ -782,7 +849,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         }
         {
             double e[4], rr[4];
-            pf_exp(md, 1.0, e, slow);
+            pf_exp1<WIDE>(md, 1.0, e, slow);
             quat_mul(e, ref_q, rr);
             ref_q[0] = rr[0], ref_q[1] = rr[1], ref_q[2] = rr[2], ref_q[3] = rr[3];
         }
@@ -799,7 +866,7 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         double c[4], r[4], d0[3];
         quat_mul_conj(m.q, ref_q, c);
         quat_mul(e0, c, r);
-        pf_log(r, d0, slow);
+        pf_log1<WIDE>(r, d0, slow);
         UKFB_UNROLL
         for (int i = 0; i < 3; ++i) {
             UKFB_UNROLL
@@ -810,12 +877,12 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
         UKFB_UNROLL
         for (int j = 0; j < 3; ++j) {
             double ep[4], en[4], rp[4], rn[4], dp[3], dn[3];
-            pf_exp(vp + 3 * j, 1.0, ep, slow);
-            pf_exp(vn + 3 * j, 1.0, en, slow);
+            pf_exp1<WIDE>(vp + 3 * j, 1.0, ep, slow);
+            pf_exp1<WIDE>(vn + 3 * j, 1.0, en, slow);
             quat_mul(ep, c, rp);
             quat_mul(en, c, rn);
-            pf_log(rp, dp, slow);
-            pf_log(rn, dn, slow);
+            pf_log1<WIDE>(rp, dp, slow);
+            pf_log1<WIDE>(rn, dn, slow);
             UKFB_UNROLL
             for (int i = 0; i < 3; ++i) {
                 UKFB_UNROLL
@@ -847,6 +914,59 @@ UKFB_D bool of_update(double* sm, int lane, double* sig, double* a, const double
     m.g += delta[12];
     passes_out = passes;
     return true;
+#undef OF_L
+}
+
+/* ---- everything the hot instances do not do, out of line (one call site per phase, as in ukf_pose_fast.cuh): the
+ * any-angle instance of the same structured code first, the literal code of ukf_thread.cuh for what is beyond that too */
+UKFB_DNI OfLit of_predict_slow(double* sm, int lane, double* sig, const double* Qp, ModelArgs ma, OriMu m, int q_diagonal)
+{
+    OfLit r;
+    r.m = m, r.status = 0, r.passes = 0;
+    double a[OriF::LP];
+    UKFB_UNROLL
+    for (int e = 0; e < OriF::LP; ++e) a[e] = sig[e * TILE];
+    bool spd = true;
+    if (of_predict<true>(q_diagonal, sm, lane, sig, a, Qp, ma, r.m, r.status, r.passes, spd)) {
+        if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+        UKFB_OF_COUNT(3);
+        return r;
+    }
+    return of_literal_predict(sig, Qp, ma, m);
+}
+
+/* stage 0: nothing has been done (the hot instance refused the filter, or the caller's trace guard did); 1: the record
+ * holds Sigma - K S K^T and `delta` = K innov (the hot instance left a polynomial range in its apply_delta) */
+UKFB_DNI OfLit of_update_slow(double* sm, int lane, double* sig, int kind, const double* zm, const double* Rm, int r_ld, ModelArgs ma,
+                              OriMu m, OfDelta delta, int stage, double gate_d2)
+{
+    if (stage == 0) {
+        OfLit r;
+        r.m = m, r.status = 0, r.passes = 0;
+        double a[OriF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < OriF::LP; ++e) a[e] = sig[e * TILE];
+        bool spd = true;
+        if (of_update<true>(sm, lane, sig, a, zm, Rm, r_ld, r.m, delta.d, r.status, r.passes, spd, stage, gate_d2)) {
+            if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+            UKFB_OF_COUNT(4);
+            return r;
+        }
+        /* stage now tells where the any-angle instance stopped */
+    } else { /* stage 1: the hot instance left a polynomial range in its apply_delta; Sigma - K S K^T is in the record */
+        OfLit r;
+        r.m = m, r.status = 0, r.passes = 0;
+        double a[OriF::LP];
+        UKFB_UNROLL
+        for (int e = 0; e < OriF::LP; ++e) a[e] = sig[e * TILE];
+        bool spd = true;
+        if (of_apply_delta<true>(sig, a, r.m, delta.d, r.status, r.passes, spd, !pf_unit(m.q))) {
+            if (!spd) r.status |= UKFB_STATUS_NOT_SPD;
+            UKFB_OF_COUNT(4);
+            return r;
+        }
+    }
+    return of_literal_update(sig, kind, zm, Rm, r_ld, ma, m, delta, stage == 0, gate_d2);
 }
 
 /* ---- the kernel: one warp per block, one filter per lane -------------------------------------------------------- */
@@ -1001,14 +1121,14 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
             UKFB_UNROLL
             for (int e = 0; e < F::LP; ++e) a[e] = sig[e * TILE];
             bool spd = true;
-            if (of_predict(p, sm, lane, sig, a, Qp, ma, m, status, passes_a, spd)) {
+            if (of_predict<false>(p.q_diagonal, sm, lane, sig, a, Qp, ma, m, status, passes_a, spd)) {
                 if (!spd) {
                     status |= UKFB_STATUS_NOT_SPD;
                     do_upd = false; /* every later factorisation of this covariance fails too */
                 } else
                     dirty_mu = true;
-            } else { /* a polynomial range was left: nothing was modified, run the literal code */
-                const OfLit r = of_literal_predict(sig, Qp, ma, m);
+            } else { /* a polynomial range was left: nothing was modified; the any-angle instance, then the literal code */
+                const OfLit r = of_predict_slow(sm, lane, sig, Qp, ma, m, p.q_diagonal);
                 status |= r.status;
                 passes_a = r.passes;
                 if (r.status & UKFB_STATUS_NOT_SPD)
@@ -1049,7 +1169,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
             UKFB_UNROLL
             for (int i = 0; i < 13; ++i) delta[i] = 0.0;
             if (!literal) {
-                fast_done = of_update(sm, lane, sig, a, zm, Rm, p.r_ld, m, delta, status, passes_b, spd, stage, p.gate_d2);
+                fast_done = of_update<false>(sm, lane, sig, a, zm, Rm, p.r_ld, m, delta, status, passes_b, spd, stage, p.gate_d2);
                 if (fast_done) {
                     if (!spd)
                         status |= UKFB_STATUS_NOT_SPD;
@@ -1061,7 +1181,7 @@ UKFB_GLOBAL void UKFB_LAUNCH_BOUNDS(4 * TILE, 2) ukf_ori_fast_kernel(const UKFB_
                 OfDelta dl;
                 UKFB_UNROLL
                 for (int i = 0; i < 13; ++i) dl.d[i] = delta[i];
-                const OfLit r = of_literal_update(sig, kind, zm, Rm, p.r_ld, ma, m, dl, stage == 0, p.gate_d2);
+                const OfLit r = of_update_slow(sm, lane, sig, kind, zm, Rm, p.r_ld, ma, m, dl, stage, p.gate_d2);
                 status |= r.status;
                 passes_b = r.passes;
                 if (!(r.status & UKFB_STATUS_NOT_SPD)) {

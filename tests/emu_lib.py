@@ -249,8 +249,8 @@ class EmuBatch:
                      r_kind_stride=0 if per_event else 9)
 
     def fallbacks(self):
-        """(literal predict, literal update, literal apply_delta, columns redone with the any-angle exp / log in the
-        predict, the same in apply_delta) calls made so far by the fast kernel's lanes"""
+        """(literal predict, literal update, literal apply_delta, predicts served by the any-angle instance of the
+        structured code, apply_deltas / updates served by it) calls made so far by the fast kernel's lanes"""
         out = (C.c_ulonglong * 5)()
         (self.lib.emu_ori_fast_fallbacks if self.kind == 1 else self.lib.emu_pose_fast_fallbacks)(out)
         return np.array(list(out), np.int64)

@@ -77,8 +77,7 @@ extern "C" int emu_ori_fast_step(const StepParams* p)
 
 extern "C" void emu_ori_fast_fallbacks(unsigned long long* out5)
 {
-    for (int i = 0; i < 3; ++i) out5[i] = of_fallbacks[i];
-    out5[3] = out5[4] = 0;
+    for (int i = 0; i < 5; ++i) out5[i] = of_fallbacks[i];
 }
 
 /* the SO(3) kernels of so3.cuh as the host build evaluates them (same layout as ukfb_selftest_so3) */

@@ -234,10 +234,13 @@ def test_orientation_bias_decay_dense_noise_guards_and_masks(kernel):
 
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_orientation_large_angles_take_the_literal_expressions(kernel):
+    """As for PoseUKF: orientation spread and rates far outside the short polynomials are served by the any-angle instance
+    of the structured code (no literal predict), a factor column next to pi sends the update to the literal code."""
     B = 4
     mu, sg = syn.orientation_initial(B)
     sg[0, 0:3, 0:3] *= 150.0  # sqrt(1.5) rad orientation sigma: exp and log leave the polynomial range
-    sg[1, 0:3, 0:3] *= 400.0  # trace 12 > 9: the update guard
+    sg[1, 0:3, 0:3] *= 400.0  # 2 rad per axis, trace 12 > 9: beyond the hot path's update guard, every column below pi
+    sg[3, 2, 2] = 3.13**2  # a factor column at the branch cut of the SO(3) log: the literal update
     o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel=kernel)
     before = e.fallbacks()
     gyro = np.tile([0.0, 0.0, 0.05], (B, 1))
@@ -252,10 +255,39 @@ def test_orientation_large_angles_take_the_literal_expressions(kernel):
     assert np.array_equal(e.get_status(), o.get_status())
     P.assert_parity(1, e.get_state(), o.get_state(), tol=1e-10, what=f"{kernel} orientation large angles")
     if kernel == "fast":
-        fb = (e.fallbacks() - before)[:3]
-        assert fb[0] > 0 and fb[1] + fb[2] > 0, f"the fallbacks were not exercised: {fb}"
-        assert fb.sum() < 2 * 3 * B, "every lane fell back: the fast path was not exercised"
+        fb = e.fallbacks() - before
+        assert fb[0] == 0 and fb[1] + fb[2] > 0, f"literal predict / update calls {fb}"
+        assert fb[3] > 0 and fb[4] > 0, f"the any-angle instance was not exercised: {fb}"
+        assert fb[:3].sum() < 2 * 3 * B, "every lane fell back: the fast path was not exercised"
     assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
+@pytest.mark.parametrize("sig", [(0.7, 0.7, 0.7), (1.0, 1.0, 1.0), (2.0, 2.0, 2.0), (0.1, 0.1, 2.9), (3.0, 3.0, 3.0)])
+def test_orientation_wide_attitude_uncertainty_stays_in_the_fast_kernel(sig):
+    """An OrientationUKF that barely knows its attitude (or only its heading: the usual start-up state) never reaches the
+    literal code: the any-angle instance of the structured predict / update serves it, the mean passes included."""
+    B = 8
+    mu, sg = syn.orientation_initial(B)
+    sg[:, 0:3, 0:3] = np.diag(np.square(sig))
+    o, e = P.make_ori(OracleBatch, B), P.make_ori(EmuBatch, B, kernel="fast")
+    before = e.fallbacks()
+    for x in (o, e):
+        x.initialize(mu, sg)
+        for k in range(1, 7):
+            gyro, acc = syn.orientation_imu(B, k)
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(acc)
+            if k % 2 == 0:
+                z, R = syn.orientation_velocity(B, k)
+                x.step(0.01, 9, z, R)
+            else:
+                x.predict_dt(0.01)
+    assert np.array_equal(e.get_status(), o.get_status()) and not o.get_status().any()
+    P.assert_parity(1, e.get_state(), o.get_state(), tol=1e-11, what=f"wide orientation sigma {sig}")
+    assert np.array_equal(e.get_mean_iter_hist(), o.get_mean_iter_hist())
+    fb = e.fallbacks() - before
+    assert not fb[:3].any(), f"literal fallbacks were taken: {fb}"
+    assert fb[3] > 0 and fb[4] > 0, f"the any-angle instance was not exercised: {fb}"
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

@@ -440,6 +440,32 @@ def test_pose_fast_kernel_fallback_lanes(Ukf):
     assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
 
 
+def test_orientation_fast_kernel_wide_attitude_lanes(Ukf):
+    """OrientationUKF filters that barely know their attitude (0.7 ... 3 rad per axis, an unknown heading, a factor column
+    at the branch cut) next to ordinary ones in the same warps: the any-angle instance of the structured code, the literal
+    update for the last kind, all against the oracle with equal status and mean-pass histogram"""
+    B = 96
+    mu, sg = syn.orientation_initial(B)
+    for start, sig in ((0, (0.7, 0.7, 0.7)), (1, (1.0, 1.0, 1.0)), (2, (2.0, 2.0, 2.0)), (3, (0.1, 0.1, 2.9)), (4, (3.0, 3.0, 3.0)),
+                       (5, (0.1, 0.1, 3.13))):
+        sg[start::8, 0:3, 0:3] = np.diag(np.square(sig))
+    g, o = P.make_ori(Ukf, B), P.make_ori(OracleBatch, B)
+    for x in (g, o):
+        x.initialize(mu, sg)
+        for k in range(1, 9):
+            gyro, acc = syn.orientation_imu(B, k)
+            x.set_rotation_rate(gyro)
+            x.set_acceleration(acc)
+            if k % 2 == 0:
+                z, R = syn.orientation_velocity(B, k)
+                x.step(0.01, 9, z, R)
+            else:
+                x.predict_dt(0.01)
+    assert np.array_equal(g.get_status(), o.get_status()) and not o.get_status().any()
+    P.assert_parity(1, g.get_state(), o.get_state(), tol=1e-9, what="orientation wide attitude lanes")
+    assert np.array_equal(g.get_mean_iter_hist(), o.get_mean_iter_hist())
+
+
 @pytest.mark.parametrize("filt", [0, 1])
 def test_unnormalised_quaternions_match_the_scale_invariant_log(Ukf, filt):
     """the fast kernels' reciprocal-free log assumes |q| = 1; states initialised with other norms run the literal code

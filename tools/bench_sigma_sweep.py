@@ -95,13 +95,75 @@ def run(B, sigma_ori, steps, label):
     return out
 
 
+def run_ori(B, sigma_ori, steps, label, K=10):
+    """the same question for OrientationUKF: K IMU ticks (sample stored + predict) per launch, initial attitude covariance
+    sigma^2 I (the predicts carry no attitude information either, so it stays wide)"""
+    import torch
+
+    import parity as P
+    from oracle.oracle_lib import OracleBatch
+    from slam_pose_estimation_b200 import synthetic as syn
+    from slam_pose_estimation_b200.batch import UkfBatch
+
+    mu, sg = syn.orientation_initial(B)
+    sg[:, 0:3, 0:3] = np.eye(3) * sigma_ori**2
+    f = P.make_ori(UkfBatch, 1)  # parameters as the tests set them
+    f.close()
+    f = UkfBatch(1, B)
+    f.initialize(mu, sg)
+    f.set_process_noise(syn.ORI_Q)
+    f.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+    dev = torch.device("cuda", 0)
+    imu = np.stack([np.concatenate(syn.orientation_imu(B, k + 1), axis=1) for k in range(K)])
+    d_imu = torch.from_numpy(imu).to(dev)
+    d_dt = torch.full((K,), syn.DT, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    warm = 2
+    for _ in range(warm):
+        f.run_dev(K, d_dt, False, d_imu=d_imu)
+    f.clear_mean_iter_hist()
+    f.synchronize()
+    f.event_record(0)
+    for _ in range(steps):
+        f.run_dev(K, d_dt, False, d_imu=d_imu)
+    f.event_record(1)
+    f.synchronize()
+    ms = f.event_elapsed_ms(0, 1) / steps
+    hist = f.get_mean_iter_hist()
+    S = 16
+    idx = (np.arange(S) * (B // S)).astype(int)
+    o = OracleBatch(1, S)
+    o.initialize(mu[idx], sg[idx])
+    o.set_process_noise(syn.ORI_Q)
+    o.set_orientation_params(syn.ORI_TAU, syn.ORI_TAU, syn.LATITUDE_BREMEN)
+    for _ in range(warm + steps):
+        for k in range(K):
+            o.set_rotation_rate(imu[k, idx, 0:3])
+            o.set_acceleration(imu[k, idx, 3:6])
+            o.predict_dt(syn.DT)
+    mg, sgg = f.get_state()
+    mo, so = o.get_state()
+    out = {"label": label, "filter": "OrientationUKF", "filters": B, "ticks_per_launch": K, "launches": steps, "ms_per_launch": ms,
+           "value": B * K / (ms * 1e-3), "unit": "filter-ticks/s",
+           "mean_passes_avg": float((hist * np.arange(8)).sum() / max(1, hist.sum())), "status_flagged": int(f.status_summary()[0]),
+           "max_mu_err": float(P.mu_error(1, mg[idx], mo).max()), "max_sigma_err": float(P.sigma_error(sgg[idx], so).max()),
+           "sigma_ori": sigma_ori}
+    f.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--filters", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--sigmas", type=float, nargs="*", help="only these points of sweep (a), and no sweep (b)")
+    ap.add_argument("--orientation", action="store_true", help="sweep (a) on OrientationUKF instead")
     args = ap.parse_args()
     B = args.filters
+    if args.orientation:
+        for s in args.sigmas or (0.1, 0.3, 0.6, 1.0, 2.0, 3.0):
+            print(json.dumps(run_ori(B, s, args.steps, f"OrientationUKF, all filters sigma_ori = {s:.3f} rad")), flush=True)
+        return
     for s in args.sigmas or (0.05, 0.1, 0.2, 0.3, 0.45, 0.6, 0.8, 1.0, 1.5, 2.0, 2.5, 3.0, float(np.pi)):
         r = run(B, s, args.steps, f"all filters sigma_ori = {s:.3f} rad")
         r["sigma_ori"] = s
