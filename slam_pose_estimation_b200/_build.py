@@ -32,13 +32,15 @@ def nvcc() -> str:
 def source_hash() -> str:
     """sha256 (first 16 hex digits) of the KERNEL sources (csrc/*.cuh; the host side of the ABI in ukf_batch.cu does not
     change what a kernel executes) the library is built from: profiles/traffic.json is stamped with it, so that ncu
-    figures of an older kernel are not reported for a newer one"""
+    figures of an older kernel are not reported for a newer one.  Comments and white space do not count."""
     import hashlib
+    import re
 
     h = hashlib.sha256()
     for d in sorted(x for x in DEPS if x.endswith(".cuh")):
-        with open(os.path.join(CSRC, d), "rb") as f:
-            h.update(d.encode() + b"\0" + f.read())
+        with open(os.path.join(CSRC, d), "r") as f:
+            code = re.sub(r"/\*.*?\*/|//[^\n]*", " ", f.read(), flags=re.S)
+        h.update(d.encode() + b"\0" + " ".join(code.split()).encode())
     return h.hexdigest()[:16]
 
 
