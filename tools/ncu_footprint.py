@@ -14,7 +14,6 @@ for r in rows[2:]:
 ex = [int(r[col["Instructions Executed"]] or 0) for r in ins]
 sm = [int(r[col["# Samples"]] or 0) for r in ins]
 ni = [int(r[col["stall_no_inst"]] or 0) if "stall_no_inst" in col else 0 for r in ins]
-print([h for h in hdr if 'no_inst' in h])
 live = sum(1 for e in ex if e > 0)
 print("static", len(ins), "executed-at-least-once", live, "=", live * 16 / 1024, "KB")
 # contiguous executed regions
