@@ -378,8 +378,9 @@ def main():
     loc = (np.arange(S) * (B // S)).astype(np.int64)
     d_mu = torch.empty((B, 13), dtype=torch.float64, device=dev)
     d_sg = torch.empty((B, 12, 12), dtype=torch.float64, device=dev)
-    if world > 1:  # NCCL sets its gather channels up on first use: not part of the transfer being timed
+    if world > 1:  # NCCL sets its channels up on first use, and for a message of this size: not part of the transfer being timed
         gather_estimates(torch.zeros((world, 13), dtype=torch.float64, device=dev)[rank:rank + 1], world)
+        gather_estimates(d_mu, world * B)  # same shapes as the timed one (contents: whatever the allocation held)
     # the host side of the gather: page-locked, allocated before the clock starts (a pageable destination is what a first
     # version of this leg timed: 0.4 s for 0.87 GB, none of it the transfer)
     host_mu = torch.empty((world * B if rank == 0 else 1, 13), dtype=torch.float64).pin_memory()
