@@ -44,11 +44,31 @@ def source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+def _content_hash() -> str:
+    """sha256 of everything the library is compiled from, and of the flags"""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def stale() -> bool:
+    """Is the library missing or built from other sources?  By content (the hash written next to the library when it was
+    built), not by time stamps: a snapshot copied to another machine keeps contents, not necessarily times.  A library
+    given through UKFB_LIB is taken as it is."""
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    if os.environ.get("UKFB_LIB"):
+        return False
+    try:
+        with open(LIB + ".srchash") as f:
+            return f.read().strip() != _content_hash()
+    except OSError:
+        t = os.path.getmtime(LIB)  # a library from before the hash file existed
+        return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
@@ -62,6 +82,9 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)
     os.replace(LIB + ".tmp", LIB)
+    if not extra:
+        with open(LIB + ".srchash", "w") as f:
+            f.write(_content_hash() + "\n")
     return LIB
 
 
