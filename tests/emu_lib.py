@@ -43,7 +43,9 @@ def load(sanitize: bool = False):
     global _LIB
     if _LIB is not None:
         return _LIB
-    out = os.path.join(_DIR, "libukfb_emu.so")
+    # UKFB_EMU_SANITIZE=1 (tools/run_emu_sanitized.sh, which also preloads libasan): the same sources under ASan + UBSan
+    sanitize = sanitize or os.environ.get("UKFB_EMU_SANITIZE") == "1"
+    out = os.path.join(_DIR, "libukfb_emu_san.so" if sanitize else "libukfb_emu.so")
     srcs = [os.path.join(_DIR, "emu_harness.cpp"), os.path.join(_DIR, "simt_emu_rt.hpp"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/ukf_device.cuh"),
             os.path.join(_DIR, "../../slam_pose_estimation_b200/csrc/so3.cuh"),
@@ -54,6 +56,9 @@ def load(sanitize: bool = False):
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", _DIR,
                "-o", out, srcs[0]]
+        if sanitize:
+            cmd[3:3] = ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+            cmd[2] = "-O1"
         subprocess.run(cmd, check=True)
     _LIB = C.CDLL(out)
     assert _LIB.emu_sizeof_params() == C.sizeof(StepParams), (_LIB.emu_sizeof_params(), C.sizeof(StepParams))
