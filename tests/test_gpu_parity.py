@@ -664,3 +664,52 @@ def test_overlapped_launches_equal_launches_in_stream_order(Ukf, filt):
             o.set_acceleration(imu[k, idx, 3:6])
             o.predict_dt(syn.DT)
     P.assert_parity(filt, (m[idx], s[idx]), o.get_state(), what="overlapped launches")
+
+
+def test_overlapped_launches_with_other_stream_work_in_between(Ukf):
+    """The same question on 128 Ki PoseUKF filters (3.5 waves: what one GPU holds of the 1 Mi batch sharded over eight), 30
+    launches, and with everything else a caller puts into the stream between two steps -- a field readback on the device,
+    a stored acceleration (its own small kernel), a status summary -- each of which is a full ordering point that the
+    overlapped launches before and after it have to respect.  Reference: eight handles of 16 Ki filters (under one wave:
+    plain stream order) given the same calls."""
+    import torch
+
+    B, H, K = 131072, 16384, 30
+    dev = torch.device("cuda", 0)
+    mu, sg = syn.pose_initial(B)
+    whole, parts = Ukf(0, B), [Ukf(0, H) for _ in range(B // H)]
+    objs = [(whole, slice(0, B))] + [(h, slice(i * H, (i + 1) * H)) for i, h in enumerate(parts)]
+    d_dt = torch.full((1,), syn.DT, dtype=torch.float64, device=dev)
+    zs = [syn.pose_measurement(8, B, k + 1)[0] for k in range(4)]
+    R = syn.pose_measurement(8, B, 1)[1]
+    acc = np.tile([0.02, -0.01, 0.03], (B, 1))
+    reads = {}
+    for x, sl in objs:
+        n = sl.stop - sl.start
+        x.initialize(mu[sl], sg[sl])
+        d_z = [torch.from_numpy(np.ascontiguousarray(z[sl])).to(dev) for z in zs]
+        d_R = torch.from_numpy(R).to(dev)
+        d_pose = torch.empty((n, 7), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        got = []
+        for k in range(K):
+            x.step_dev(d_dt, False, 8, d_z[k % 4], d_R, False)
+            if k % 7 == 3:
+                x.get_mu_range_dev(0, 7, d_pose)  # unpack kernel on the handle's stream
+                x.synchronize()
+                got.append(d_pose.cpu().numpy().copy())
+            if k == 11:
+                x.set_acceleration(acc[sl], np.eye(3) * 1e-4)  # host-pointer call: copy + store kernel; the next predicts use it
+            if k == 20:
+                got.append(np.array(x.status_summary()))
+        x.synchronize()
+        reads[sl.start, n] = got
+    assert whole.overlapped_launch_count() == K and parts[0].overlapped_launch_count() == 0
+    m, s = whole.get_state()
+    for h, (_, sl) in zip(parts, objs[1:]):
+        mh, sh = h.get_state()
+        assert np.array_equal(m[sl], mh) and np.array_equal(s[sl], sh)
+        for a, b in zip(reads[0, B], reads[sl.start, H]):
+            if a.ndim == 2:
+                assert np.array_equal(a[sl], b), "a readback between two overlapped launches saw another state"
+    assert not whole.get_status().any()
