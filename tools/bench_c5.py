@@ -65,6 +65,23 @@ def main():
             f.synchronize()
             t_dev.append(f.event_elapsed_ms(0, 1))
         ms = float(np.median(t_dev))
+        # the same as a STREAM of windows, as a host that keeps the queues coming makes them: the timestamp arrays of the
+        # next windows are on the device beforehand, so nothing but the launches is in the stream (consecutive launches
+        # of a handle of a few waves then overlap at their ends: ukfb_overlapped_launch_count)
+        nstream = 5
+        with torch.cuda.stream(stream):
+            d_ts_next = [d_ts + i * period for i in range(nstream)]
+        f.synchronize()
+        f.event_record(2)
+        for i in range(nstream):
+            f.run_events_dev(K, d_ts_next[i], d_kinds, d_mu3, d_tab, per_event=False)
+        f.event_record(3)
+        f.synchronize()
+        ms_stream = f.event_elapsed_ms(2, 3) / nstream
+        with torch.cuda.stream(stream):
+            d_ts.add_(nstream * period)
+        del d_ts_next
+        f.synchronize()
         flagged, bits = f.status_summary()
         # end to end: host queues in, estimates out.  Blocking calls, then the streaming ones (the next window's queues are
         # copied while the current window is integrated; estimates leave on the copy-out stream).  Two host copies of the
@@ -103,6 +120,8 @@ def main():
             "filters": B, "ticks_per_launch": ticks, "slots_per_launch": K, "samples_per_launch": live,
             "launch_ms": ms, "samples_per_s": live / ms * 1e3, "filter_ticks_per_s": B * ticks / ms * 1e3,
             "us_per_sample_per_filter": ms * 1e3 / K,
+            "stream_of_launches_ms": ms_stream, "stream_samples_per_s": live / ms_stream * 1e3,
+            "launches_overlapped": f.overlapped_launch_count() > 0,
             "e2e_ms": ms_e2e, "e2e_samples_per_s": live / ms_e2e * 1e3, "e2e_api": "ukfb_run_events_async + ukfb_get_state_async, pinned host arrays",
             "e2e_blocking_ms": ms_blk, "e2e_blocking_samples_per_s": live / ms_blk * 1e3,
             "e2e_h2d_bytes": int(ts_h[0].nbytes + kinds_h.nbytes + mu3_h.nbytes + tab.nbytes), "e2e_d2h_bytes": int(out[0].nbytes),
