@@ -116,3 +116,28 @@ int main(void) {
         assert out[1].split() == ["12", "13"]
     else:
         assert "CUDA" in out[1] or "device" in out[1]
+
+
+def test_library_staleness_is_by_content_not_by_time():
+    """The built library travels with a snapshot of the tree (the GPU box, the round-end run): a copy keeps contents, not
+    necessarily time stamps, and must not trigger a rebuild -- nor may a changed source go unnoticed."""
+    import os
+
+    from slam_pose_estimation_b200 import _build
+
+    if os.environ.get("UKFB_LIB"):
+        pytest.skip("a library chosen through UKFB_LIB is taken as it is")
+    _build.build()
+    assert not _build.stale()
+    dep = os.path.join(_build.CSRC, "so3.cuh")
+    st = os.stat(dep)
+    try:
+        os.utime(dep, (st.st_atime, os.path.getmtime(_build.LIB) + 3600.0))  # "newer" than the library, same content
+        assert not _build.stale()
+        saved = open(_build.LIB + ".srchash").read()
+        open(_build.LIB + ".srchash", "w").write("0" * 64 + "\n")  # as if a source had changed since the build
+        assert _build.stale()
+        open(_build.LIB + ".srchash", "w").write(saved)
+        assert not _build.stale()
+    finally:
+        os.utime(dep, (st.st_atime, st.st_mtime))
