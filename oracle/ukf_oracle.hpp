@@ -6,13 +6,19 @@
  * of its un-vendored dependency `slam/mtk` (ukfom::ukf<>, MTK::SO3, MTK::vect;
  * no version is pinned by the reference: manifest.xml:13, src/CMakeLists.txt:25).
  *
- *   PARITY UNPINNED: the reference holds no test, golden vector or fixture for
- *   any UKF quantity (test/CMakeLists.txt:1-4 builds only the GDAL projection
- *   test; test/test_models.cpp:1-10 is a dead stub) and the reference cannot be
- *   built here (Rock CMake macros, Eigen, Boost, base-types, GDAL, LAPACK and
- *   slam/mtk are all absent).  This oracle is therefore pinned only by
- *   (i) analytic known-answer tests and (ii) an independent NumPy/LAPACK
- *   restatement (oracle/numpy_ukf.py); see tests/test_oracle_*.py.
+ *   PARITY PARTLY PINNED.  The reference holds no test, golden vector or fixture
+ *   for any UKF quantity (test/CMakeLists.txt:1-4 builds only the GDAL projection
+ *   test; test/test_models.cpp:1-10 is a dead stub) and its own build cannot run
+ *   here (Rock CMake macros, Eigen, Boost, base-types, GDAL, LAPACK and slam/mtk
+ *   are all absent).  What is pinned: the WRAPPER layers (models, process-noise
+ *   shaping with its quirks, time guards and latches) -- oracle/_ref compiles the
+ *   reference's own PoseUKF.cpp, OrientationUKF.cpp and UnscentedKalmanFilter.hpp
+ *   unmodified against stand-in headers (oracle/ref_shim, oracle/ref_recipe.mk)
+ *   and this oracle equals it bit for bit (tests/test_ref_pin.py).  What stays
+ *   UNPINNED: the ukfom / MTK engine underneath (sigma points, manifold mean and
+ *   its tolerance, update / apply_delta, SO(3) conventions), which the reference
+ *   does not vendor: pinned only by (i) analytic known-answer tests and (ii) an
+ *   independent NumPy/LAPACK restatement (oracle/numpy_ukf.py); tests/test_oracle.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may include, link or execute this code.  The product
